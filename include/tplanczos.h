@@ -1,0 +1,194 @@
+/* =====================================================================================
+ * tplanczos.h -- C ABI of the B200-native two-pass Lanczos engine (libtplanczos.so).
+ *
+ * This is the drop-in boundary for the reference's hot path (lukefleed/two-pass-lanczos).
+ * The reference has no FFI: its boundary is the generic Rust surface
+ *     solvers::lanczos / solvers::lanczos_two_pass          src/solvers.rs:46-58, 133-145
+ *     algorithms::lanczos::lanczos_standard                 src/algorithms/lanczos.rs:55-61
+ *     algorithms::lanczos_two_pass::lanczos_pass_one        src/algorithms/lanczos_two_pass.rs:65-70
+ *     algorithms::lanczos_two_pass::lanczos_pass_two[_with_basis]   :128-134, :149-155
+ *     utils::data_loader::load_kkt_system                   src/utils/data_loader.rs:211-214
+ * over faer's `LinOp<f64>` operator trait.  Each entry point below states which of those it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` block + safe wrappers a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the boundary; every function returns a
+ *     tpl_status (0 = OK) and leaves a human-readable message in tpl_last_error_message()
+ *     (thread-local).  Messages equal the reference's `Display` strings (src/error.rs:23-57,
+ *     src/utils/data_loader.rs:18-42).
+ *   - vectors b, x, y, V may live in host memory OR in device memory of the operator's GPU
+ *     (detected with cudaPointerGetAttributes); alphas/betas/steps/b_norm are host outputs.
+ *   - all arithmetic is f64.  A handle is not thread-safe; distinct handles are independent.
+ *   - breakdown (beta <= 1000*eps) is NOT an error: it shortens steps_taken (mod.rs:206-211).
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point returns
+ *     TPL_ERR_CUDA.
+ * ===================================================================================== */
+#ifndef TPLANCZOS_H
+#define TPLANCZOS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tpl_status {
+  TPL_OK = 0,
+  /* LanczosErrorKind, declaration order of src/error.rs:20-58 */
+  TPL_ERR_BREAKDOWN = 1,          /* never produced (as in the reference) */
+  TPL_ERR_DIMENSION_MISMATCH = 2, /* never produced by the reference; here: b/operator size misuse */
+  TPL_ERR_INPUT = 3,              /* InputError(String): zero vector b */
+  TPL_ERR_PARAMETER_MISMATCH = 4, /* ParameterMismatch{param_name, expected, actual} */
+  TPL_ERR_EVD = 5,                /* tpl_ftk_exp did not converge */
+  TPL_ERR_SOLVER = 6,             /* SolverError: the f(T_k) callback failed */
+  TPL_ERR_PANIC = 7,              /* inputs on which the reference panics (k == 0, null pointers) */
+  /* DataLoaderError, declaration order of src/utils/data_loader.rs:16-43 */
+  TPL_ERR_IO = 101,
+  TPL_ERR_PARSE_INT = 102,
+  TPL_ERR_PARSE_FLOAT = 103,
+  TPL_ERR_PROBLEM_LINE_MISSING = 104,
+  TPL_ERR_UNEXPECTED_EOF = 105,
+  TPL_ERR_ARC_COUNT_MISMATCH = 106,
+  TPL_ERR_SPARSE_CONSTRUCTION = 107,
+  TPL_ERR_INVALID_NODE_INDEX = 108,
+  TPL_ERR_MALFORMED_ARC_LINE = 109, /* reference panics: `a` line with < 3 tokens (data_loader.rs:118-119) */
+  /* device layer */
+  TPL_ERR_CUDA = 200,
+  TPL_ERR_COMM = 201
+} tpl_status;
+
+const char* tpl_last_error_message(void);
+const char* tpl_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * KKT loader  --  replaces utils::data_loader::load_kkt_system + KKTSystem
+ * (src/utils/data_loader.rs:51-58, 68-259).  Host-side C++; keeps the reference's line
+ * semantics verbatim, including the `.qfc` "skip m lines, take <= m lines" rule that yields a
+ * SHORT or EMPTY D block on files written by qfcgen (data_loader.rs:172-195).
+ * ------------------------------------------------------------------------------------ */
+typedef struct tpl_kkt tpl_kkt;
+
+int tpl_load_kkt(const char* dmx_path, const char* qfc_path, tpl_kkt** out);
+void tpl_kkt_free(tpl_kkt* kkt);
+size_t tpl_kkt_num_nodes(const tpl_kkt* kkt); /* KKTSystem.num_nodes */
+size_t tpl_kkt_num_arcs(const tpl_kkt* kkt);  /* KKTSystem.num_arcs  */
+size_t tpl_kkt_num_costs(const tpl_kkt* kkt); /* how many quadratic costs the .qfc really gave (<= arcs) */
+size_t tpl_kkt_nnz(const tpl_kkt* kkt);
+/* KKTSystem.a as faer holds it: CSC, n = nodes + arcs, 8-byte indices, rows ascending per column.
+ * Pointers are owned by the handle. */
+int tpl_kkt_csc(const tpl_kkt* kkt, size_t* n, size_t* nnz, const uint64_t** colptr,
+                const uint64_t** rowidx, const double** val);
+/* Incidence view (arc j: +1 at tail, -1 at head, 0-based node ids).  *regular is 1 when every `a` line
+ * was a plain arc between two distinct nodes and the arc count matches the `p` line, i.e. when the
+ * incidence operator below represents KKTSystem.a exactly. */
+int tpl_kkt_incidence(const tpl_kkt* kkt, const uint32_t** tail, const uint32_t** head,
+                      const double** d, size_t* d_len, int* regular);
+
+/* ------------------------------------------------------------------------------------
+ * Operators  --  the device-resident stand-in for `&impl faer::matrix_free::LinOp<f64>`
+ * (src/solvers.rs:56, src/algorithms/mod.rs:167).  Construction uploads the matrix to HBM and builds
+ * the kernel-side format; the handle also owns the solver workspace and its CUDA stream.
+ * ------------------------------------------------------------------------------------ */
+typedef struct tpl_op tpl_op;
+
+/* Generic symmetric sparse operator from a host CSC exactly as SparseColMat<usize,f64> stores it
+ * (what `&a.as_ref()` is at src/bin/tradeoff.rs:268).  device < 0: current device. */
+int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, const double* val,
+                    int device, tpl_op** out);
+/* Network-incidence form of A = [[D, E^T], [E, 0]]: reads arc tail/head instead of stored +-1.
+ * d_len <= m honours the loader's short-D quirk (rows >= d_len have no diagonal entry). */
+int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d,
+                    size_t d_len, int device, tpl_op** out);
+/* Convenience: operator for a loaded KKTSystem.  format: 0 = auto (incidence when regular, else CSR),
+ * 1 = generic CSR, 2 = incidence (error if not regular). */
+int tpl_op_from_kkt_system(const tpl_kkt* kkt, int format, int device, tpl_op** out);
+void tpl_op_free(tpl_op* op);
+size_t tpl_op_nrows(const tpl_op* op); /* LinOp::nrows == ncols */
+int tpl_op_format(const tpl_op* op);   /* 1 = CSR, 2 = incidence */
+int tpl_op_device(const tpl_op* op);
+/* LinOp::apply: y = A x (used by the reference's property tests, mod.rs:510). */
+int tpl_op_apply(tpl_op* op, const double* x, double* y);
+/* Use an externally owned CUDA stream (a cudaStream_t passed as void*) instead of the handle's own. */
+int tpl_op_set_stream(tpl_op* op, void* cuda_stream);
+/* Device time (ms, CUDA events on the operator's stream) of the last pass-one / pass-two / standard /
+ * gemv launched through this handle, and the number of kernels this library launched so far. */
+int tpl_op_last_timing(const tpl_op* op, double* pass_one_ms, double* pass_two_ms, double* gemv_ms);
+uint64_t tpl_op_kernel_launches(const tpl_op* op);
+/* Algorithmic bytes per SpMV of the kernel-side format (B_csr = 12 nnz + 4(n+1),
+ * B_inc = 24 m + 4 p) and bytes of HBM the handle currently holds. */
+uint64_t tpl_op_matrix_bytes(const tpl_op* op);
+uint64_t tpl_op_device_bytes(const tpl_op* op);
+/* Execution mode: 0 = persistent cooperative kernels (default), 1 = one cooperative launch per
+ * Lanczos step (same kernels, same arithmetic; used when a step callback is installed). */
+int tpl_op_set_mode(tpl_op* op, int mode);
+
+/* ------------------------------------------------------------------------------------
+ * algorithms::*  building blocks
+ * ------------------------------------------------------------------------------------ */
+
+/* lanczos_pass_one (src/algorithms/lanczos_two_pass.rs:65-110).
+ * alphas: capacity k, betas: capacity k-1 (may be NULL when k == 1).
+ * On return *steps == alphas.len(), betas.len() == *steps - 1, *b_norm == ||b||_2.
+ * k == 0 -> TPL_ERR_PANIC (the reference panics in Vec::with_capacity(k-1)). */
+int tpl_pass_one(tpl_op* op, const double* b, size_t k, double* alphas, double* betas, size_t* steps,
+                 double* b_norm);
+
+/* lanczos_pass_two / lanczos_pass_two_with_basis (lanczos_two_pass.rs:128-166, 206-312).
+ * y has y_len entries (must equal steps, else ParameterMismatch{"y_k"}).  x: n outputs.
+ * V: NULL, or an n x steps column-major buffer with leading dimension ldv >= n that receives the
+ * regenerated basis V'_k (the `_with_basis` variant). */
+int tpl_pass_two(tpl_op* op, const double* b, const double* alphas, const double* betas, size_t steps,
+                 double b_norm, const double* y, size_t y_len, double* x, double* V, size_t ldv);
+
+/* LanczosCallback (src/algorithms/mod.rs:82-86): called after each step with the step count, the
+ * n x steps basis so far (DEVICE pointer, column-major, leading dimension ld), and the T_k view
+ * (alphas[steps], betas[steps-1], host).  Return non-zero to continue, 0 to stop. */
+typedef int (*tpl_step_callback)(size_t steps, const double* v_dev, size_t ld, const double* alphas,
+                                 const double* betas, void* user);
+
+/* lanczos_standard (src/algorithms/lanczos.rs:55-156).  V: n x k column-major, ldv >= n, host or
+ * device; columns >= *steps are zero (the reference trims them, lanczos.rs:135-145). */
+int tpl_standard(tpl_op* op, const double* b, size_t k, double* V, size_t ldv, double* alphas,
+                 double* betas, size_t* steps, double* b_norm, tpl_step_callback cb, void* user);
+
+/* ------------------------------------------------------------------------------------
+ * solvers::*  (src/solvers.rs)
+ * f_tk_solver closure: F: FnMut(&[R], &[R]) -> Result<Mat<T>, anyhow::Error>  (solvers.rs:58).
+ * The callback writes y' into y (capacity *y_len == na on entry) and sets *y_len to the number of
+ * rows it produced; a non-zero return becomes SolverError, *y_len != steps becomes
+ * ParameterMismatch{"y_k_prime"} (solvers.rs:71-87, 155-165).
+ * ------------------------------------------------------------------------------------ */
+typedef int (*tpl_ftk_solver)(const double* alphas, size_t na, const double* betas, size_t nb, double* y,
+                              size_t* y_len, void* user);
+
+int tpl_lanczos(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f_tk, void* user, double* x);
+int tpl_lanczos_two_pass(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f_tk, void* user,
+                         double* x);
+
+/* Host f(T_k) e1 solvers with the tpl_ftk_solver signature (the closures the reference's benches
+ * and tests define): inverse via tridiagonal partial-pivot LU (src/bin/tradeoff.rs:245-258),
+ * exponential via symmetric tridiagonal EVD (src/bin/stability.rs:175-193), square = T*T*e1
+ * (tests/correctness.rs:290-299).  `user` is ignored. */
+int tpl_ftk_inv(const double* alphas, size_t na, const double* betas, size_t nb, double* y, size_t* y_len,
+                void* user);
+int tpl_ftk_exp(const double* alphas, size_t na, const double* betas, size_t nb, double* y, size_t* y_len,
+                void* user);
+int tpl_ftk_square(const double* alphas, size_t na, const double* betas, size_t nb, double* y,
+                   size_t* y_len, void* user);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU (arc-partitioned KKT operator): rank r of `world` owns arcs
+ * [arc_begin, arc_end) and a replica of the p node rows.  The communicator is NCCL; the caller
+ * supplies the 128-byte ncclUniqueId made by rank 0 (tpl_comm_unique_id) through its own
+ * rendezvous (torch.distributed in bench.py).
+ * ------------------------------------------------------------------------------------ */
+int tpl_comm_unique_id(uint8_t id_out[128]);
+int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end, const uint32_t* tail,
+                            const uint32_t* head, const double* d, size_t d_len, int device, int rank,
+                            int world, const uint8_t nccl_id[128], tpl_op** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPLANCZOS_H */

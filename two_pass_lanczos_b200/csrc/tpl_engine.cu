@@ -1,0 +1,862 @@
+// tpl_engine.cu -- host driver + C ABI of the B200-native two-pass Lanczos engine (component H1).
+//
+// Mirrors the control flow of the reference's src/solvers.rs and src/algorithms/{lanczos,lanczos_two_pass}.rs
+// around the persistent kernels of tpl_kernels.cuh.  No CPU fallback: every compute entry point needs a
+// CUDA device and fails with TPL_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tpl_internal.h"
+#include "tpl_kernels.cuh"
+
+// ============================================================================ errors
+namespace tpl {
+static thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+void clear_error() { g_err.clear(); }
+int fail_parameter_mismatch(const char* param_name, size_t expected, size_t actual) {
+  // src/error.rs:40 "Parameter mismatch: `{param_name}` expects size {expected}, but got {actual}."
+  return fail(TPL_ERR_PARAMETER_MISMATCH, "Parameter mismatch: `%s` expects size %zu, but got %zu.", param_name,
+              expected, actual);
+}
+int fail_input(const char* msg) { return fail(TPL_ERR_INPUT, "Invalid input parameter: %s", msg); }  // error.rs:37
+int fail_solver(const char* msg) {
+  return fail(TPL_ERR_SOLVER, "The user-provided f(T_k) solver failed: %s", msg);  // error.rs:50
+}
+}  // namespace tpl
+
+using tpl::fail;
+
+#define CUDA_TRY(expr)                                                                                \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(TPL_ERR_CUDA, "CUDA error: %s (%s) at %s:%d", cudaGetErrorString(e_), #expr, __FILE__, \
+                  __LINE__);                                                                          \
+  } while (0)
+
+extern "C" const char* tpl_last_error_message(void) { return tpl::g_err.c_str(); }
+extern "C" const char* tpl_version(void) { return "tplanczos 0.1 (sm_100a)"; }
+
+// ============================================================================ handle
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+constexpr size_t kHeaderDoubles = 8;  // State (48 B) padded to 64 B in the coefficient block
+
+}  // namespace
+
+struct tpl_op {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int format = 0;  // 1 = CSR, 2 = incidence
+  uint32_t n = 0;
+  int G = 0;  // CTAs of the persistent grid (= SM count)
+  tpl::IncidenceOp inc{};
+  tpl::CsrOp csr{};
+  std::vector<std::pair<void*, size_t>> allocs;
+  size_t device_bytes = 0;
+  uint64_t matrix_bytes = 0;
+  size_t smem_bytes = 0;
+  // workspace
+  double* buf[3] = {nullptr, nullptr, nullptr};
+  double* b_d = nullptr;
+  double* x_d = nullptr;
+  double* coef_d = nullptr;  // [header | alphas cap | betas cap | y cap]
+  size_t coef_cap = 0;
+  unsigned int* flags = nullptr;
+  double* partials = nullptr;
+  double* h_pin = nullptr;  // pinned mirror of coef_d
+  double* V_int = nullptr;
+  size_t V_int_elems = 0;
+  cudaEvent_t ev[6] = {};
+  bool timed[3] = {false, false, false};
+  uint64_t launches = 0;
+  int mode = 0;
+
+  tpl::State* st_d() const { return reinterpret_cast<tpl::State*>(coef_d); }
+  double* alphas_d() const { return coef_d + kHeaderDoubles; }
+  double* betas_d() const { return coef_d + kHeaderDoubles + coef_cap; }
+  double* y_d() const { return coef_d + kHeaderDoubles + 2 * coef_cap; }
+  tpl::GridSync gs() const { return tpl::GridSync{flags, partials}; }
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(tpl_op* op, T** out, size_t count) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  op->allocs.emplace_back(p, bytes);
+  op->device_bytes += bytes;
+  *out = static_cast<T*>(p);
+  return TPL_OK;
+}
+template <class T>
+int dev_upload(tpl_op* op, const T** out, const std::vector<T>& host) {
+  T* p = nullptr;
+  if (int rc = dev_alloc(op, &p, host.size())) return rc;
+  if (!host.empty()) CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = p;
+  return TPL_OK;
+}
+int dev_free(tpl_op* op, void* p) {
+  if (!p) return TPL_OK;
+  auto it = std::find_if(op->allocs.begin(), op->allocs.end(), [p](const std::pair<void*, size_t>& a) { return a.first == p; });
+  if (it != op->allocs.end()) {
+    op->device_bytes -= it->second;
+    op->allocs.erase(it);
+  }
+  CUDA_TRY(cudaFree(p));
+  return TPL_OK;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------- long-row (segment) format
+struct HostLongRows {
+  std::vector<uint32_t> row, seg_ptr, ent_ptr, ent_idx, cta_ptr;
+  std::vector<double> ent_val;
+  uint32_t max_segs = 0;
+};
+
+// row_ent[q]..row_ent[q+1] is the entry range of long row q inside ent_idx/ent_val (already filled).
+void build_segments(HostLongRows& h, const std::vector<uint64_t>& row_ent, int G) {
+  const size_t nlong = h.row.size();
+  uint64_t L = 256;
+  for (;;) {
+    uint64_t segs = 0;
+    for (size_t q = 0; q < nlong; ++q) segs += (row_ent[q + 1] - row_ent[q] + L - 1) / L;
+    if (segs <= (uint64_t)G * 3072) break;
+    L *= 2;
+  }
+  h.seg_ptr.assign(nlong + 1, 0);
+  h.ent_ptr.clear();
+  for (size_t q = 0; q < nlong; ++q) {
+    h.seg_ptr[q] = (uint32_t)h.ent_ptr.size();
+    for (uint64_t e = row_ent[q]; e < row_ent[q + 1]; e += L) h.ent_ptr.push_back((uint32_t)e);
+  }
+  h.seg_ptr[nlong] = (uint32_t)h.ent_ptr.size();
+  h.ent_ptr.push_back((uint32_t)row_ent[nlong]);
+  // Fix segment ends: a segment ends where the next one starts, except the last of a row which ends at
+  // the row end.  Because rows are stored back to back, ent_ptr[s+1] is correct in both cases.
+  const uint32_t nseg = h.seg_ptr[nlong];
+  const uint32_t target = std::max<uint32_t>(1, (nseg + G - 1) / G);
+  h.cta_ptr.assign(G + 1, 0);
+  for (int c = 0; c <= G; ++c) {
+    const uint64_t want = (uint64_t)c * target;
+    size_t q = std::lower_bound(h.seg_ptr.begin(), h.seg_ptr.begin() + nlong, want,
+                                [](uint32_t a, uint64_t b) { return (uint64_t)a < b; }) -
+               h.seg_ptr.begin();
+    h.cta_ptr[c] = (uint32_t)q;
+  }
+  h.cta_ptr[0] = 0;
+  h.cta_ptr[G] = (uint32_t)nlong;
+  // rows without segments at the tail must still be owned: spread every row, by count, if there are no segments
+  if (nseg == 0)
+    for (int c = 0; c <= G; ++c) h.cta_ptr[c] = (uint32_t)std::min<uint64_t>(nlong, ((uint64_t)nlong * c + G - 1) / G);
+  h.max_segs = 0;
+  for (int c = 0; c < G; ++c)
+    h.max_segs = std::max(h.max_segs, h.seg_ptr[h.cta_ptr[c + 1]] - h.seg_ptr[h.cta_ptr[c]]);
+}
+
+int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
+  d.nlong = (uint32_t)h.row.size();
+  d.max_segs = h.max_segs;
+  if (int rc = dev_upload(op, &d.row, h.row)) return rc;
+  if (int rc = dev_upload(op, &d.seg_ptr, h.seg_ptr)) return rc;
+  if (int rc = dev_upload(op, &d.ent_ptr, h.ent_ptr)) return rc;
+  if (int rc = dev_upload(op, &d.ent_idx, h.ent_idx)) return rc;
+  if (int rc = dev_upload(op, &d.cta_ptr, h.cta_ptr)) return rc;
+  d.ent_val = nullptr;
+  if (!h.ent_val.empty())
+    if (int rc = dev_upload(op, &d.ent_val, h.ent_val)) return rc;
+  return TPL_OK;
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return TPL_OK;
+}
+
+int open_device(tpl_op* op, int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(TPL_ERR_CUDA, "CUDA error: no usable CUDA device (%s); libtplanczos has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= count) return fail(TPL_ERR_CUDA, "CUDA error: device %d out of range (%d devices)", device, count);
+  op->device = device;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (!prop.cooperativeLaunch) return fail(TPL_ERR_CUDA, "CUDA error: device lacks cooperative launch");
+  op->G = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
+  for (auto& ev : op->ev) CUDA_TRY(cudaEventCreate(&ev));
+  return TPL_OK;
+}
+
+int ensure_coef(tpl_op* op, size_t k) {
+  if (k <= op->coef_cap && op->coef_d) return TPL_OK;
+  size_t cap = std::max<size_t>(k, 64);
+  if (op->coef_d) {
+    if (int rc = dev_free(op, op->coef_d)) return rc;
+    op->coef_d = nullptr;
+  }
+  if (op->h_pin) {
+    cudaFreeHost(op->h_pin);
+    op->h_pin = nullptr;
+  }
+  const size_t doubles = kHeaderDoubles + 3 * cap;
+  if (int rc = dev_alloc(op, &op->coef_d, doubles)) return rc;
+  CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&op->h_pin), doubles * sizeof(double)));
+  op->coef_cap = cap;
+  return TPL_OK;
+}
+
+int finish_setup(tpl_op* op) {
+  const size_t n = op->n;
+  for (auto& b : op->buf)
+    if (int rc = dev_alloc(op, &b, n)) return rc;
+  if (int rc = dev_alloc(op, &op->b_d, n)) return rc;
+  if (int rc = dev_alloc(op, &op->x_d, n)) return rc;
+  if (int rc = dev_alloc(op, &op->flags, (size_t)op->G)) return rc;
+  if (int rc = dev_alloc(op, &op->partials, 2 * (size_t)op->G)) return rc;
+  CUDA_TRY(cudaMemset(op->flags, 0, sizeof(unsigned int) * op->G));
+  if (int rc = ensure_coef(op, 1024)) return rc;
+  // opt in to the dynamic shared memory the kernels need and check the grid is co-resident
+  const size_t smem = op->smem_bytes;
+  int per_sm = 0;
+  if (op->format == 2) {
+    if (int rc = set_smem(tpl::pass1_kernel<tpl::IncidenceOp, false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass1_kernel<tpl::IncidenceOp, true>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_kernel<tpl::IncidenceOp, false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_kernel<tpl::IncidenceOp, true>, smem)) return rc;
+    if (int rc = set_smem(tpl::apply_kernel<tpl::IncidenceOp>, smem)) return rc;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_kernel<tpl::IncidenceOp, true>,
+                                                           tpl::kBlock, smem));
+  } else {
+    if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, true>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_kernel<tpl::CsrOp, false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_kernel<tpl::CsrOp, true>, smem)) return rc;
+    if (int rc = set_smem(tpl::apply_kernel<tpl::CsrOp>, smem)) return rc;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_kernel<tpl::CsrOp, true>,
+                                                           tpl::kBlock, smem));
+  }
+  if (per_sm < 1) return fail(TPL_ERR_CUDA, "CUDA error: persistent kernel does not fit on an SM (smem %zu B)", smem);
+  return TPL_OK;
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+}  // namespace
+
+// ============================================================================ operator construction
+extern "C" {
+
+void tpl_op_free(tpl_op* op) {
+  if (!op) return;
+  DeviceGuard g(op->device);
+  if (op->stream) cudaStreamSynchronize(op->stream);
+  for (auto& a : op->allocs) cudaFree(a.first);
+  if (op->h_pin) cudaFreeHost(op->h_pin);
+  for (auto& ev : op->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (op->own_stream && op->stream) cudaStreamDestroy(op->stream);
+  delete op;
+}
+
+int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, const double* val, int device,
+                    tpl_op** out) {
+  tpl::clear_error();
+  if (!colptr || !out || (n && colptr[n] && (!rowidx || !val))) return fail(TPL_ERR_PANIC, "null argument");
+  const uint64_t nnz = colptr[n];
+  if (n == 0 || n >= 0x7fffffffull || nnz >= 0xffffffffull)
+    return fail(TPL_ERR_DIMENSION_MISMATCH, "Dimension mismatch: operator has %zu columns but vector has %zu rows.", n, n);
+  for (size_t j = 0; j < n; ++j)
+    if (colptr[j] > colptr[j + 1])
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  for (uint64_t q = 0; q < nnz; ++q)
+    if (rowidx[q] >= n)
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  tpl_op* op = new tpl_op;
+  int rc = open_device(op, device);
+  if (rc) {
+    delete op;
+    return rc;
+  }
+  op->format = 1;
+  op->n = (uint32_t)n;
+  // CSC -> CSR (column indices ascending within every row, i.e. the reference's accumulation order)
+  std::vector<uint32_t> row_ptr(n + 1, 0), col(nnz);
+  std::vector<double> v(nnz);
+  for (uint64_t q = 0; q < nnz; ++q) ++row_ptr[rowidx[q] + 1];
+  for (size_t i = 0; i < n; ++i) row_ptr[i + 1] += row_ptr[i];
+  {
+    std::vector<uint32_t> fill(row_ptr.begin(), row_ptr.end() - 1);
+    for (size_t j = 0; j < n; ++j)
+      for (uint64_t q = colptr[j]; q < colptr[j + 1]; ++q) {
+        const uint32_t dst = fill[rowidx[q]]++;
+        col[dst] = (uint32_t)j;
+        v[dst] = val[q];
+      }
+  }
+  const uint32_t long_thresh = 96;
+  HostLongRows h;
+  std::vector<uint64_t> row_ent{0};
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t len = row_ptr[i + 1] - row_ptr[i];
+    if (len > long_thresh) {
+      h.row.push_back((uint32_t)i);
+      h.ent_idx.insert(h.ent_idx.end(), col.begin() + row_ptr[i], col.begin() + row_ptr[i + 1]);
+      h.ent_val.insert(h.ent_val.end(), v.begin() + row_ptr[i], v.begin() + row_ptr[i + 1]);
+      row_ent.push_back(h.ent_idx.size());
+    }
+  }
+  build_segments(h, row_ent, op->G);
+  op->csr.n = (uint32_t)n;
+  op->csr.long_thresh = long_thresh;
+  rc = dev_upload(op, &op->csr.row_ptr, row_ptr);
+  if (!rc) rc = dev_upload(op, &op->csr.col, col);
+  if (!rc) rc = dev_upload(op, &op->csr.val, v);
+  if (!rc) rc = upload_long_rows(op, h, op->csr.lr);
+  op->matrix_bytes = 12ull * nnz + 4ull * (n + 1);
+  op->smem_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
+  if (!rc) rc = finish_setup(op);
+  if (rc) {
+    std::string keep = tpl::g_err;
+    tpl_op_free(op);
+    tpl::g_err = keep;
+    return rc;
+  }
+  *out = op;
+  return TPL_OK;
+}
+
+int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len,
+                    int device, tpl_op** out) {
+  tpl::clear_error();
+  if (!out || (m && (!tail || !head)) || (d_len && !d)) return fail(TPL_ERR_PANIC, "null argument");
+  if (d_len > m) return fail(TPL_ERR_PARAMETER_MISMATCH, "Parameter mismatch: `d` expects size %zu, but got %zu.", m, d_len);
+  const size_t n = m + p;
+  if (n == 0 || n >= 0x7fffffffull)
+    return fail(TPL_ERR_DIMENSION_MISMATCH, "Dimension mismatch: operator has %zu columns but vector has %zu rows.", n, n);
+  for (size_t j = 0; j < m; ++j)
+    if (tail[j] >= p || head[j] >= p)
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  tpl_op* op = new tpl_op;
+  int rc = open_device(op, device);
+  if (rc) {
+    delete op;
+    return rc;
+  }
+  op->format = 2;
+  op->n = (uint32_t)n;
+  // node -> arc lists, ascending arc index inside each node (tail: +x_j, head: -x_j; self-loops cancel)
+  HostLongRows h;
+  std::vector<uint64_t> row_ent(p + 1, 0);
+  for (size_t j = 0; j < m; ++j)
+    if (tail[j] != head[j]) {
+      ++row_ent[tail[j] + 1];
+      ++row_ent[head[j] + 1];
+    }
+  for (size_t u = 0; u < p; ++u) row_ent[u + 1] += row_ent[u];
+  h.ent_idx.resize(row_ent[p]);
+  {
+    std::vector<uint64_t> fill(row_ent.begin(), row_ent.end() - 1);
+    for (size_t j = 0; j < m; ++j)
+      if (tail[j] != head[j]) {
+        h.ent_idx[fill[tail[j]]++] = (uint32_t)j;
+        h.ent_idx[fill[head[j]]++] = (uint32_t)j | tpl::kSignBit;
+      }
+  }
+  h.row.resize(p);
+  for (size_t u = 0; u < p; ++u) h.row[u] = (uint32_t)(m + u);
+  build_segments(h, row_ent, op->G);
+  std::vector<double> dd(m, 0.0);
+  if (d_len) std::memcpy(dd.data(), d, d_len * sizeof(double));
+  std::vector<uint32_t> t(tail, tail + m), hd(head, head + m);
+  op->inc.m = (uint32_t)m;
+  op->inc.p = (uint32_t)p;
+  rc = dev_upload(op, &op->inc.d, dd);
+  if (!rc) rc = dev_upload(op, &op->inc.tail, t);
+  if (!rc) rc = dev_upload(op, &op->inc.head, hd);
+  if (!rc) rc = upload_long_rows(op, h, op->inc.lr);
+  const size_t seg_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
+  op->inc.stage_nodes = (p * sizeof(double) + seg_bytes <= kSmemBudget) ? 1 : 0;
+  op->smem_bytes = seg_bytes + (op->inc.stage_nodes ? p * sizeof(double) : 0);
+  op->matrix_bytes = 24ull * m + 4ull * p;  // (d, tail, head) + node->arc lists + list pointers
+  if (!rc) rc = finish_setup(op);
+  if (rc) {
+    std::string keep = tpl::g_err;
+    tpl_op_free(op);
+    tpl::g_err = keep;
+    return rc;
+  }
+  *out = op;
+  return TPL_OK;
+}
+
+int tpl_op_from_kkt_system(const tpl_kkt* kkt, int format, int device, tpl_op** out) {
+  tpl::clear_error();
+  if (!kkt || !out) return fail(TPL_ERR_PANIC, "null argument");
+  if (format == 2 && !kkt->regular)
+    return fail(TPL_ERR_SPARSE_CONSTRUCTION,
+                "Internal error: the instance is not a plain arc list; use the generic CSR operator.");
+  if (format == 2 || (format == 0 && kkt->regular))
+    return tpl_op_from_kkt(kkt->num_arcs, kkt->num_nodes, kkt->tail.data(), kkt->head.data(), kkt->d.data(),
+                           kkt->costs.size(), device, out);
+  return tpl_op_from_csc(kkt->num_arcs + kkt->num_nodes, kkt->colptr.data(), kkt->rowidx.data(), kkt->val.data(),
+                         device, out);
+}
+
+size_t tpl_op_nrows(const tpl_op* op) { return op ? op->n : 0; }
+int tpl_op_format(const tpl_op* op) { return op ? op->format : 0; }
+int tpl_op_device(const tpl_op* op) { return op ? op->device : -1; }
+uint64_t tpl_op_kernel_launches(const tpl_op* op) { return op ? op->launches : 0; }
+uint64_t tpl_op_matrix_bytes(const tpl_op* op) { return op ? op->matrix_bytes : 0; }
+uint64_t tpl_op_device_bytes(const tpl_op* op) { return op ? op->device_bytes : 0; }
+
+int tpl_op_set_stream(tpl_op* op, void* cuda_stream) {
+  if (!op) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  CUDA_TRY(cudaStreamSynchronize(op->stream));
+  if (op->own_stream) CUDA_TRY(cudaStreamDestroy(op->stream));
+  op->stream = static_cast<cudaStream_t>(cuda_stream);
+  op->own_stream = false;
+  return TPL_OK;
+}
+
+int tpl_op_set_mode(tpl_op* op, int mode) {
+  if (!op || mode < 0 || mode > 1) return fail(TPL_ERR_PANIC, "invalid mode");
+  op->mode = mode;
+  return TPL_OK;
+}
+
+int tpl_op_last_timing(const tpl_op* op, double* pass_one_ms, double* pass_two_ms, double* gemv_ms) {
+  if (!op) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  double* outs[3] = {pass_one_ms, pass_two_ms, gemv_ms};
+  for (int i = 0; i < 3; ++i) {
+    if (!outs[i]) continue;
+    *outs[i] = 0.0;
+    if (!op->timed[i]) continue;
+    float ms = 0.f;
+    CUDA_TRY(cudaEventSynchronize(op->ev[2 * i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, op->ev[2 * i], op->ev[2 * i + 1]));
+    *outs[i] = ms;
+  }
+  return TPL_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================ launches
+namespace {
+
+template <class KERNEL, class OP, class ARGS>
+int launch_coop(tpl_op* op, KERNEL kernel, const OP& dop, const ARGS& args) {
+  void* params[] = {const_cast<OP*>(&dop), const_cast<ARGS*>(&args)};
+  CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->G), dim3(tpl::kBlock), params,
+                                       op->smem_bytes, op->stream));
+  op->launches += 1;
+  return TPL_OK;
+}
+
+int launch_pass1(tpl_op* op, const tpl::Pass1Args& a) {
+  const bool with_v = a.V != nullptr;
+  if (op->format == 2)
+    return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, true>, op->inc, a)
+                  : launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, false>, op->inc, a);
+  return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::CsrOp, true>, op->csr, a)
+                : launch_coop(op, tpl::pass1_kernel<tpl::CsrOp, false>, op->csr, a);
+}
+int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
+  const bool with_v = a.V != nullptr;
+  if (op->format == 2)
+    return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, true>, op->inc, a)
+                  : launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, false>, op->inc, a);
+  return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::CsrOp, true>, op->csr, a)
+                : launch_coop(op, tpl::pass2_kernel<tpl::CsrOp, false>, op->csr, a);
+}
+
+// Brings b to the device (no copy when it already lives there).
+int stage_b(tpl_op* op, const double* b, const double** b_dev) {
+  if (is_device_ptr(b)) {
+    *b_dev = b;
+    return TPL_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(op->b_d, b, sizeof(double) * op->n, cudaMemcpyHostToDevice, op->stream));
+  *b_dev = op->b_d;
+  return TPL_OK;
+}
+
+int reset_sync_state(tpl_op* op) {
+  tpl::State st{};
+  st.s_cur = 1.0;
+  st.s_prev = 1.0;
+  st.status = tpl::ST_RUNNING;
+  std::memcpy(op->h_pin, &st, sizeof st);
+  CUDA_TRY(cudaMemsetAsync(op->flags, 0, sizeof(unsigned int) * op->G, op->stream));
+  CUDA_TRY(cudaMemcpyAsync(op->coef_d, op->h_pin, sizeof st, cudaMemcpyHostToDevice, op->stream));
+  return TPL_OK;
+}
+
+struct Decomp {  // LanczosDecomposition (src/algorithms/mod.rs:94-108) on the host
+  std::vector<double> alphas, betas;
+  size_t steps = 0;
+  double b_norm = 0.0;
+};
+
+// Reads [State | alphas | betas] back in one copy and applies the reference's push rules
+// (lanczos_two_pass.rs:86-98: alpha every step, beta only when not broken down and i < k-1).
+int fetch_decomp(tpl_op* op, size_t k, Decomp& out, int& status) {
+  const size_t doubles = kHeaderDoubles + 2 * op->coef_cap;
+  (void)k;
+  CUDA_TRY(cudaMemcpyAsync(op->h_pin, op->coef_d, doubles * sizeof(double), cudaMemcpyDeviceToHost, op->stream));
+  CUDA_TRY(cudaStreamSynchronize(op->stream));
+  tpl::State st;
+  std::memcpy(&st, op->h_pin, sizeof st);
+  status = st.status;
+  out.b_norm = st.b_norm;
+  out.steps = (size_t)st.steps;
+  const double* al = op->h_pin + kHeaderDoubles;
+  const double* be = op->h_pin + kHeaderDoubles + op->coef_cap;
+  out.alphas.assign(al, al + out.steps);
+  out.betas.assign(be, be + (out.steps ? out.steps - 1 : 0));
+  return TPL_OK;
+}
+
+// lanczos_pass_one / basis generation of lanczos_standard on a device-resident b.
+int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_t ldv, tpl_step_callback cb,
+                 void* user, Decomp& out) {
+  if (k == 0) return fail(TPL_ERR_PANIC, "capacity overflow (k == 0; the reference panics in Vec::with_capacity(k - 1))");
+  if (k > 0x7ffffff0ull) return fail(TPL_ERR_PANIC, "k too large");
+  if (int rc = ensure_coef(op, k)) return rc;
+  if (int rc = reset_sync_state(op)) return rc;
+  tpl::Pass1Args a{};
+  for (int i = 0; i < 3; ++i) a.buf[i] = op->buf[i];
+  a.b = b_dev;
+  a.alphas = op->alphas_d();
+  a.betas = op->betas_d();
+  a.V = V_dev;
+  a.ldv = ldv;
+  a.n = op->n;
+  a.st = op->st_d();
+  a.gs = op->gs();
+  a.tol = tpl::kBreakdownTol;
+  int status = tpl::ST_RUNNING;
+  CUDA_TRY(cudaEventRecord(op->ev[0], op->stream));
+  if (!cb && op->mode == 0) {
+    a.j_begin = 0;
+    a.j_end = (int)k;
+    if (int rc = launch_pass1(op, a)) return rc;
+    CUDA_TRY(cudaEventRecord(op->ev[1], op->stream));
+    if (int rc = fetch_decomp(op, k, out, status)) return rc;
+  } else {
+    // one cooperative launch per step: lets the host run the LanczosCallback (lanczos.rs:93-106)
+    for (size_t j = 0; j < k; ++j) {
+      a.j_begin = (int)j;
+      a.j_end = (int)j + 1;
+      if (int rc = launch_pass1(op, a)) return rc;
+      if (!cb && j + 1 < k) continue;  // mode 1 without a callback: no host round trip needed
+      if (int rc = fetch_decomp(op, k, out, status)) return rc;
+      if (status != tpl::ST_RUNNING) break;
+      if (cb && out.steps == j + 1) {
+        if (!cb(out.steps, V_dev, ldv, out.alphas.data(), out.betas.data(), user)) break;
+      }
+    }
+    CUDA_TRY(cudaEventRecord(op->ev[1], op->stream));
+    if (int rc = fetch_decomp(op, k, out, status)) return rc;
+  }
+  op->timed[0] = true;
+  if (status == tpl::ST_ZERO_B) return tpl::fail_input("Input vector `b` must not be a zero vector.");  // mod.rs:268-273
+  return TPL_OK;
+}
+
+// lanczos_pass_two_impl on device-resident b / x (host alphas, betas, y).
+int run_pass_two(tpl_op* op, const double* b_dev, const double* alphas, const double* betas, size_t steps,
+                 double b_norm, const double* y, size_t y_len, double* x_dev, double* V_dev, size_t ldv) {
+  if (steps != y_len) return tpl::fail_parameter_mismatch("y_k", steps, y_len);  // lanczos_two_pass.rs:220-227
+  if (b_norm <= tpl::kBreakdownTol)                                                // :229-235
+    return tpl::fail_input("The initial vector `b` must not be a zero vector.");
+  if (steps == 0) {                                                                // :237-244
+    CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * op->n, op->stream));
+    return TPL_OK;
+  }
+  if (int rc = ensure_coef(op, steps)) return rc;
+  if (int rc = reset_sync_state(op)) return rc;
+  // coefficients: [alphas | betas | y] -> device in one copy through the pinned mirror
+  double* hp = op->h_pin + kHeaderDoubles;
+  std::memcpy(hp, alphas, steps * sizeof(double));
+  if (steps > 1) std::memcpy(hp + op->coef_cap, betas, (steps - 1) * sizeof(double));
+  std::memcpy(hp + 2 * op->coef_cap, y, steps * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(op->alphas_d(), hp, 3 * op->coef_cap * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+  tpl::Pass2Args a{};
+  for (int i = 0; i < 3; ++i) a.buf[i] = op->buf[i];
+  a.b = b_dev;
+  a.alphas = op->alphas_d();
+  a.betas = op->betas_d();
+  a.y = op->y_d();
+  a.x = x_dev;
+  a.V = V_dev;
+  a.ldv = ldv;
+  a.n = op->n;
+  a.steps = (int)steps;
+  a.b_norm = b_norm;
+  a.st = op->st_d();
+  a.gs = op->gs();
+  CUDA_TRY(cudaEventRecord(op->ev[2], op->stream));
+  if (int rc = launch_pass2(op, a)) return rc;
+  CUDA_TRY(cudaEventRecord(op->ev[3], op->stream));
+  op->timed[1] = true;
+  return TPL_OK;
+}
+
+int gemv_vy(tpl_op* op, const double* V_dev, size_t ldv, size_t steps, const double* y_host, double b_norm,
+            double* x_dev) {
+  if (int rc = ensure_coef(op, steps)) return rc;
+  double* hp = op->h_pin + kHeaderDoubles + 2 * op->coef_cap;
+  std::memcpy(hp, y_host, steps * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(op->y_d(), hp, steps * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+  const int block = 256;
+  const int grid = (int)std::min<size_t>((op->n + block - 1) / block, (size_t)op->G * 16);
+  CUDA_TRY(cudaEventRecord(op->ev[4], op->stream));
+  tpl::gemv_vy_kernel<<<grid, block, steps * sizeof(double), op->stream>>>(V_dev, ldv, op->n, (int)steps, op->y_d(),
+                                                                          b_norm, x_dev);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(op->ev[5], op->stream));
+  op->timed[2] = true;
+  op->launches += 1;
+  return TPL_OK;
+}
+
+int ensure_internal_basis(tpl_op* op, size_t elems) {
+  if (elems <= op->V_int_elems) return TPL_OK;
+  if (op->V_int) {
+    if (int rc = dev_free(op, op->V_int)) return rc;
+    op->V_int = nullptr;
+    op->V_int_elems = 0;
+  }
+  if (int rc = dev_alloc(op, &op->V_int, elems)) return rc;
+  op->V_int_elems = elems;
+  return TPL_OK;
+}
+
+// copies a column-major n x cols device matrix (leading dimension n) into a host matrix with ldv
+int basis_to_host(tpl_op* op, const double* V_dev, double* V_host, size_t ldv, size_t cols) {
+  if (!cols) return TPL_OK;
+  CUDA_TRY(cudaMemcpy2DAsync(V_host, ldv * sizeof(double), V_dev, (size_t)op->n * sizeof(double),
+                             (size_t)op->n * sizeof(double), cols, cudaMemcpyDeviceToHost, op->stream));
+  return TPL_OK;
+}
+
+int finish_x(tpl_op* op, const double* x_dev, double* x) {
+  if (x_dev != x) CUDA_TRY(cudaMemcpyAsync(x, x_dev, sizeof(double) * op->n, cudaMemcpyDeviceToHost, op->stream));
+  CUDA_TRY(cudaStreamSynchronize(op->stream));
+  return TPL_OK;
+}
+
+int call_ftk(tpl_ftk_solver f, void* user, const Decomp& d, std::vector<double>& y) {
+  // closure call + shape validation (solvers.rs:71-87, 155-165)
+  y.assign(d.steps + 1, 0.0);
+  size_t y_len = d.steps;
+  const std::string before = tpl::g_err;
+  int rc = f(d.alphas.data(), d.alphas.size(), d.betas.data(), d.betas.size(), y.data(), &y_len, user);
+  if (rc != 0) {
+    std::string inner = tpl::g_err != before && !tpl::g_err.empty() ? tpl::g_err : ("callback returned " + std::to_string(rc));
+    return tpl::fail_solver(inner.c_str());
+  }
+  if (y_len != d.steps) return tpl::fail_parameter_mismatch("y_k_prime", d.steps, y_len);
+  y.resize(d.steps);
+  return TPL_OK;
+}
+
+}  // namespace
+
+// ============================================================================ public compute entry points
+extern "C" {
+
+int tpl_op_apply(tpl_op* op, const double* x, double* y) {
+  tpl::clear_error();
+  if (!op || !x || !y) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  const double* x_dev = nullptr;
+  if (int rc = stage_b(op, x, &x_dev)) return rc;
+  double* y_dev = is_device_ptr(y) ? y : op->x_d;
+  if (op->format == 2)
+    tpl::apply_kernel<tpl::IncidenceOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->inc, x_dev, y_dev);
+  else
+    tpl::apply_kernel<tpl::CsrOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->csr, x_dev, y_dev);
+  CUDA_TRY(cudaGetLastError());
+  op->launches += 1;
+  return finish_x(op, y_dev, y);
+}
+
+int tpl_pass_one(tpl_op* op, const double* b, size_t k, double* alphas, double* betas, size_t* steps,
+                 double* b_norm) {
+  tpl::clear_error();
+  if (!op || !b || !alphas || !steps || !b_norm || (k > 1 && !betas)) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  Decomp d;
+  int rc = run_pass_one(op, b_dev, k, nullptr, 0, nullptr, nullptr, d);
+  *b_norm = d.b_norm;
+  if (rc) return rc;
+  *steps = d.steps;
+  std::copy(d.alphas.begin(), d.alphas.end(), alphas);
+  if (!d.betas.empty()) std::copy(d.betas.begin(), d.betas.end(), betas);
+  return TPL_OK;
+}
+
+int tpl_pass_two(tpl_op* op, const double* b, const double* alphas, const double* betas, size_t steps, double b_norm,
+                 const double* y, size_t y_len, double* x, double* V, size_t ldv) {
+  tpl::clear_error();
+  if (!op || !b || !x || (steps && (!alphas || !y)) || (steps > 1 && !betas)) return fail(TPL_ERR_PANIC, "null argument");
+  if (V && ldv < op->n) return tpl::fail_parameter_mismatch("ldv", op->n, ldv);
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  double* x_dev = is_device_ptr(x) ? x : op->x_d;
+  double* V_dev = V;
+  size_t ld_dev = ldv;
+  const bool v_host = V && !is_device_ptr(V);
+  if (v_host && steps == y_len && steps > 0) {
+    if (int rc = ensure_internal_basis(op, (size_t)op->n * steps)) return rc;
+    V_dev = op->V_int;
+    ld_dev = op->n;
+  }
+  if (int rc = run_pass_two(op, b_dev, alphas, betas, steps, b_norm, y, y_len, x_dev, V_dev, ld_dev)) return rc;
+  if (v_host && steps > 0)
+    if (int rc = basis_to_host(op, V_dev, V, ldv, steps)) return rc;
+  return finish_x(op, x_dev, x);
+}
+
+int tpl_standard(tpl_op* op, const double* b, size_t k, double* V, size_t ldv, double* alphas, double* betas,
+                 size_t* steps, double* b_norm, tpl_step_callback cb, void* user) {
+  tpl::clear_error();
+  if (!op || !b || !V || !alphas || !steps || !b_norm || (k > 1 && !betas)) return fail(TPL_ERR_PANIC, "null argument");
+  if (k == 0) return fail(TPL_ERR_PANIC, "capacity overflow (k == 0; the reference panics in Vec::with_capacity(k - 1))");
+  if (ldv < op->n) return tpl::fail_parameter_mismatch("ldv", op->n, ldv);
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  const bool v_host = !is_device_ptr(V);
+  double* V_dev = V;
+  size_t ld_dev = ldv;
+  if (v_host) {
+    if (int rc = ensure_internal_basis(op, (size_t)op->n * k)) return rc;
+    V_dev = op->V_int;
+    ld_dev = op->n;
+  }
+  // Mat::zeros(n, k) (lanczos.rs:70): columns that are never reached stay zero
+  CUDA_TRY(cudaMemset2DAsync(V_dev, ld_dev * sizeof(double), 0, (size_t)op->n * sizeof(double), k, op->stream));
+  Decomp d;
+  int rc = run_pass_one(op, b_dev, k, V_dev, ld_dev, cb, user, d);
+  *b_norm = d.b_norm;
+  if (rc) return rc;
+  *steps = d.steps;
+  std::copy(d.alphas.begin(), d.alphas.end(), alphas);
+  if (!d.betas.empty()) std::copy(d.betas.begin(), d.betas.end(), betas);
+  if (v_host) {
+    if (int rc2 = basis_to_host(op, V_dev, V, ldv, k)) return rc2;
+    CUDA_TRY(cudaStreamSynchronize(op->stream));
+  }
+  return TPL_OK;
+}
+
+// solvers::lanczos (src/solvers.rs:46-107): V_k stays in HBM, x = ||b|| * (V_k y') is one streaming GEMV.
+int tpl_lanczos(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f_tk, void* user, double* x) {
+  tpl::clear_error();
+  if (!op || !b || !x || !f_tk) return fail(TPL_ERR_PANIC, "null argument");
+  if (k == 0) return fail(TPL_ERR_PANIC, "capacity overflow (k == 0; the reference panics in Vec::with_capacity(k - 1))");
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  if (int rc = ensure_internal_basis(op, (size_t)op->n * k)) return rc;
+  Decomp d;
+  if (int rc = run_pass_one(op, b_dev, k, op->V_int, op->n, nullptr, nullptr, d)) return rc;
+  double* x_dev = is_device_ptr(x) ? x : op->x_d;
+  if (d.steps == 0) {  // solvers.rs:65-67
+    CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * op->n, op->stream));
+    return finish_x(op, x_dev, x);
+  }
+  std::vector<double> y;
+  if (int rc = call_ftk(f_tk, user, d, y)) return rc;
+  if (int rc = gemv_vy(op, op->V_int, op->n, d.steps, y.data(), d.b_norm, x_dev)) return rc;
+  return finish_x(op, x_dev, x);
+}
+
+// solvers::lanczos_two_pass (src/solvers.rs:133-175)
+int tpl_lanczos_two_pass(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f_tk, void* user, double* x) {
+  tpl::clear_error();
+  if (!op || !b || !x || !f_tk) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  Decomp d;
+  if (int rc = run_pass_one(op, b_dev, k, nullptr, 0, nullptr, nullptr, d)) return rc;
+  double* x_dev = is_device_ptr(x) ? x : op->x_d;
+  if (d.steps == 0) {  // solvers.rs:150-152
+    CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * op->n, op->stream));
+    return finish_x(op, x_dev, x);
+  }
+  std::vector<double> y;
+  if (int rc = call_ftk(f_tk, user, d, y)) return rc;
+  for (double& yi : y) yi = yi * d.b_norm;  // solvers.rs:169
+  if (int rc = run_pass_two(op, b_dev, d.alphas.data(), d.betas.data(), d.steps, d.b_norm, y.data(), y.size(), x_dev,
+                            nullptr, 0))
+    return rc;
+  return finish_x(op, x_dev, x);
+}
+
+// ---------------------------------------------------------------------------- multi-GPU (stage 7)
+int tpl_comm_unique_id(uint8_t id_out[128]) {
+  (void)id_out;
+  return fail(TPL_ERR_COMM, "communicator support is not built into this library yet");
+}
+int tpl_op_from_kkt_sharded(size_t, size_t, size_t, size_t, const uint32_t*, const uint32_t*, const double*, size_t, int,
+                            int, int, const uint8_t[128], tpl_op**) {
+  return fail(TPL_ERR_COMM, "communicator support is not built into this library yet");
+}
+
+}  // extern "C"

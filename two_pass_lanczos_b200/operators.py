@@ -1,0 +1,117 @@
+"""Device-resident operators: the stand-in for `&impl faer::matrix_free::LinOp<f64>`
+(src/solvers.rs:56, src/algorithms/mod.rs:167).  Thin RAII wrappers over `tpl_op*` handles."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_dp, c_u32p, c_u64p
+
+
+def _vec_ptr(v):
+    """(pointer, keepalive, is_torch) for a host numpy vector or a torch tensor (host or CUDA)."""
+    if hasattr(v, "data_ptr"):  # torch tensor; CUDA tensors are consumed in place (no copy)
+        t = v.contiguous()
+        if str(t.dtype) != "torch.float64":
+            raise TypeError("vectors must be float64")
+        return C.c_void_p(t.data_ptr()), t, True
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+    return C.c_void_p(a.ctypes.data), a, False
+
+
+class LinOp:
+    """Owns a `tpl_op*`.  `nrows()`/`ncols()`/`apply()` mirror faer's LinOp trait."""
+
+    FORMAT = {1: "csr", 2: "incidence"}
+
+    def __init__(self, handle: C.c_void_p):
+        self._h = handle
+
+    # -- construction ---------------------------------------------------------------------------
+    @classmethod
+    def from_csc(cls, n, colptr, rowidx, val, device: int = -1) -> "LinOp":
+        colptr = np.ascontiguousarray(colptr, dtype=np.uint64)
+        rowidx = np.ascontiguousarray(rowidx, dtype=np.uint64)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        h = C.c_void_p()
+        _lib.check(_lib.load().tpl_op_from_csc(n, colptr.ctypes.data_as(c_u64p), rowidx.ctypes.data_as(c_u64p),
+                                               val.ctypes.data_as(c_dp), device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_scipy(cls, a, device: int = -1) -> "LinOp":
+        import scipy.sparse as sp
+
+        a = sp.csc_matrix(a)
+        a.sort_indices()
+        return cls.from_csc(a.shape[0], a.indptr, a.indices, a.data, device)
+
+    @classmethod
+    def from_dense(cls, a, device: int = -1) -> "LinOp":
+        import scipy.sparse as sp
+
+        return cls.from_scipy(sp.csc_matrix(np.asarray(a, dtype=np.float64)), device)
+
+    @classmethod
+    def from_kkt(cls, m, p, tail, head, d, device: int = -1) -> "LinOp":
+        tail = np.ascontiguousarray(tail, dtype=np.uint32)
+        head = np.ascontiguousarray(head, dtype=np.uint32)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        h = C.c_void_p()
+        _lib.check(_lib.load().tpl_op_from_kkt(m, p, tail.ctypes.data_as(c_u32p), head.ctypes.data_as(c_u32p),
+                                               d.ctypes.data_as(c_dp), len(d), device, C.byref(h)))
+        return cls(h)
+
+    # -- LinOp ------------------------------------------------------------------------------------
+    def nrows(self) -> int:
+        return _lib.load().tpl_op_nrows(self._h)
+
+    ncols = nrows
+
+    @property
+    def format(self) -> str:
+        return self.FORMAT.get(_lib.load().tpl_op_format(self._h), "?")
+
+    def apply(self, x):
+        xp, keep, is_torch = _vec_ptr(x)
+        if is_torch and keep.is_cuda:
+            y = keep.new_empty(keep.shape)
+            _lib.check(_lib.load().tpl_op_apply(self._h, xp, C.c_void_p(y.data_ptr())))
+            return y
+        y = np.empty(self.nrows())
+        _lib.check(_lib.load().tpl_op_apply(self._h, xp, C.c_void_p(y.ctypes.data)))
+        return y
+
+    # -- engine knobs / introspection -----------------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        _lib.check(_lib.load().tpl_op_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_mode(self, mode: int):
+        _lib.check(_lib.load().tpl_op_set_mode(self._h, mode))
+
+    def last_timing(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(_lib.load().tpl_op_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"pass_one_ms": a.value, "pass_two_ms": b.value, "gemv_ms": c.value}
+
+    def kernel_launches(self) -> int:
+        return _lib.load().tpl_op_kernel_launches(self._h)
+
+    def matrix_bytes(self) -> int:
+        return _lib.load().tpl_op_matrix_bytes(self._h)
+
+    def device_bytes(self) -> int:
+        return _lib.load().tpl_op_device_bytes(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().tpl_op_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

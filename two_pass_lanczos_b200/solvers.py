@@ -1,0 +1,71 @@
+"""High-level solvers, same names and meaning as the reference's `solvers` module (src/solvers.rs)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FTK_FN
+from .operators import LinOp, _vec_ptr
+
+# Host f(T_k) e1 solvers implemented in the library (C++); usable wherever a closure is expected.
+INV, EXP, SQUARE = "inv", "exp", "square"
+
+
+def _native_ftk(name: str):
+    fn = getattr(_lib.load(), {"inv": "tpl_ftk_inv", "exp": "tpl_ftk_exp", "square": "tpl_ftk_square"}[name])
+    return C.cast(fn, FTK_FN)
+
+
+def _wrap_closure(f_tk_solver, errors: list):
+    """F: FnMut(&[R], &[R]) -> Result<Mat<T>, anyhow::Error>  (solvers.rs:58)"""
+
+    def _f(ap, na, bp, nb, yp, ylenp, _u):
+        try:
+            a_ = np.ctypeslib.as_array(ap, shape=(na,)).copy() if na else np.zeros(0)
+            b_ = np.ctypeslib.as_array(bp, shape=(nb,)).copy() if nb else np.zeros(0)
+            y = np.asarray(f_tk_solver(a_, b_), dtype=np.float64)
+            if y.ndim == 2 and y.shape[1] != 1:  # y' must be steps x 1 (solvers.rs:75,158)
+                ylenp[0] = y.shape[0] + 1 if y.shape[0] == na else y.shape[0]
+                return 0
+            y = y.reshape(-1)
+            ylenp[0] = len(y)
+            for i in range(min(len(y), na)):
+                yp[i] = y[i]
+            return 0
+        except Exception as e:  # noqa: BLE001 - becomes SolverError(e.to_string()) (solvers.rs:72,156)
+            errors.append(e)
+            return 1
+
+    return FTK_FN(_f)
+
+
+def _solve(entry: str, operator: LinOp, b, k: int, f_tk_solver):
+    bp, keep, is_torch = _vec_ptr(b)
+    n = operator.nrows()
+    if is_torch and keep.is_cuda:
+        x = keep.new_empty(n)
+        xptr = C.c_void_p(x.data_ptr())
+    else:
+        x = np.empty(n)
+        xptr = C.c_void_p(x.ctypes.data)
+    errors: list = []
+    cb = _native_ftk(f_tk_solver) if isinstance(f_tk_solver, str) else _wrap_closure(f_tk_solver, errors)
+    rc = getattr(_lib.load(), entry)(operator._h, bp, k, cb, None, xptr)
+    if rc == 6 and errors:  # SolverError carries the closure's message
+        from .error import LanczosError
+
+        raise LanczosError(6, f"The user-provided f(T_k) solver failed: {errors[0]}")
+    _lib.check(rc)
+    return x
+
+
+def lanczos(operator: LinOp, b, k: int, f_tk_solver):
+    """One-pass f(A)b (src/solvers.rs:46-107): V_k kept in HBM, x = ||b|| V_k f(T_k) e1."""
+    return _solve("tpl_lanczos", operator, b, k, f_tk_solver)
+
+
+def lanczos_two_pass(operator: LinOp, b, k: int, f_tk_solver):
+    """Two-pass f(A)b (src/solvers.rs:133-175): O(n) memory, basis regenerated in pass 2."""
+    return _solve("tpl_lanczos_two_pass", operator, b, k, f_tk_solver)
