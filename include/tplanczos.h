@@ -181,7 +181,7 @@ int tpl_ftk_square(const double* alphas, size_t na, const double* betas, size_t 
  * Multi-GPU (arc-partitioned KKT operator): rank r of `world` owns arcs
  * [arc_begin, arc_end) and a replica of the p node rows.  The communicator is NCCL; the caller
  * supplies the 128-byte ncclUniqueId made by rank 0 (tpl_comm_unique_id) through its own
- * rendezvous (torch.distributed in bench.py).
+ * rendezvous (any out-of-band channel; bench.py broadcasts it between its ranks).
  * ------------------------------------------------------------------------------------ */
 int tpl_comm_unique_id(uint8_t id_out[128]);
 int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end, const uint32_t* tail,

@@ -46,7 +46,8 @@ bool tridiag_solve(size_t n, std::vector<double>& dl, std::vector<double>& d, st
   if (d[n - 1] == 0.0) return false;
   b[n - 1] /= d[n - 1];
   if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / d[n - 2];
-  for (size_t i = n - 2; i-- > 0;) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) / d[i];
+  if (n > 2)
+    for (size_t i = n - 2; i-- > 0;) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) / d[i];
   return true;
 }
 
