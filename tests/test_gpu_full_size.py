@@ -102,7 +102,7 @@ def test_stability_harness(func, scenario, k, published):
     assert max(published, 1e-15) / 30.0 < max(err, 1e-15) < max(published, 1e-15) * 30.0
     assert helpers.rel(x1, x2) < 1e-13
     x_ref = orc.lanczos_two_pass(oop, b, k, helpers.FTK[func])
-    assert abs(err - helpers.rel(x_ref, x_true)) <= 0.5 * err + 1e-14  # same convergence curve as the oracle
+    assert abs(err - helpers.rel(x_ref, x_true)) <= 0.5 * err + 1e-12  # same convergence curve as the oracle
 
 
 @pytest.mark.parametrize("func,scenario", [("exp", "well"), ("inv", "ill")])
