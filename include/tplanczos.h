@@ -119,9 +119,16 @@ uint64_t tpl_op_kernel_launches(const tpl_op* op);
  * B_inc = 24 m + 4 p) and bytes of HBM the handle currently holds. */
 uint64_t tpl_op_matrix_bytes(const tpl_op* op);
 uint64_t tpl_op_device_bytes(const tpl_op* op);
-/* Execution mode: 0 = persistent cooperative kernels (default), 1 = one cooperative launch per
- * Lanczos step (same kernels, same arithmetic; used when a step callback is installed). */
+/* Execution mode: 0 = automatic (default): persistent cooperative kernels, shared-memory-resident when the
+ * per-SM slice of the operator fits, streaming otherwise; 1 = one cooperative launch per Lanczos step
+ * (streaming kernels; what a step callback uses); 2 = persistent streaming kernels even when the resident
+ * shape would fit.  All modes run the same per-element arithmetic and give bit-identical results. */
 int tpl_op_set_mode(tpl_op* op, int mode);
+/* Diagnostics: per-CTA, per-step phase timestamps (SM clock) of the resident kernels.  enable(max_steps > 0)
+ * allocates ctas x max_steps x marks 64-bit words in HBM, enable(0) frees them; read() copies them out (row-major
+ * [cta][step][mark]) and clears the buffer.  Off by default; costs one predicated store per mark when on. */
+int tpl_op_trace_enable(tpl_op* op, size_t max_steps);
+int tpl_op_trace_read(tpl_op* op, uint64_t* out, size_t capacity, size_t* ctas, size_t* steps, size_t* marks);
 
 /* ------------------------------------------------------------------------------------
  * algorithms::*  building blocks

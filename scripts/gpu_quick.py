@@ -76,6 +76,15 @@ def main():
             wall = time.time() - t
             tm = gop.last_timing()
             print(f"m={big} k={k} wall {wall*1e3:.2f} ms  pass1 {tm['pass_one_ms']:.3f} ms pass2 {tm['pass_two_ms']:.3f} ms")
+    for mode in (2, 1, 0):
+        gop.set_mode(mode)
+        xm = tpl.lanczos_two_pass(gop, bb, 500, "inv")
+        tm = gop.last_timing()
+        print(f"mode {mode}: pass1 {tm['pass_one_ms']:.3f} ms pass2 {tm['pass_two_ms']:.3f} ms  bitwise equal to mode 0: {np.array_equal(xm, x)}")
+        dm = alg.lanczos_pass_one(gop, bb, 60)
+        if mode == 2:
+            d2 = dm
+        print("   alpha/beta equal to mode 2:", np.array_equal(dm.alphas, d2.alphas), np.array_equal(dm.betas, d2.betas))
     n = inst.n
     bm = gop.matrix_bytes()
     k = 500

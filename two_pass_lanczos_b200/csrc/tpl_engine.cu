@@ -90,8 +90,10 @@ struct tpl_op {
   double* x_d = nullptr;
   double* coef_d = nullptr;  // [header | alphas cap | betas cap | y cap]
   size_t coef_cap = 0;
-  unsigned int* flags = nullptr;
-  double* partials = nullptr;
+  uint4* slots = nullptr;      // grid-sync slots [2][G]
+  bool resident_ok = false;    // the per-CTA slice of the incidence operator fits in shared memory
+  tpl::ResidentOp res{};
+  size_t smem_res1 = 0, smem_res2 = 0;
   double* h_pin = nullptr;  // pinned mirror of coef_d
   double* V_int = nullptr;
   size_t V_int_elems = 0;
@@ -104,7 +106,9 @@ struct tpl_op {
   double* alphas_d() const { return coef_d + kHeaderDoubles; }
   double* betas_d() const { return coef_d + kHeaderDoubles + coef_cap; }
   double* y_d() const { return coef_d + kHeaderDoubles + 2 * coef_cap; }
-  tpl::GridSync gs() const { return tpl::GridSync{flags, partials}; }
+  unsigned long long* trace_d = nullptr;
+  int trace_steps = 0;
+  tpl::GridSync gs() const { return tpl::GridSync{slots, tpl::Trace{trace_d, trace_steps}, -1, 4}; }
 };
 
 namespace {
@@ -151,7 +155,7 @@ bool is_device_ptr(const void* p) {
 struct HostLongRows {
   std::vector<uint32_t> row, seg_ptr, ent_ptr, ent_idx, cta_ptr;
   std::vector<double> ent_val;
-  uint32_t max_segs = 0;
+  uint32_t max_segs = 0, max_ents = 0, max_rows = 0;
 };
 
 // row_ent[q]..row_ent[q+1] is the entry range of long row q inside ent_idx/ent_val (already filled).
@@ -189,14 +193,20 @@ void build_segments(HostLongRows& h, const std::vector<uint64_t>& row_ent, int G
   // rows without segments at the tail must still be owned: spread every row, by count, if there are no segments
   if (nseg == 0)
     for (int c = 0; c <= G; ++c) h.cta_ptr[c] = (uint32_t)std::min<uint64_t>(nlong, ((uint64_t)nlong * c + G - 1) / G);
-  h.max_segs = 0;
-  for (int c = 0; c < G; ++c)
-    h.max_segs = std::max(h.max_segs, h.seg_ptr[h.cta_ptr[c + 1]] - h.seg_ptr[h.cta_ptr[c]]);
+  h.max_segs = h.max_ents = h.max_rows = 0;
+  for (int c = 0; c < G; ++c) {
+    const uint32_t q0 = h.cta_ptr[c], q1 = h.cta_ptr[c + 1];
+    h.max_segs = std::max(h.max_segs, h.seg_ptr[q1] - h.seg_ptr[q0]);
+    h.max_ents = std::max(h.max_ents, h.ent_ptr[h.seg_ptr[q1]] - h.ent_ptr[h.seg_ptr[q0]]);
+    h.max_rows = std::max(h.max_rows, q1 - q0);
+  }
 }
 
 int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
   d.nlong = (uint32_t)h.row.size();
   d.max_segs = h.max_segs;
+  d.max_ents = h.max_ents;
+  d.max_rows = h.max_rows;
   if (int rc = dev_upload(op, &d.row, h.row)) return rc;
   if (int rc = dev_upload(op, &d.seg_ptr, h.seg_ptr)) return rc;
   if (int rc = dev_upload(op, &d.ent_ptr, h.ent_ptr)) return rc;
@@ -257,9 +267,8 @@ int finish_setup(tpl_op* op) {
     if (int rc = dev_alloc(op, &b, n)) return rc;
   if (int rc = dev_alloc(op, &op->b_d, n)) return rc;
   if (int rc = dev_alloc(op, &op->x_d, n)) return rc;
-  if (int rc = dev_alloc(op, &op->flags, (size_t)op->G)) return rc;
-  if (int rc = dev_alloc(op, &op->partials, 2 * (size_t)op->G)) return rc;
-  CUDA_TRY(cudaMemset(op->flags, 0, sizeof(unsigned int) * op->G));
+  if (int rc = dev_alloc(op, &op->slots, 2 * (size_t)op->G)) return rc;
+  CUDA_TRY(cudaMemset(op->slots, 0, sizeof(uint4) * 2 * op->G));
   if (int rc = ensure_coef(op, 1024)) return rc;
   // opt in to the dynamic shared memory the kernels need and check the grid is co-resident
   const size_t smem = op->smem_bytes;
@@ -272,6 +281,27 @@ int finish_setup(tpl_op* op) {
     if (int rc = set_smem(tpl::apply_kernel<tpl::IncidenceOp>, smem)) return rc;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_kernel<tpl::IncidenceOp, true>,
                                                            tpl::kBlock, smem));
+    // resident shape: the CTA's slice of the operator and of the vectors stays in shared memory
+    if (op->resident_ok) {
+      const uint32_t A = (op->inc.m + op->G - 1) / op->G;
+      op->smem_res1 = tpl::resident_smem_bytes(op->inc.p, A, op->G, op->res.R, op->res.max_long, false);
+      op->smem_res2 = tpl::resident_smem_bytes(op->inc.p, A, op->G, op->res.R, op->res.max_long, true);
+      int max_optin = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
+      op->resident_ok = op->smem_res2 + 1024 <= (size_t)max_optin;
+    }
+    if (op->resident_ok) {
+      if (int rc = set_smem(tpl::pass1_resident_kernel<false>, op->smem_res1)) return rc;
+      if (int rc = set_smem(tpl::pass1_resident_kernel<true>, op->smem_res1)) return rc;
+      if (int rc = set_smem(tpl::pass2_resident_kernel<false>, op->smem_res2)) return rc;
+      if (int rc = set_smem(tpl::pass2_resident_kernel<true>, op->smem_res2)) return rc;
+      int r1 = 0, r2 = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r1, tpl::pass1_resident_kernel<true>, tpl::kBlock,
+                                                             op->smem_res1));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r2, tpl::pass2_resident_kernel<true>, tpl::kBlock,
+                                                             op->smem_res2));
+      if (r1 < 1 || r2 < 1) op->resident_ok = false;
+    }
   } else {
     if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, false>, smem)) return rc;
     if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, true>, smem)) return rc;
@@ -420,6 +450,53 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   if (!rc) rc = dev_upload(op, &op->inc.tail, t);
   if (!rc) rc = dev_upload(op, &op->inc.head, hd);
   if (!rc) rc = upload_long_rows(op, h, op->inc.lr);
+  // resident shape: per-CTA node -> local-arc lists (tail: +, head: - with bit 15), ascending local arc index
+  {
+    const int G = op->G;
+    const size_t A = (m + G - 1) / G;
+    const uint32_t R = (uint32_t)((p + G - 1) / G);
+    op->res.R = std::max<uint32_t>(R, 1);
+    if (A <= 0x7fff && !rc) {
+      std::vector<uint32_t> nl_ptr((size_t)G * (p + 1), 0), nl_long_ptr(G + 1, 0), nl_long;
+      std::vector<uint16_t> nl_ent;
+      nl_ent.reserve(2 * m);
+      std::vector<uint32_t> cnt(p + 1);
+      uint32_t max_long = 0;
+      for (int c = 0; c < G; ++c) {
+        const size_t lo = std::min(m, A * (size_t)c), hi = std::min(m, lo + A);
+        std::fill(cnt.begin(), cnt.end(), 0u);
+        for (size_t j = lo; j < hi; ++j)
+          if (tail[j] != head[j]) {
+            ++cnt[tail[j] + 1];
+            ++cnt[head[j] + 1];
+          }
+        uint32_t* lp = nl_ptr.data() + (size_t)c * (p + 1);
+        const uint32_t base = (uint32_t)nl_ent.size();
+        lp[0] = base;
+        for (size_t u = 0; u < p; ++u) lp[u + 1] = lp[u] + cnt[u + 1];
+        nl_ent.resize(lp[p]);
+        std::vector<uint32_t> fill(lp, lp + p);
+        for (size_t j = lo; j < hi; ++j)
+          if (tail[j] != head[j]) {
+            nl_ent[fill[tail[j]]++] = (uint16_t)(j - lo);
+            nl_ent[fill[head[j]]++] = (uint16_t)((j - lo) | 0x8000u);
+          }
+        nl_long_ptr[c] = (uint32_t)nl_long.size();
+        for (size_t u = 0; u < p; ++u)
+          if (lp[u + 1] - lp[u] > tpl::kLongList) nl_long.push_back((uint32_t)u);
+        max_long = std::max<uint32_t>(max_long, (uint32_t)nl_long.size() - nl_long_ptr[c]);
+      }
+      nl_long_ptr[G] = (uint32_t)nl_long.size();
+      op->res.max_long = std::max<uint32_t>(max_long, 1);
+      rc = dev_upload(op, &op->res.nl_ptr, nl_ptr);
+      if (!rc) rc = dev_upload(op, &op->res.nl_ent, nl_ent);
+      if (!rc) rc = dev_upload(op, &op->res.nl_long_ptr, nl_long_ptr);
+      if (!rc) rc = dev_upload(op, &op->res.nl_long, nl_long);
+      if (!rc) rc = dev_alloc(op, &op->res.partials, 2 * (size_t)G * G * op->res.R);
+      if (!rc) rc = dev_alloc(op, &op->res.nodebuf, 2 * p);
+      op->resident_ok = !rc;
+    }
+  }
   const size_t seg_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
   op->inc.stage_nodes = (p * sizeof(double) + seg_bytes <= kSmemBudget) ? 1 : 0;
   op->smem_bytes = seg_bytes + (op->inc.stage_nodes ? p * sizeof(double) : 0);
@@ -465,8 +542,40 @@ int tpl_op_set_stream(tpl_op* op, void* cuda_stream) {
   return TPL_OK;
 }
 
+int tpl_op_trace_enable(tpl_op* op, size_t max_steps) {
+  if (!op) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  if (op->trace_d) {
+    if (int rc = dev_free(op, op->trace_d)) return rc;
+    op->trace_d = nullptr;
+    op->trace_steps = 0;
+  }
+  if (max_steps == 0) return TPL_OK;
+  const size_t words = (size_t)op->G * max_steps * tpl::kTraceMarks;
+  if (int rc = dev_alloc(op, &op->trace_d, words)) return rc;
+  CUDA_TRY(cudaMemset(op->trace_d, 0, words * sizeof(unsigned long long)));
+  op->trace_steps = (int)max_steps;
+  return TPL_OK;
+}
+
+int tpl_op_trace_read(tpl_op* op, uint64_t* out, size_t capacity, size_t* ctas, size_t* steps, size_t* marks) {
+  if (!op || !ctas || !steps || !marks) return fail(TPL_ERR_PANIC, "null argument");
+  DeviceGuard g(op->device);
+  *ctas = (size_t)op->G;
+  *steps = (size_t)op->trace_steps;
+  *marks = (size_t)tpl::kTraceMarks;
+  const size_t words = *ctas * *steps * *marks;
+  if (!out) return TPL_OK;  // size query
+  if (capacity < words) return tpl::fail_parameter_mismatch("out", words, capacity);
+  if (!words) return TPL_OK;
+  CUDA_TRY(cudaStreamSynchronize(op->stream));
+  CUDA_TRY(cudaMemcpy(out, op->trace_d, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(op->trace_d, 0, words * sizeof(unsigned long long)));
+  return TPL_OK;
+}
+
 int tpl_op_set_mode(tpl_op* op, int mode) {
-  if (!op || mode < 0 || mode > 1) return fail(TPL_ERR_PANIC, "invalid mode");
+  if (!op || mode < 0 || mode > 2) return fail(TPL_ERR_PANIC, "invalid mode");
   op->mode = mode;
   return TPL_OK;
 }
@@ -492,17 +601,32 @@ int tpl_op_last_timing(const tpl_op* op, double* pass_one_ms, double* pass_two_m
 // ============================================================================ launches
 namespace {
 
-template <class KERNEL, class OP, class ARGS>
-int launch_coop(tpl_op* op, KERNEL kernel, const OP& dop, const ARGS& args) {
-  void* params[] = {const_cast<OP*>(&dop), const_cast<ARGS*>(&args)};
+template <class KERNEL, class ARGS>
+int launch_resident(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
+  void* params[] = {&op->inc, &op->res, const_cast<ARGS*>(&args)};
   CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->G), dim3(tpl::kBlock), params,
-                                       op->smem_bytes, op->stream));
+                                       smem, op->stream));
   op->launches += 1;
   return TPL_OK;
 }
 
-int launch_pass1(tpl_op* op, const tpl::Pass1Args& a) {
+template <class KERNEL, class OP, class ARGS>
+int launch_coop(tpl_op* op, KERNEL kernel, const OP& dop, const ARGS& args, size_t smem = SIZE_MAX) {
+  void* params[] = {const_cast<OP*>(&dop), const_cast<ARGS*>(&args)};
+  CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->G), dim3(tpl::kBlock), params,
+                                       smem == SIZE_MAX ? op->smem_bytes : smem, op->stream));
+  op->launches += 1;
+  return TPL_OK;
+}
+
+// mode 0: resident kernels whenever the slice fits and the whole pass runs in one launch
+bool use_resident(const tpl_op* op) { return op->format == 2 && op->resident_ok && op->mode == 0; }
+
+int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   const bool with_v = a.V != nullptr;
+  if (whole_pass && use_resident(op))
+    return with_v ? launch_resident(op, tpl::pass1_resident_kernel<true>, a, op->smem_res1)
+                  : launch_resident(op, tpl::pass1_resident_kernel<false>, a, op->smem_res1);
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, false>, op->inc, a);
@@ -511,6 +635,9 @@ int launch_pass1(tpl_op* op, const tpl::Pass1Args& a) {
 }
 int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   const bool with_v = a.V != nullptr;
+  if (use_resident(op))
+    return with_v ? launch_resident(op, tpl::pass2_resident_kernel<true>, a, op->smem_res2)
+                  : launch_resident(op, tpl::pass2_resident_kernel<false>, a, op->smem_res2);
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, false>, op->inc, a);
@@ -535,7 +662,7 @@ int reset_sync_state(tpl_op* op) {
   st.s_prev = 1.0;
   st.status = tpl::ST_RUNNING;
   std::memcpy(op->h_pin, &st, sizeof st);
-  CUDA_TRY(cudaMemsetAsync(op->flags, 0, sizeof(unsigned int) * op->G, op->stream));
+  CUDA_TRY(cudaMemsetAsync(op->slots, 0, sizeof(uint4) * 2 * op->G, op->stream));
   CUDA_TRY(cudaMemcpyAsync(op->coef_d, op->h_pin, sizeof st, cudaMemcpyHostToDevice, op->stream));
   return TPL_OK;
 }
@@ -585,10 +712,10 @@ int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_
   a.tol = tpl::kBreakdownTol;
   int status = tpl::ST_RUNNING;
   CUDA_TRY(cudaEventRecord(op->ev[0], op->stream));
-  if (!cb && op->mode == 0) {
+  if (!cb && op->mode != 1) {
     a.j_begin = 0;
     a.j_end = (int)k;
-    if (int rc = launch_pass1(op, a)) return rc;
+    if (int rc = launch_pass1(op, a, true)) return rc;
     CUDA_TRY(cudaEventRecord(op->ev[1], op->stream));
     if (int rc = fetch_decomp(op, k, out, status)) return rc;
   } else {
@@ -596,7 +723,7 @@ int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_
     for (size_t j = 0; j < k; ++j) {
       a.j_begin = (int)j;
       a.j_end = (int)j + 1;
-      if (int rc = launch_pass1(op, a)) return rc;
+      if (int rc = launch_pass1(op, a, false)) return rc;
       if (!cb && j + 1 < k) continue;  // mode 1 without a callback: no host round trip needed
       if (int rc = fetch_decomp(op, k, out, status)) return rc;
       if (status != tpl::ST_RUNNING) break;

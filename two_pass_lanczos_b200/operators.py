@@ -91,6 +91,19 @@ class LinOp:
     def set_mode(self, mode: int):
         _lib.check(_lib.load().tpl_op_set_mode(self._h, mode))
 
+    def trace_enable(self, max_steps: int):
+        _lib.check(_lib.load().tpl_op_trace_enable(self._h, max_steps))
+
+    def trace_read(self) -> np.ndarray:
+        """uint64[ctas, steps, marks] phase timestamps of the last resident-kernel launches."""
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.load().tpl_op_trace_read(self._h, None, 0, C.byref(a), C.byref(b), C.byref(c)))
+        out = np.zeros((a.value, b.value, c.value), dtype=np.uint64)
+        if out.size:
+            _lib.check(_lib.load().tpl_op_trace_read(self._h, out.ctypes.data_as(_lib.c_u64p), out.size, C.byref(a),
+                                                     C.byref(b), C.byref(c)))
+        return out
+
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _lib.check(_lib.load().tpl_op_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
