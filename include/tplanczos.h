@@ -194,6 +194,9 @@ int tpl_comm_unique_id(uint8_t id_out[128]);
 int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end, const uint32_t* tail,
                             const uint32_t* head, const double* d, size_t d_len, int device, int rank,
                             int world, const uint8_t nccl_id[128], tpl_op** out);
+/* rank / world of a handle (0 / 1 for an unsharded one), its local arc count and the node count.  Vectors of a
+ * sharded handle are rank-local: [the rank's arc slice | all p node entries (replicated)], nrows() = local_arcs + p. */
+int tpl_op_shard_info(const tpl_op* op, int* rank, int* world, size_t* local_arcs, size_t* nodes);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ Python mirror of the reference crate's public surface (lukefleed/two-pass-lanczo
 
 All compute goes through the C ABI of libtplanczos.so (include/tplanczos.h); there is no CPU fallback.
 """
-from . import algorithms, data_loader, datagen, error, operators, solvers  # noqa: F401
+from . import algorithms, data_loader, datagen, error, operators, sharding, solvers  # noqa: F401
 from .error import CudaError, DataLoaderError, LanczosError  # noqa: F401
 from .operators import LinOp  # noqa: F401
 from .solvers import lanczos, lanczos_two_pass  # noqa: F401

@@ -4,6 +4,7 @@
 // around the persistent kernels of tpl_kernels.cuh.  No CPU fallback: every compute entry point needs a
 // CUDA device and fails with TPL_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -13,6 +14,7 @@
 
 #include "tpl_internal.h"
 #include "tpl_kernels.cuh"
+#include "tpl_sharded.cuh"
 
 // ============================================================================ errors
 namespace tpl {
@@ -51,6 +53,65 @@ using tpl::fail;
 
 extern "C" const char* tpl_last_error_message(void) { return tpl::g_err.c_str(); }
 extern "C" const char* tpl_version(void) { return "tplanczos 0.1 (sm_100a)"; }
+
+// ============================================================================ NCCL (bound at run time)
+// The communicator of the arc-partitioned multi-GPU mode is NCCL over NVLink.  libnccl.so.2 is resolved with dlopen
+// the first time a sharded operator is made, so that the library itself loads (and every single-GPU entry point
+// works) on hosts without NCCL, and so that a process that already carries an NCCL (e.g. the one bundled with
+// torch.distributed) shares that copy instead of loading a second one.
+namespace nccl {
+struct UniqueId {
+  char internal[128];
+};
+typedef struct ncclComm* Comm;
+typedef int Result;
+constexpr int kSum = 0, kFloat64 = 8;
+typedef Result (*GetUniqueIdFn)(UniqueId*);
+typedef Result (*CommInitRankFn)(Comm*, int, UniqueId, int);
+typedef Result (*CommDestroyFn)(Comm);
+typedef Result (*AllReduceFn)(const void*, void*, size_t, int, int, Comm, cudaStream_t);
+typedef const char* (*GetErrorStringFn)(Result);
+struct Api {
+  GetUniqueIdFn GetUniqueId = nullptr;
+  CommInitRankFn CommInitRank = nullptr;
+  CommDestroyFn CommDestroy = nullptr;
+  AllReduceFn AllReduce = nullptr;
+  GetErrorStringFn GetErrorString = nullptr;
+  bool ok = false;
+  std::string why;
+};
+static Api& api() {
+  static Api a = [] {
+    Api r;
+    void* h = nullptr;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (h) break;
+    }
+    if (!h) {
+      r.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown error");
+      return r;
+    }
+    r.GetUniqueId = (GetUniqueIdFn)dlsym(h, "ncclGetUniqueId");
+    r.CommInitRank = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
+    r.CommDestroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
+    r.AllReduce = (AllReduceFn)dlsym(h, "ncclAllReduce");
+    r.GetErrorString = (GetErrorStringFn)dlsym(h, "ncclGetErrorString");
+    r.ok = r.GetUniqueId && r.CommInitRank && r.CommDestroy && r.AllReduce && r.GetErrorString;
+    if (!r.ok) r.why = "libnccl.so.2 lacks a required symbol";
+    return r;
+  }();
+  return a;
+}
+}  // namespace nccl
+
+#define NCCL_TRY(expr)                                                                                       \
+  do {                                                                                                       \
+    nccl::Result r_ = (expr);                                                                                \
+    if (r_ != 0)                                                                                             \
+      return fail(TPL_ERR_COMM, "NCCL error: %s (%s) at %s:%d", nccl::api().GetErrorString(r_), #expr, __FILE__, \
+                  __LINE__);                                                                                 \
+  } while (0)
 
 // ============================================================================ handle
 namespace {
@@ -101,6 +162,11 @@ struct tpl_op {
   bool timed[3] = {false, false, false};
   uint64_t launches = 0;
   int mode = 0;
+  // arc-partitioned multi-GPU mode (world > 1): this handle holds rank `rank`'s arc block and a node replica
+  int rank = 0, world = 1;
+  nccl::Comm comm = nullptr;
+  double* red_d = nullptr;   // [2][p + 1] node sums + alpha partial (double-buffered for pass 2)
+  double* red2_d = nullptr;  // [1]
 
   tpl::State* st_d() const { return reinterpret_cast<tpl::State*>(coef_d); }
   double* alphas_d() const { return coef_d + kHeaderDoubles; }
@@ -326,6 +392,7 @@ void tpl_op_free(tpl_op* op) {
   if (!op) return;
   DeviceGuard g(op->device);
   if (op->stream) cudaStreamSynchronize(op->stream);
+  if (op->comm) nccl::api().CommDestroy(op->comm);
   for (auto& a : op->allocs) cudaFree(a.first);
   if (op->h_pin) cudaFreeHost(op->h_pin);
   for (auto& ev : op->ev)
@@ -692,6 +759,90 @@ int fetch_decomp(tpl_op* op, size_t k, Decomp& out, int& status) {
   return TPL_OK;
 }
 
+// ---------------------------------------------------------------- arc-partitioned (sharded) drivers
+template <class KERNEL>
+int launch_shard(tpl_op* op, KERNEL kernel, const tpl::ShardArgs& a, size_t smem) {
+  void* params[] = {&op->inc, const_cast<tpl::ShardArgs*>(&a)};
+  CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->G), dim3(tpl::kBlock), params, smem,
+                                       op->stream));
+  op->launches += 1;
+  return TPL_OK;
+}
+int shard_allreduce(tpl_op* op, double* buf, size_t count) {
+  NCCL_TRY(nccl::api().AllReduce(buf, buf, count, nccl::kFloat64, nccl::kSum, op->comm, op->stream));
+  return TPL_OK;
+}
+tpl::ShardArgs shard_args(tpl_op* op, const double* b_dev) {
+  tpl::ShardArgs a{};
+  for (int i = 0; i < 3; ++i) a.buf[i] = op->buf[i];
+  a.b = b_dev;
+  a.alphas = op->alphas_d();
+  a.betas = op->betas_d();
+  a.y = op->y_d();
+  a.red = op->red_d;
+  a.red_in = op->red_d;
+  a.red2 = op->red2_d;
+  a.st = op->st_d();
+  a.gs = op->gs();
+  a.tol = tpl::kBreakdownTol;
+  return a;
+}
+
+// Pass 1 / basis generation on rank-local slices: 2 launches + 2 all-reduces per step, all asynchronous; breakdown is
+// detected on the device (later launches return at once), the host reads the state back once at the end.
+int run_pass_one_sharded(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_t ldv, tpl::ShardArgs a) {
+  const size_t p1 = (size_t)op->inc.p + 1;
+  a.V = V_dev;
+  a.ldv = ldv;
+  if (int rc = launch_shard(op, tpl::shard_init_kernel, a, 0)) return rc;
+  if (int rc = shard_allreduce(op, op->red2_d, 1)) return rc;
+  for (size_t j = 0; j <= k; ++j) {
+    a.j = (int)j;
+    a.head_only = j == k;
+    if (int rc = V_dev ? launch_shard(op, tpl::shard_phase_a_kernel<true>, a, op->smem_bytes)
+                       : launch_shard(op, tpl::shard_phase_a_kernel<false>, a, op->smem_bytes))
+      return rc;
+    if (j == k) break;
+    if (int rc = shard_allreduce(op, op->red_d, p1)) return rc;
+    if (int rc = launch_shard(op, tpl::shard_phase_b_kernel, a, 0)) return rc;
+    if (int rc = shard_allreduce(op, op->red2_d, 1)) return rc;
+  }
+  return TPL_OK;
+}
+
+int run_pass_two_sharded(tpl_op* op, size_t steps, double b_norm, double* x_dev, double* V_dev, size_t ldv,
+                         tpl::ShardArgs a) {
+  const size_t p1 = (size_t)op->inc.p + 1;
+  a.x = x_dev;
+  a.V = V_dev;
+  a.ldv = ldv;
+  a.steps = (int)steps;
+  a.b_norm = b_norm;
+  a.j = -1;
+  auto launch = [&]() {
+    return V_dev ? launch_shard(op, tpl::shard_pass2_kernel<true>, a, op->smem_bytes)
+                 : launch_shard(op, tpl::shard_pass2_kernel<false>, a, op->smem_bytes);
+  };
+  if (int rc = launch()) return rc;
+  for (size_t j = 0; j + 1 < steps; ++j) {
+    a.j = (int)j;
+    a.head_only = 0;
+    a.red = op->red_d + (j & 1) * p1;
+    a.red_in = op->red_d + ((j + 1) & 1) * p1;
+    if (int rc = launch()) return rc;
+    if (int rc = shard_allreduce(op, a.red, p1)) return rc;
+  }
+  if (steps > 1) {
+    const size_t j = steps - 1;
+    a.j = (int)j;
+    a.head_only = 1;
+    a.red = op->red_d + (j & 1) * p1;
+    a.red_in = op->red_d + ((j + 1) & 1) * p1;
+    if (int rc = launch()) return rc;
+  }
+  return TPL_OK;
+}
+
 // lanczos_pass_one / basis generation of lanczos_standard on a device-resident b.
 int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_t ldv, tpl_step_callback cb,
                  void* user, Decomp& out) {
@@ -712,7 +863,12 @@ int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_
   a.tol = tpl::kBreakdownTol;
   int status = tpl::ST_RUNNING;
   CUDA_TRY(cudaEventRecord(op->ev[0], op->stream));
-  if (!cb && op->mode != 1) {
+  if (op->comm) {
+    if (cb) return fail(TPL_ERR_COMM, "step callbacks are not supported on a sharded operator");
+    if (int rc = run_pass_one_sharded(op, b_dev, k, V_dev, ldv, shard_args(op, b_dev))) return rc;
+    CUDA_TRY(cudaEventRecord(op->ev[1], op->stream));
+    if (int rc = fetch_decomp(op, k, out, status)) return rc;
+  } else if (!cb && op->mode != 1) {
     a.j_begin = 0;
     a.j_end = (int)k;
     if (int rc = launch_pass1(op, a, true)) return rc;
@@ -772,7 +928,11 @@ int run_pass_two(tpl_op* op, const double* b_dev, const double* alphas, const do
   a.st = op->st_d();
   a.gs = op->gs();
   CUDA_TRY(cudaEventRecord(op->ev[2], op->stream));
-  if (int rc = launch_pass2(op, a)) return rc;
+  if (op->comm) {
+    if (int rc = run_pass_two_sharded(op, steps, b_norm, x_dev, V_dev, ldv, shard_args(op, b_dev))) return rc;
+  } else if (int rc = launch_pass2(op, a)) {
+    return rc;
+  }
   CUDA_TRY(cudaEventRecord(op->ev[3], op->stream));
   op->timed[1] = true;
   return TPL_OK;
@@ -855,6 +1015,8 @@ int tpl_op_apply(tpl_op* op, const double* x, double* y) {
     tpl::apply_kernel<tpl::CsrOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->csr, x_dev, y_dev);
   CUDA_TRY(cudaGetLastError());
   op->launches += 1;
+  if (op->comm)  // node rows of the local operator are partial sums over this rank's arcs
+    if (int rc = shard_allreduce(op, y_dev + op->inc.m, op->inc.p)) return rc;
   return finish_x(op, y_dev, y);
 }
 
@@ -976,14 +1138,66 @@ int tpl_lanczos_two_pass(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f
   return finish_x(op, x_dev, x);
 }
 
-// ---------------------------------------------------------------------------- multi-GPU (stage 7)
+// ---------------------------------------------------------------------------- multi-GPU
 int tpl_comm_unique_id(uint8_t id_out[128]) {
-  (void)id_out;
-  return fail(TPL_ERR_COMM, "communicator support is not built into this library yet");
+  tpl::clear_error();
+  if (!id_out) return fail(TPL_ERR_PANIC, "null argument");
+  if (!nccl::api().ok) return fail(TPL_ERR_COMM, "NCCL error: %s", nccl::api().why.c_str());
+  nccl::UniqueId id;
+  NCCL_TRY(nccl::api().GetUniqueId(&id));
+  std::memcpy(id_out, id.internal, 128);
+  return TPL_OK;
 }
-int tpl_op_from_kkt_sharded(size_t, size_t, size_t, size_t, const uint32_t*, const uint32_t*, const double*, size_t, int,
-                            int, int, const uint8_t[128], tpl_op**) {
-  return fail(TPL_ERR_COMM, "communicator support is not built into this library yet");
+
+int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end, const uint32_t* tail,
+                            const uint32_t* head, const double* d, size_t d_len, int device, int rank, int world,
+                            const uint8_t nccl_id[128], tpl_op** out) {
+  tpl::clear_error();
+  if (!out || !nccl_id || (m && (!tail || !head)) || (d_len && !d)) return fail(TPL_ERR_PANIC, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(TPL_ERR_COMM, "invalid rank %d of %d", rank, world);
+  if (arc_begin > arc_end || arc_end > m)
+    return tpl::fail_parameter_mismatch("arc_end", m, arc_end);
+  if (d_len > m) return tpl::fail_parameter_mismatch("d", m, d_len);
+  if (!nccl::api().ok) return fail(TPL_ERR_COMM, "NCCL error: %s", nccl::api().why.c_str());
+  const size_t m_r = arc_end - arc_begin;
+  const size_t d_local = d_len > arc_begin ? std::min(d_len - arc_begin, m_r) : 0;
+  tpl_op* op = nullptr;
+  if (int rc = tpl_op_from_kkt(m_r, p, tail ? tail + arc_begin : nullptr, head ? head + arc_begin : nullptr,
+                               d_local ? d + arc_begin : nullptr, d_local, device, &op))
+    return rc;
+  auto bail = [&](int rc) {
+    std::string keep = tpl::g_err;
+    tpl_op_free(op);
+    tpl::g_err = keep;
+    return rc;
+  };
+  DeviceGuard g(op->device);
+  if (!op->inc.stage_nodes)
+    return bail(fail(TPL_ERR_COMM, "sharded mode needs the node segment (%zu doubles) to fit in shared memory", p));
+  op->resident_ok = false;
+  op->rank = rank;
+  op->world = world;
+  if (int rc = dev_alloc(op, &op->red_d, 2 * (p + 1))) return bail(rc);
+  if (int rc = dev_alloc(op, &op->red2_d, 1)) return bail(rc);
+  if (cudaMemset(op->red_d, 0, sizeof(double) * 2 * (p + 1)) != cudaSuccess) return bail(fail(TPL_ERR_CUDA, "CUDA error: memset"));
+  if (set_smem(tpl::shard_phase_a_kernel<false>, op->smem_bytes) || set_smem(tpl::shard_phase_a_kernel<true>, op->smem_bytes) ||
+      set_smem(tpl::shard_pass2_kernel<false>, op->smem_bytes) || set_smem(tpl::shard_pass2_kernel<true>, op->smem_bytes))
+    return bail(TPL_ERR_CUDA);
+  nccl::UniqueId id;
+  std::memcpy(id.internal, nccl_id, 128);
+  nccl::Result r = nccl::api().CommInitRank(&op->comm, world, id, rank);
+  if (r != 0) return bail(fail(TPL_ERR_COMM, "NCCL error: %s (ncclCommInitRank)", nccl::api().GetErrorString(r)));
+  *out = op;
+  return TPL_OK;
+}
+
+int tpl_op_shard_info(const tpl_op* op, int* rank, int* world, size_t* local_arcs, size_t* nodes) {
+  if (!op) return fail(TPL_ERR_PANIC, "null argument");
+  if (rank) *rank = op->rank;
+  if (world) *world = op->world;
+  if (local_arcs) *local_arcs = op->format == 2 ? op->inc.m : 0;
+  if (nodes) *nodes = op->format == 2 ? op->inc.p : 0;
+  return TPL_OK;
 }
 
 }  // extern "C"

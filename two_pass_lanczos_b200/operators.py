@@ -109,6 +109,11 @@ class LinOp:
         _lib.check(_lib.load().tpl_op_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"pass_one_ms": a.value, "pass_two_ms": b.value, "gemv_ms": c.value}
 
+    def shard_info(self):
+        r, w, a, p = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.load().tpl_op_shard_info(self._h, C.byref(r), C.byref(w), C.byref(a), C.byref(p)))
+        return {"rank": r.value, "world": w.value, "local_arcs": a.value, "nodes": p.value}
+
     def kernel_launches(self) -> int:
         return _lib.load().tpl_op_kernel_launches(self._h)
 
