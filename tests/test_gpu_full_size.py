@@ -125,5 +125,10 @@ def test_orthogonality_harness(func, scenario):
         assert loss_std == loss_regen
         assert np.linalg.norm(p2.x_k) == 0.0  # dummy y = 0 (orthogonality.rs:185-187)
         losses[k] = loss_std
+    # soft golden curves: results/orthogonality_{exp_well,inv_ill}-conditioned.csv rows k = 20, 100, 400
+    published = {("exp", "well"): {20: 9.450129381865854e-15, 100: 6.200746375824939e-14, 400: 1.4341356746045474e-11},
+                 ("inv", "ill"): {20: 1.0e-14, 100: 3.00357411682582e-14, 400: 0.08480779566223172}}[(func, scenario)]
     assert losses[20] < 1e-13
-    assert losses[400] > 1e-3  # orthogonality is lost, as in the published curves
+    for k in (100, 400):  # same order of magnitude as the reference's curve (loss growth is chaotic in the last digits)
+        assert published[k] / 50.0 < losses[k] < published[k] * 50.0, (k, losses[k], published[k])
+    assert losses[400] > 10.0 * losses[20]  # orthogonality degrades with k, as in the published curves
