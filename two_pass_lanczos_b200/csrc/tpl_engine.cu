@@ -15,6 +15,7 @@
 #include "tpl_internal.h"
 #include "tpl_kernels.cuh"
 #include "tpl_sharded.cuh"
+#include "tpl_tiles.cuh"
 
 // ============================================================================ errors
 namespace tpl {
@@ -155,6 +156,9 @@ struct tpl_op {
   bool resident_ok = false;    // the per-CTA slice of the incidence operator fits in shared memory
   tpl::ResidentOp res{};
   size_t smem_res1 = 0, smem_res2 = 0;
+  bool tiled_ok = false;       // streaming kernels with tiled node sums are usable (shared-memory budget)
+  tpl::TileOp tile{};
+  size_t smem_tile1 = 0, smem_tile2 = 0;
   double* h_pin = nullptr;  // pinned mirror of coef_d
   double* V_int = nullptr;
   size_t V_int_elems = 0;
@@ -284,6 +288,83 @@ int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
   return TPL_OK;
 }
 
+// ---------------------------------------------------------------- tiled node-sum lists (tpl_tiles.cuh)
+struct HostTiles {
+  uint32_t T = 0, ntile = 0, npt = 0;
+  std::vector<uint32_t> lptr, lent, pptr, piece;
+};
+
+void build_tiles(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int G, uint32_t T, HostTiles& h) {
+  const size_t A = (m + G - 1) / G;
+  h.T = T;
+  h.ntile = (uint32_t)std::max<size_t>(1, (A + T - 1) / T);
+  h.npt = (uint32_t)std::max<size_t>(1, (p + tpl::kBlock - 1) / tpl::kBlock);
+  const size_t ntiles = (size_t)G * h.ntile;
+  h.lptr.assign(ntiles * (tpl::kBlock + 1), 0);
+  h.pptr.assign(ntiles + 1, 0);
+  h.lent.clear();
+  h.lent.reserve(2 * m);
+  h.piece.clear();
+  std::vector<uint32_t> cnt(p + 1), e_node, e_code, order;
+  for (int c = 0; c < G; ++c) {
+    const size_t lo = std::min(m, A * (size_t)c), hi = std::min(m, lo + A);
+    for (uint32_t t = 0; t < h.ntile; ++t) {
+      const size_t tile_id = (size_t)c * h.ntile + t;
+      const size_t t0 = std::min(hi, lo + (size_t)t * T), t1 = std::min(hi, t0 + T);
+      h.pptr[tile_id] = (uint32_t)h.piece.size();
+      e_node.clear();
+      e_code.clear();
+      uint32_t npieces = 0;
+      for (size_t i = t0; i < t1;) {  // tail side: maximal runs of equal tail (self-loops contribute nothing)
+        if (tail[i] == head[i]) {
+          ++i;
+          continue;
+        }
+        size_t j = i;
+        while (j < t1 && tail[j] == tail[i] && tail[j] != head[j]) ++j;
+        const size_t len = j - i;
+        const size_t need = (len + tpl::kPieceMax - 1) / tpl::kPieceMax;
+        if (len >= tpl::kPieceMin && npieces + need <= tpl::kMaxPieces) {
+          for (size_t q = i; q < j; q += tpl::kPieceMax) {
+            const uint32_t l = (uint32_t)std::min<size_t>(tpl::kPieceMax, j - q);
+            h.piece.push_back((uint32_t)(q - t0) | ((l - 1) << 16));
+            e_node.push_back(tail[i]);
+            e_code.push_back(T + npieces);
+            ++npieces;
+          }
+        } else {
+          for (size_t q = i; q < j; ++q) {
+            e_node.push_back(tail[i]);
+            e_code.push_back((uint32_t)(q - t0));
+          }
+        }
+        i = j;
+      }
+      for (size_t i = t0; i < t1; ++i)  // head side
+        if (tail[i] != head[i]) {
+          e_node.push_back(head[i]);
+          e_code.push_back((uint32_t)(i - t0) | 0x8000u);
+        }
+      // stable counting sort by node: per node the tail entries come first (ascending index), then the head entries
+      const size_t ne = e_node.size();
+      std::fill(cnt.begin(), cnt.end(), 0u);
+      for (size_t e = 0; e < ne; ++e) ++cnt[e_node[e] + 1];
+      for (size_t u = 0; u < p; ++u) cnt[u + 1] += cnt[u];
+      uint32_t* lp = h.lptr.data() + tile_id * (tpl::kBlock + 1);
+      const uint32_t base = (uint32_t)h.lent.size();
+      for (int i = 0; i <= tpl::kBlock; ++i) lp[i] = base + cnt[std::min<size_t>(p, (size_t)i * h.npt)];
+      h.lent.resize(base + ne);
+      order.assign(cnt.begin(), cnt.end() - 1);
+      for (size_t e = 0; e < ne; ++e) {
+        const uint32_t u = e_node[e];
+        const uint32_t owner = u / h.npt;
+        h.lent[base + order[u]++] = ((u - owner * h.npt) << 16) | e_code[e];
+      }
+    }
+  }
+  h.pptr[ntiles] = (uint32_t)h.piece.size();
+}
+
 template <class K>
 int set_smem(K kernel, size_t bytes) {
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -367,6 +448,16 @@ int finish_setup(tpl_op* op) {
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r2, tpl::pass2_resident_kernel<true>, tpl::kBlock,
                                                              op->smem_res2));
       if (r1 < 1 || r2 < 1) op->resident_ok = false;
+    }
+    if (op->tiled_ok) {
+      if (int rc = set_smem(tpl::pass1_tiled_kernel<false>, op->smem_tile1)) return rc;
+      if (int rc = set_smem(tpl::pass1_tiled_kernel<true>, op->smem_tile1)) return rc;
+      if (int rc = set_smem(tpl::pass2_tiled_kernel<false>, op->smem_tile2)) return rc;
+      if (int rc = set_smem(tpl::pass2_tiled_kernel<true>, op->smem_tile2)) return rc;
+      int t1 = 0, t2 = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t1, tpl::pass1_tiled_kernel<true>, tpl::kBlock, op->smem_tile1));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t2, tpl::pass2_tiled_kernel<true>, tpl::kBlock, op->smem_tile2));
+      if (t1 < 1 || t2 < 1) op->tiled_ok = false;
     }
   } else {
     if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, false>, smem)) return rc;
@@ -564,6 +655,34 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       op->resident_ok = !rc;
     }
   }
+  // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of kUnroll * kBlock arcs, at most
+  // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
+  if (!rc && p >= 1 && p <= 0xffffull * tpl::kBlock) {
+    int max_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
+    const long budget = (long)max_optin - 2048 - (long)(2 * p + tpl::kMaxPieces) * 8;
+    const uint32_t step = tpl::kUnroll * tpl::kBlock;
+    uint32_t T = budget > 0 ? (uint32_t)std::min<long>(16384, budget / 8 / step * step) : 0;
+    const size_t A = (m + op->G - 1) / op->G;
+    if (T >= step) {
+      T = (uint32_t)std::min<size_t>(T, std::max<size_t>(step, (A + step - 1) / step * step));
+      HostTiles ht;
+      build_tiles(m, p, tail, head, op->G, T, ht);
+      op->tile.T = ht.T;
+      op->tile.ntile = ht.ntile;
+      op->tile.npt = ht.npt;
+      op->tile.R = (uint32_t)std::max<size_t>(1, (p + op->G - 1) / op->G);
+      rc = dev_upload(op, &op->tile.lptr, ht.lptr);
+      if (!rc) rc = dev_upload(op, &op->tile.lent, ht.lent);
+      if (!rc) rc = dev_upload(op, &op->tile.pptr, ht.pptr);
+      if (!rc) rc = dev_upload(op, &op->tile.piece, ht.piece);
+      if (!rc) rc = dev_alloc(op, &op->tile.partials, 2 * (size_t)op->G * p);
+      if (!rc) rc = dev_alloc(op, &op->tile.nodebuf, 2 * p);
+      op->smem_tile1 = tpl::tile_smem_bytes((uint32_t)p, T, false);
+      op->smem_tile2 = tpl::tile_smem_bytes((uint32_t)p, T, true);
+      op->tiled_ok = !rc;
+    }
+  }
   const size_t seg_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
   op->inc.stage_nodes = (p * sizeof(double) + seg_bytes <= kSmemBudget) ? 1 : 0;
   op->smem_bytes = seg_bytes + (op->inc.stage_nodes ? p * sizeof(double) : 0);
@@ -642,7 +761,7 @@ int tpl_op_trace_read(tpl_op* op, uint64_t* out, size_t capacity, size_t* ctas, 
 }
 
 int tpl_op_set_mode(tpl_op* op, int mode) {
-  if (!op || mode < 0 || mode > 2) return fail(TPL_ERR_PANIC, "invalid mode");
+  if (!op || mode < 0 || mode > 3) return fail(TPL_ERR_PANIC, "invalid mode");
   op->mode = mode;
   return TPL_OK;
 }
@@ -686,14 +805,28 @@ int launch_coop(tpl_op* op, KERNEL kernel, const OP& dop, const ARGS& args, size
   return TPL_OK;
 }
 
-// mode 0: resident kernels whenever the slice fits and the whole pass runs in one launch
+// mode 0: resident kernels whenever the slice fits and the whole pass runs in one launch; otherwise (and in mode 2) the
+// streaming kernels with tiled node sums; mode 3 (and any operator the tiles do not fit) the gather kernels
 bool use_resident(const tpl_op* op) { return op->format == 2 && op->resident_ok && op->mode == 0; }
+bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op->mode == 0 || op->mode == 2); }
+
+template <class KERNEL, class ARGS>
+int launch_tiled(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
+  void* params[] = {&op->inc, &op->tile, const_cast<ARGS*>(&args)};
+  CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->G), dim3(tpl::kBlock), params,
+                                       smem, op->stream));
+  op->launches += 1;
+  return TPL_OK;
+}
 
 int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   const bool with_v = a.V != nullptr;
   if (whole_pass && use_resident(op))
     return with_v ? launch_resident(op, tpl::pass1_resident_kernel<true>, a, op->smem_res1)
                   : launch_resident(op, tpl::pass1_resident_kernel<false>, a, op->smem_res1);
+  if (whole_pass && use_tiled(op))
+    return with_v ? launch_tiled(op, tpl::pass1_tiled_kernel<true>, a, op->smem_tile1)
+                  : launch_tiled(op, tpl::pass1_tiled_kernel<false>, a, op->smem_tile1);
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, false>, op->inc, a);
@@ -705,6 +838,9 @@ int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   if (use_resident(op))
     return with_v ? launch_resident(op, tpl::pass2_resident_kernel<true>, a, op->smem_res2)
                   : launch_resident(op, tpl::pass2_resident_kernel<false>, a, op->smem_res2);
+  if (use_tiled(op))
+    return with_v ? launch_tiled(op, tpl::pass2_tiled_kernel<true>, a, op->smem_tile2)
+                  : launch_tiled(op, tpl::pass2_tiled_kernel<false>, a, op->smem_tile2);
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, false>, op->inc, a);

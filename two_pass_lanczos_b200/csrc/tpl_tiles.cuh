@@ -1,0 +1,435 @@
+// tpl_tiles.cuh -- streaming kernels of the KKT incidence operator with TILED node sums (any size that fits the
+// shared-memory budget below; the gather kernels of tpl_kernels.cuh stay as the generic fallback and the CSR path).
+//
+// Why: the node rows of A = [[D, E^T], [E, 0]] are sums over ~2m/p arc values each.  Gathering them from HBM through a
+// node -> arc list costs one 32-byte sector per 8-byte value (measured: 24-33 % of the HBM roofline at 5M-50M arcs).
+// Here every CTA instead forms the PARTIAL node sums of its own contiguous arc chunk while the freshly computed arc
+// values are still in shared memory:
+//   * the chunk is cut into tiles of T arcs; a tile's values are written to shared memory as they are produced;
+//   * thread i of the CTA owns nodes [i*npt, (i+1)*npt) and walks, per tile, its own slice of a host-built entry list
+//     sorted by node: entry = (node offset, +-, index into the tile), adding into a private slice of a p-long
+//     shared-memory accumulator (no atomics, fixed order);
+//   * runs of >= 32 consecutive arcs with the same tail (netgen emits arcs grouped by tail) are summed by one warp as a
+//     "piece" (lane-strided + xor tree) whose result is appended to the tile as a virtual arc, so that the walk treats
+//     it like any other entry; instances without such runs simply have every tail in the entry list.
+//   * after the last tile the p partial sums of the CTA go to HBM once per step ([G][p] doubles, ~0.3 % of the step's
+//     traffic); after the grid barrier that the step needs anyway, the owner of a node block adds the G partials in a
+//     fixed order.
+// Per step the operator costs 16 B/arc (d, tail, head) + 4..8 B/arc (entries) of coalesced HBM traffic, which is the
+// algorithmic figure of SURVEY 8d (B_inc = 24m + 4p).  Summation order depends only on the operator and the grid, so
+// pass 1, the one-pass variant and pass 2 still produce bit-identical basis vectors.
+#pragma once
+#include "tpl_kernels.cuh"
+
+namespace tpl {
+
+constexpr uint32_t kPieceMin = 32;     // shortest same-tail run summed as a piece
+constexpr uint32_t kPieceMax = 1024;   // longest piece (longer runs are split at fixed offsets)
+constexpr uint32_t kMaxPieces = 512;   // per tile (shared-memory slots after the T arc values)
+constexpr int kUnroll = 4;             // arcs per thread per batch of the streaming loops
+
+struct TileOp {
+  uint32_t T;         // arcs per tile
+  uint32_t ntile;     // tiles per CTA chunk
+  uint32_t npt;       // nodes per thread
+  uint32_t R;         // node rows per owner block = ceil(p / G)
+  const uint32_t* lptr;   // [G * ntile][kBlock + 1] entry ranges (per tile, per owning thread)
+  const uint32_t* lent;   // entries: node offset << 16 | minus << 15 | index into the tile (arcs, then pieces)
+  const uint32_t* pptr;   // [G * ntile + 1] piece ranges
+  const uint32_t* piece;  // first | (len - 1) << 16
+  double* partials;       // [2][G][p]  per-CTA partial node sums (double-buffered by step parity)
+  double* nodebuf;        // [2][p]     node part of the newest vector as published by the owners (un-normalised)
+};
+
+struct TileSmem {
+  double* node;  // [p]  scaled node segment of the current vector (phases that form arc rows)
+  double* acc;   // [p]  partial node sums of this CTA            (phases that produce a new vector)
+  double* wt;    // [T + kMaxPieces] arc values of the current tile + piece sums
+};
+// pass 1 never needs node and acc at the same time (they alias); pass 2 needs both.
+__host__ __device__ inline size_t tile_smem_bytes(uint32_t p, uint32_t T, bool pass2) {
+  return ((pass2 ? 2 : 1) * (size_t)p + T + kMaxPieces) * sizeof(double);
+}
+__device__ __forceinline__ TileSmem carve_tiles(double* base, uint32_t p, bool pass2) {
+  TileSmem s;
+  s.node = base;
+  s.acc = pass2 ? base + p : base;
+  s.wt = s.acc + p;
+  return s;
+}
+
+// Adds the node sums of the tile held in s.wt[0 .. n_arcs) into s.acc.  Caller has synchronised after filling s.wt and
+// must synchronise before refilling it.
+__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, uint32_t tile_id) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t q0 = __ldg(to.pptr + tile_id), q1 = __ldg(to.pptr + tile_id + 1);
+  if (q1 > q0) {
+    for (uint32_t q = q0 + warp; q < q1; q += kWarps) {
+      const uint32_t pc = __ldg(to.piece + q);
+      const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
+      double a = 0.0;
+      for (uint32_t e = lane; e < len; e += 32) a = __dadd_rn(a, s.wt[first + e]);
+      a = warp_sum(a);
+      if (lane == 0) s.wt[to.T + (q - q0)] = a;
+    }
+    __syncthreads();
+  }
+  const uint32_t* lp = to.lptr + (size_t)tile_id * (kBlock + 1) + threadIdx.x;
+  const uint32_t e0 = __ldg(lp), e1 = __ldg(lp + 1);
+  double* mine = s.acc + (size_t)threadIdx.x * to.npt;
+  uint32_t cur = 0xffffffffu;
+  double r = 0.0;
+  for (uint32_t e = e0; e < e1; ++e) {
+    const uint32_t ent = __ldg(to.lent + e);
+    const uint32_t off = ent >> 16;
+    const double val = s.wt[ent & 0x7fffu];
+    if (off != cur) {
+      if (cur != 0xffffffffu) mine[cur] = r;
+      cur = off;
+      r = mine[off];
+    }
+    r = (ent & 0x8000u) ? __dsub_rn(r, val) : __dadd_rn(r, val);
+  }
+  if (cur != 0xffffffffu) mine[cur] = r;
+}
+
+struct TileCtx {
+  uint32_t alo, ahi;  // owned arcs
+  uint32_t ulo, uhi;  // owned node rows (node index)
+};
+__device__ __forceinline__ TileCtx tile_ctx(const IncidenceOp& op, const TileOp& to) {
+  TileCtx c;
+  cta_chunk(op.m, c.alo, c.ahi);
+  c.ulo = min(op.p, blockIdx.x * to.R);
+  c.uhi = min(op.p, c.ulo + to.R);
+  return c;
+}
+
+// writes this CTA's p partial sums (s.acc) to HBM; caller synchronised before
+__device__ __forceinline__ void publish_tile_partials(const IncidenceOp& op, const TileSmem& s, double* Pout) {
+  double* mine = Pout + (size_t)blockIdx.x * op.p;
+  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) __stcg(mine + u, s.acc[u]);
+}
+// T_u = sum over the G partials in a fixed order (one warp per owned node, lanes stride the CTAs, xor tree)
+__device__ __forceinline__ double tile_node_total(const IncidenceOp& op, const double* Pin, uint32_t u, int lane) {
+  double a = 0.0;
+  for (uint32_t c = lane; c < gridDim.x; c += 32) a = __dadd_rn(a, __ldcg(Pin + (size_t)c * op.p + u));
+  return warp_sum(a);
+}
+
+// node partial sums of an arbitrary arc vector X (init: b) over the CTA's chunk, tile by tile
+__device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp& to, const TileSmem& s, const TileCtx& c,
+                                             const double* X) {
+  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) s.acc[u] = 0.0;
+  for (uint32_t t = 0; t < to.ntile; ++t) {
+    const uint32_t t0 = c.alo + t * to.T;
+    if (t0 >= c.ahi) break;
+    const uint32_t t1 = min(c.ahi, t0 + to.T);
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += kBlock) s.wt[i - t0] = __ldg(X + i);
+    __syncthreads();
+    tile_node_sums(to, s, blockIdx.x * to.ntile + t);
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
+// pass 1 / one-pass basis generation, streaming with tiled node sums (single GPU, persistent, cooperative)
+// =============================================================================================
+template <bool WITH_V>
+__global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceOp op, const TileOp to, const Pass1Args a) {
+  extern __shared__ double smem[];
+  __shared__ CtaShared sh;
+  const TileSmem s = carve_tiles(smem, op.p, false);
+  const TileCtx c = tile_ctx(op, to);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t m = op.m, p = op.p;
+  const size_t pstride = (size_t)gridDim.x * p;
+
+  unsigned int epoch = a.st->epoch;
+  int steps = 0, status = ST_RUNNING, rot = 0;
+  double sc = 1.0, sp = 1.0, bp = 0.0, bnorm = 0.0;
+  double* const buf0 = a.buf[0];
+  double* const buf1 = a.buf[1];
+  double* const buf2 = a.buf[2];
+  auto pick = [&](int r) { return r == 0 ? buf0 : (r == 1 ? buf1 : buf2); };
+  {
+    // K0: ||b||, W_cur = b, W_prev = 0, partial node sums of b for step 0
+    double* Wp = pick(0);
+    double* Wc = pick(1);
+    double acc = 0.0;
+    for (uint32_t i = c.alo + threadIdx.x; i < c.ahi; i += kBlock) {
+      const double bi = __ldg(a.b + i);
+      __stcg(Wc + i, bi);
+      __stcg(Wp + i, 0.0);
+      acc = fma(bi, bi, acc);
+    }
+    for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
+      const double bi = __ldg(a.b + m + u);
+      __stcg(Wc + m + u, bi);
+      __stcg(Wp + m + u, 0.0);
+      __stcg(to.nodebuf + p + u, bi);  // parity of "step -1"
+      acc = fma(bi, bi, acc);
+    }
+    tile_sums_of(op, to, s, c, a.b);
+    publish_tile_partials(op, s, to.partials);
+    bnorm = sqrt(grid_sync<true>(acc, a.gs, epoch, sh));
+    if (bnorm <= a.tol) status = ST_ZERO_B;
+    sc = 1.0 / bnorm;
+  }
+  if (status == ST_RUNNING) {
+    for (int j = 0; j < a.j_end; ++j) {
+      const double* Wp = pick(rot);
+      const double* Wc = pick((rot + 1) % 3);
+      double* Wn = pick((rot + 2) % 3);
+      const double* Xnode = to.nodebuf + (size_t)((j + 1) & 1) * p;  // node part of the current vector
+      double* Nout = to.nodebuf + (size_t)(j & 1) * p;
+      const double* Pin = to.partials + (size_t)(j & 1) * pstride;
+      double* Pout = to.partials + (size_t)((j + 1) & 1) * pstride;
+      double* Vcol = WITH_V ? a.V + (size_t)j * a.ldv : nullptr;
+
+      // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
+      for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.node[u] = __dmul_rn(__ldcg(Xnode + u), sc);
+      __syncthreads();
+      double acc = 0.0;
+      for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
+        const double t = __dmul_rn(sc, tile_node_total(op, Pin, u, lane));
+        if (lane == 0) {
+          const double v = s.node[u];
+          const double vp = __dmul_rn(__ldcg(Wp + m + u), sp);
+          const double wt = rec_sub(t, bp, vp);
+          acc = fma(v, wt, acc);
+          __stcg(Wn + m + u, wt);
+          if (WITH_V) __stcs(Vcol + m + u, v);
+        }
+      }
+      for (uint32_t base = c.alo; base < c.ahi; base += kUnroll * kBlock) {
+        double wc[kUnroll], wp[kUnroll], dd[kUnroll];
+        uint32_t tl[kUnroll], hd[kUnroll];
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = base + q * kBlock + threadIdx.x;
+          if (i < c.ahi) {
+            wc[q] = __ldcg(Wc + i);
+            wp[q] = __ldcg(Wp + i);
+            dd[q] = __ldg(op.d + i);
+            tl[q] = __ldg(op.tail + i);
+            hd[q] = __ldg(op.head + i);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = base + q * kBlock + threadIdx.x;
+          if (i < c.ahi) {
+            const double v = __dmul_rn(wc[q], sc);
+            const double vp = __dmul_rn(wp[q], sp);
+            const double wt = rec_sub(arc_row(dd[q], v, tl[q], hd[q], s.node[tl[q]], s.node[hd[q]]), bp, vp);
+            acc = fma(v, wt, acc);
+            __stcg(Wn + i, wt);
+            if (WITH_V) __stcs(Vcol + i, v);
+          }
+        }
+      }
+      const double alpha = grid_sync<true>(acc, a.gs, epoch, sh);
+
+      // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
+      acc = 0.0;
+      for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.acc[u] = 0.0;  // (aliases s.node: phase A is over)
+      for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
+        const double v = __dmul_rn(__ldcg(Wc + m + u), sc);
+        const double w = rec_sub(__ldcg(Wn + m + u), alpha, v);
+        __stcg(Wn + m + u, w);
+        __stcg(Nout + u, w);
+        acc = fma(w, w, acc);
+      }
+      for (uint32_t t = 0; t < to.ntile; ++t) {
+        const uint32_t t0 = c.alo + t * to.T;
+        if (t0 >= c.ahi) break;
+        const uint32_t t1 = min(c.ahi, t0 + to.T);
+        for (uint32_t base = t0; base < t1; base += kUnroll * kBlock) {
+          double wn[kUnroll], wc[kUnroll];
+#pragma unroll
+          for (int q = 0; q < kUnroll; ++q) {
+            const uint32_t i = base + q * kBlock + threadIdx.x;
+            if (i < t1) {
+              wn[q] = __ldcg(Wn + i);
+              wc[q] = __ldcg(Wc + i);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < kUnroll; ++q) {
+            const uint32_t i = base + q * kBlock + threadIdx.x;
+            if (i < t1) {
+              const double w = rec_sub(wn[q], alpha, __dmul_rn(wc[q], sc));
+              __stcg(Wn + i, w);
+              s.wt[i - t0] = w;
+              acc = fma(w, w, acc);
+            }
+          }
+        }
+        __syncthreads();
+        tile_node_sums(to, s, blockIdx.x * to.ntile + t);
+        __syncthreads();
+      }
+      publish_tile_partials(op, s, Pout);
+      const double beta = sqrt(grid_sync<true>(acc, a.gs, epoch, sh));
+
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.alphas[j] = alpha;
+        a.betas[j] = beta;
+      }
+      steps = j + 1;
+      if (beta <= a.tol) {
+        status = ST_BREAKDOWN;
+        break;
+      }
+      sp = sc;
+      sc = 1.0 / beta;
+      bp = beta;
+      rot = (rot + 1) % 3;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    State st;
+    st.s_cur = sc;
+    st.s_prev = sp;
+    st.beta_prev = bp;
+    st.b_norm = bnorm;
+    st.epoch = epoch;
+    st.rot = rot;
+    st.steps = steps;
+    st.status = status;
+    *a.st = st;
+  }
+}
+
+// =============================================================================================
+// pass 2, streaming with tiled node sums: one sweep and one grid barrier per step
+// =============================================================================================
+template <bool WITH_V>
+__global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceOp op, const TileOp to, const Pass2Args a) {
+  extern __shared__ double smem[];
+  __shared__ CtaShared sh;
+  const TileSmem s = carve_tiles(smem, op.p, true);
+  const TileCtx c = tile_ctx(op, to);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t m = op.m, p = op.p;
+  const size_t pstride = (size_t)gridDim.x * p;
+  unsigned int epoch = a.st->epoch;
+  double* const buf0 = a.buf[0];
+  double* const buf1 = a.buf[1];
+  double* const buf2 = a.buf[2];
+  auto pick = [&](int r) { return r == 0 ? buf0 : (r == 1 ? buf1 : buf2); };
+  int rot = 0;
+  double sc_cur = 1.0 / a.b_norm;  // scale of the vector whose un-normalised partial node sums are in `partials`
+  {
+    // v_1 = b * (1/||b||), x = y_0 v_1; partial node sums of b
+    const double inv = 1.0 / a.b_norm;
+    const double y0 = __ldg(a.y);
+    double* Vp = buf0;
+    double* Vc = buf1;
+    for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.acc[u] = 0.0;
+    for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
+      const double v = __dmul_rn(__ldg(a.b + m + u), inv);
+      __stcg(Vc + m + u, v);
+      __stcg(Vp + m + u, 0.0);
+      __stcg(to.nodebuf + p + u, v);
+      __stcg(a.x + m + u, __dmul_rn(v, y0));
+      if (WITH_V) __stcs(a.V + m + u, v);
+    }
+    for (uint32_t t = 0; t < to.ntile; ++t) {
+      const uint32_t t0 = c.alo + t * to.T;
+      if (t0 >= c.ahi) break;
+      const uint32_t t1 = min(c.ahi, t0 + to.T);
+      for (uint32_t i = t0 + threadIdx.x; i < t1; i += kBlock) {
+        const double v = __dmul_rn(__ldg(a.b + i), inv);
+        __stcg(Vc + i, v);
+        __stcg(Vp + i, 0.0);
+        __stcg(a.x + i, __dmul_rn(v, y0));
+        if (WITH_V) __stcs(a.V + i, v);
+        s.wt[i - t0] = __ldg(a.b + i);  // node sums are taken over the UN-normalised vector and scaled afterwards,
+      }                                  // exactly as pass 1 does with its lazily scaled w (bit-identical node rows)
+      __syncthreads();
+      tile_node_sums(to, s, blockIdx.x * to.ntile + t);
+      __syncthreads();
+    }
+    publish_tile_partials(op, s, to.partials);
+    grid_sync<false>(0.0, a.gs, epoch, sh);
+  }
+  for (int j = 0; j + 1 < a.steps; ++j) {
+    const double* Vp = pick(rot);
+    const double* Vc = pick((rot + 1) % 3);
+    double* Vn = pick((rot + 2) % 3);
+    const double* Xnode = to.nodebuf + (size_t)((j + 1) & 1) * p;
+    double* Nout = to.nodebuf + (size_t)(j & 1) * p;
+    const double* Pin = to.partials + (size_t)(j & 1) * pstride;
+    double* Pout = to.partials + (size_t)((j + 1) & 1) * pstride;
+    double* Vcol = WITH_V ? a.V + (size_t)(j + 1) * a.ldv : nullptr;
+    const double alpha = __ldg(a.alphas + j);
+    const double beta = __ldg(a.betas + j);
+    const double bp = j == 0 ? 0.0 : __ldg(a.betas + j - 1);
+    const double sinv = 1.0 / beta;
+    const double yj = __ldg(a.y + j + 1);
+
+    for (uint32_t u = threadIdx.x; u < p; u += kBlock) {
+      s.node[u] = __ldcg(Xnode + u);
+      s.acc[u] = 0.0;
+    }
+    __syncthreads();
+    for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
+      const double t = __dmul_rn(sc_cur, tile_node_total(op, Pin, u, lane));
+      if (lane == 0) {
+        const double w = rec_sub(rec_sub(t, bp, __ldcg(Vp + m + u)), alpha, s.node[u]);
+        const double vn = __dmul_rn(w, sinv);
+        __stcg(Vn + m + u, vn);
+        __stcg(Nout + u, vn);
+        __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(yj, vn)));
+        if (WITH_V) __stcs(Vcol + m + u, vn);
+      }
+    }
+    for (uint32_t t = 0; t < to.ntile; ++t) {
+      const uint32_t t0 = c.alo + t * to.T;
+      if (t0 >= c.ahi) break;
+      const uint32_t t1 = min(c.ahi, t0 + to.T);
+      for (uint32_t base = t0; base < t1; base += kUnroll * kBlock) {
+        double vc[kUnroll], vp[kUnroll], dd[kUnroll], xx[kUnroll];
+        uint32_t tl[kUnroll], hd[kUnroll];
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = base + q * kBlock + threadIdx.x;
+          if (i < t1) {
+            vc[q] = __ldcg(Vc + i);
+            vp[q] = __ldcg(Vp + i);
+            xx[q] = __ldcg(a.x + i);
+            dd[q] = __ldg(op.d + i);
+            tl[q] = __ldg(op.tail + i);
+            hd[q] = __ldg(op.head + i);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = base + q * kBlock + threadIdx.x;
+          if (i < t1) {
+            const double v = vc[q];
+            const double w =
+                rec_sub(rec_sub(arc_row(dd[q], v, tl[q], hd[q], s.node[tl[q]], s.node[hd[q]]), bp, vp[q]), alpha, v);
+            const double vn = __dmul_rn(w, sinv);
+            __stcg(Vn + i, vn);
+            __stcg(a.x + i, __dadd_rn(xx[q], __dmul_rn(yj, vn)));
+            if (WITH_V) __stcs(Vcol + i, vn);
+            s.wt[i - t0] = w;
+          }
+        }
+      }
+      __syncthreads();
+      tile_node_sums(to, s, blockIdx.x * to.ntile + t);
+      __syncthreads();
+    }
+    publish_tile_partials(op, s, Pout);
+    grid_sync<false>(0.0, a.gs, epoch, sh);
+    rot = (rot + 1) % 3;
+    sc_cur = sinv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.st->epoch = epoch;
+}
+
+}  // namespace tpl
