@@ -290,28 +290,28 @@ int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
 
 // ---------------------------------------------------------------- tiled node-sum lists (tpl_tiles.cuh)
 struct HostTiles {
-  uint32_t T = 0, ntile = 0, npt = 0;
-  std::vector<uint32_t> lptr, lent, pptr, piece;
+  uint32_t T = 0, ntile = 0;
+  std::vector<uint4> thdr;
+  std::vector<uint32_t> lent, piece;
 };
 
 void build_tiles(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int G, uint32_t T, HostTiles& h) {
   const size_t A = (m + G - 1) / G;
+  const int B = tpl::kBlock;
   h.T = T;
   h.ntile = (uint32_t)std::max<size_t>(1, (A + T - 1) / T);
-  h.npt = (uint32_t)std::max<size_t>(1, (p + tpl::kBlock - 1) / tpl::kBlock);
   const size_t ntiles = (size_t)G * h.ntile;
-  h.lptr.assign(ntiles * (tpl::kBlock + 1), 0);
-  h.pptr.assign(ntiles + 1, 0);
+  h.thdr.assign(ntiles, make_uint4(0, 0, 0, 0));
   h.lent.clear();
-  h.lent.reserve(2 * m);
+  h.lent.reserve(m + m / 4);
   h.piece.clear();
-  std::vector<uint32_t> cnt(p + 1), e_node, e_code, order;
+  std::vector<uint32_t> cnt(p + 1), e_node, e_code, sorted_node, sorted_code, order, cut(B + 1);
   for (int c = 0; c < G; ++c) {
     const size_t lo = std::min(m, A * (size_t)c), hi = std::min(m, lo + A);
     for (uint32_t t = 0; t < h.ntile; ++t) {
       const size_t tile_id = (size_t)c * h.ntile + t;
       const size_t t0 = std::min(hi, lo + (size_t)t * T), t1 = std::min(hi, t0 + T);
-      h.pptr[tile_id] = (uint32_t)h.piece.size();
+      const uint32_t q0 = (uint32_t)h.piece.size();
       e_node.clear();
       e_code.clear();
       uint32_t npieces = 0;
@@ -343,26 +343,39 @@ void build_tiles(size_t m, size_t p, const uint32_t* tail, const uint32_t* head,
       for (size_t i = t0; i < t1; ++i)  // head side
         if (tail[i] != head[i]) {
           e_node.push_back(head[i]);
-          e_code.push_back((uint32_t)(i - t0) | 0x8000u);
+          e_code.push_back((uint32_t)(i - t0) | 0x4000u);
         }
       // stable counting sort by node: per node the tail entries come first (ascending index), then the head entries
       const size_t ne = e_node.size();
       std::fill(cnt.begin(), cnt.end(), 0u);
       for (size_t e = 0; e < ne; ++e) ++cnt[e_node[e] + 1];
       for (size_t u = 0; u < p; ++u) cnt[u + 1] += cnt[u];
-      uint32_t* lp = h.lptr.data() + tile_id * (tpl::kBlock + 1);
-      const uint32_t base = (uint32_t)h.lent.size();
-      for (int i = 0; i <= tpl::kBlock; ++i) lp[i] = base + cnt[std::min<size_t>(p, (size_t)i * h.npt)];
-      h.lent.resize(base + ne);
+      sorted_node.resize(ne);
+      sorted_code.resize(ne);
       order.assign(cnt.begin(), cnt.end() - 1);
       for (size_t e = 0; e < ne; ++e) {
-        const uint32_t u = e_node[e];
-        const uint32_t owner = u / h.npt;
-        h.lent[base + order[u]++] = ((u - owner * h.npt) << 16) | e_code[e];
+        const uint32_t dst = order[e_node[e]]++;
+        sorted_node[dst] = e_node[e];
+        sorted_code[dst] = e_code[e];
       }
+      // cut into B slices of nearly equal length at node boundaries (a node never straddles two threads)
+      cut[0] = 0;
+      for (int i = 1; i <= B; ++i) {
+        size_t want = std::max<size_t>(cut[i - 1], (ne * (size_t)i + B - 1) / B);
+        while (want < ne && want > 0 && sorted_node[want] == sorted_node[want - 1]) ++want;
+        cut[i] = (uint32_t)std::min(want, ne);
+      }
+      cut[B] = (uint32_t)ne;
+      uint32_t L = 0;
+      for (int i = 0; i < B; ++i) L = std::max(L, cut[i + 1] - cut[i]);
+      const size_t base = h.lent.size();
+      h.lent.resize(base + (size_t)L * B, tpl::kEntPad);
+      for (int i = 0; i < B; ++i)
+        for (uint32_t q = 0; q < cut[i + 1] - cut[i]; ++q)
+          h.lent[base + (size_t)q * B + i] = (sorted_node[cut[i] + q] << 15) | sorted_code[cut[i] + q];
+      h.thdr[tile_id] = make_uint4((uint32_t)base, L, q0, (uint32_t)h.piece.size());
     }
   }
-  h.pptr[ntiles] = (uint32_t)h.piece.size();
 }
 
 template <class K>
@@ -657,30 +670,30 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   }
   // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of kUnroll * kBlock arcs, at most
   // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
-  if (!rc && p >= 1 && p <= 0xffffull * tpl::kBlock) {
+  if (!rc && p >= 1 && p < (1u << 17)) {
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
     const long budget = (long)max_optin - 2048 - (long)(2 * p + tpl::kMaxPieces) * 8;
     const uint32_t step = tpl::kUnroll * tpl::kBlock;
-    uint32_t T = budget > 0 ? (uint32_t)std::min<long>(16384, budget / 8 / step * step) : 0;
+    uint32_t T = budget > 0 ? (uint32_t)std::min<long>(8192, budget / 8 / step * step) : 0;  // <= ~kPre entries per thread
     const size_t A = (m + op->G - 1) / op->G;
     if (T >= step) {
       T = (uint32_t)std::min<size_t>(T, std::max<size_t>(step, (A + step - 1) / step * step));
       HostTiles ht;
       build_tiles(m, p, tail, head, op->G, T, ht);
-      op->tile.T = ht.T;
-      op->tile.ntile = ht.ntile;
-      op->tile.npt = ht.npt;
-      op->tile.R = (uint32_t)std::max<size_t>(1, (p + op->G - 1) / op->G);
-      rc = dev_upload(op, &op->tile.lptr, ht.lptr);
-      if (!rc) rc = dev_upload(op, &op->tile.lent, ht.lent);
-      if (!rc) rc = dev_upload(op, &op->tile.pptr, ht.pptr);
-      if (!rc) rc = dev_upload(op, &op->tile.piece, ht.piece);
-      if (!rc) rc = dev_alloc(op, &op->tile.partials, 2 * (size_t)op->G * p);
-      if (!rc) rc = dev_alloc(op, &op->tile.nodebuf, 2 * p);
-      op->smem_tile1 = tpl::tile_smem_bytes((uint32_t)p, T, false);
-      op->smem_tile2 = tpl::tile_smem_bytes((uint32_t)p, T, true);
-      op->tiled_ok = !rc;
+      if (ht.lent.size() < 0xffffffffull) {
+        op->tile.T = ht.T;
+        op->tile.ntile = ht.ntile;
+        op->tile.R = (uint32_t)std::max<size_t>(1, (p + op->G - 1) / op->G);
+        rc = dev_upload(op, &op->tile.thdr, ht.thdr);
+        if (!rc) rc = dev_upload(op, &op->tile.lent, ht.lent);
+        if (!rc) rc = dev_upload(op, &op->tile.piece, ht.piece);
+        if (!rc) rc = dev_alloc(op, &op->tile.partials, 2 * (size_t)op->G * p);
+        if (!rc) rc = dev_alloc(op, &op->tile.nodebuf, 2 * p);
+        op->smem_tile1 = tpl::tile_smem_bytes((uint32_t)p, T, false);
+        op->smem_tile2 = tpl::tile_smem_bytes((uint32_t)p, T, true);
+        op->tiled_ok = !rc;
+      }
     }
   }
   const size_t seg_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);

@@ -25,21 +25,27 @@ namespace tpl {
 
 constexpr uint32_t kPieceMin = 32;     // shortest same-tail run summed as a piece
 constexpr uint32_t kPieceMax = 1024;   // longest piece (longer runs are split at fixed offsets)
-constexpr uint32_t kMaxPieces = 512;   // per tile (shared-memory slots after the T arc values)
+constexpr uint32_t kMaxPieces = 512;   // per tile (shared-memory slots after the T arc values); T + kMaxPieces <= 16384
 constexpr int kUnroll = 4;             // arcs per thread per batch of the streaming loops
+constexpr int kUnroll2 = 2;            // pass 2: six loads per arc, two batches of registers in flight
+constexpr int kPre = 16;               // list entries per thread fetched into registers BEFORE the tile is streamed
 
 struct TileOp {
   uint32_t T;         // arcs per tile
   uint32_t ntile;     // tiles per CTA chunk
-  uint32_t npt;       // nodes per thread
   uint32_t R;         // node rows per owner block = ceil(p / G)
-  const uint32_t* lptr;   // [G * ntile][kBlock + 1] entry ranges (per tile, per owning thread)
-  const uint32_t* lent;   // entries: node offset << 16 | minus << 15 | index into the tile (arcs, then pieces)
-  const uint32_t* pptr;   // [G * ntile + 1] piece ranges
+  // per tile: {first entry word, entries per thread L, first piece, end piece}
+  const uint4* thdr;      // [G * ntile]
+  // entries, per tile L x kBlock words, thread-interleaved (word q of thread i at q * kBlock + i => coalesced):
+  //   node << 15 | minus << 14 | index into the tile (arcs, then pieces);  0xffffffff = padding.
+  // A tile's entries are sorted by node and cut into kBlock slices of (nearly) equal length at node boundaries, so a
+  // node is folded by exactly one thread per tile and all threads carry the same load.
+  const uint32_t* lent;
   const uint32_t* piece;  // first | (len - 1) << 16
   double* partials;       // [2][G][p]  per-CTA partial node sums (double-buffered by step parity)
   double* nodebuf;        // [2][p]     node part of the newest vector as published by the owners (un-normalised)
 };
+constexpr uint32_t kEntPad = 0xffffffffu;
 
 struct TileSmem {
   double* node;  // [p]  scaled node segment of the current vector (phases that form arc rows)
@@ -58,39 +64,77 @@ __device__ __forceinline__ TileSmem carve_tiles(double* base, uint32_t p, bool p
   return s;
 }
 
+// Everything a thread needs from HBM to fold a tile is requested before the tile's arcs are streamed, so that the
+// latency of these small dependent loads (tile header -> list words) hides behind the stream: the header of tile t+1 is
+// fetched while tile t is processed, the first kPre list words and the warp's first piece while tile t itself streams.
+struct TileHdr {
+  uint32_t e0, L;   // first entry word of the tile, entries per thread
+  uint32_t q0, q1;  // the tile's pieces
+};
+struct TilePre {
+  uint32_t ent[kPre];
+  uint32_t pc;
+};
+__device__ __forceinline__ TileHdr tile_hdr(const TileOp& to, uint32_t tile_id) {
+  const uint4 h = __ldg(to.thdr + tile_id);
+  return TileHdr{h.x, h.y, h.z, h.w};
+}
+__device__ __forceinline__ void tile_pre(const TileOp& to, const TileHdr& h, TilePre& pre) {
+  const uint32_t* mine = to.lent + h.e0 + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < kPre; ++q) pre.ent[q] = (uint32_t)q < h.L ? __ldg(mine + (size_t)q * kBlock) : kEntPad;
+  const uint32_t q = h.q0 + (threadIdx.x >> 5);
+  pre.pc = q < h.q1 ? __ldg(to.piece + q) : 0u;
+}
+
+// one list entry: acc[node] +- wt[index]; `cur` / `r` carry the accumulator of the node being folded
+__device__ __forceinline__ void fold_entry(uint32_t ent, double v, double* acc, uint32_t& cur, double& r) {
+  if (ent == kEntPad) return;
+  const uint32_t node = ent >> 15;
+  if (node != cur) {
+    if (cur != kEntPad) acc[cur] = r;
+    cur = node;
+    r = acc[node];
+  }
+  r = (ent & 0x4000u) ? __dsub_rn(r, v) : __dadd_rn(r, v);
+}
+
 // Adds the node sums of the tile held in s.wt[0 .. n_arcs) into s.acc.  Caller has synchronised after filling s.wt and
 // must synchronise before refilling it.
-__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, uint32_t tile_id) {
+__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, const TileHdr& h, const TilePre& pre) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t q0 = __ldg(to.pptr + tile_id), q1 = __ldg(to.pptr + tile_id + 1);
-  if (q1 > q0) {
-    for (uint32_t q = q0 + warp; q < q1; q += kWarps) {
-      const uint32_t pc = __ldg(to.piece + q);
+  if (h.q1 > h.q0) {
+    for (uint32_t q = h.q0 + warp; q < h.q1; q += kWarps) {
+      const uint32_t pc = q == h.q0 + warp ? pre.pc : __ldg(to.piece + q);
       const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
       double a = 0.0;
       for (uint32_t e = lane; e < len; e += 32) a = __dadd_rn(a, s.wt[first + e]);
       a = warp_sum(a);
-      if (lane == 0) s.wt[to.T + (q - q0)] = a;
+      if (lane == 0) s.wt[to.T + (q - h.q0)] = a;
     }
     __syncthreads();
   }
-  const uint32_t* lp = to.lptr + (size_t)tile_id * (kBlock + 1) + threadIdx.x;
-  const uint32_t e0 = __ldg(lp), e1 = __ldg(lp + 1);
-  double* mine = s.acc + (size_t)threadIdx.x * to.npt;
-  uint32_t cur = 0xffffffffu;
+  uint32_t cur = kEntPad;
   double r = 0.0;
-  for (uint32_t e = e0; e < e1; ++e) {
-    const uint32_t ent = __ldg(to.lent + e);
-    const uint32_t off = ent >> 16;
-    const double val = s.wt[ent & 0x7fffu];
-    if (off != cur) {
-      if (cur != 0xffffffffu) mine[cur] = r;
-      cur = off;
-      r = mine[off];
-    }
-    r = (ent & 0x8000u) ? __dsub_rn(r, val) : __dadd_rn(r, val);
+  {
+    double v[kPre];
+#pragma unroll
+    for (int q = 0; q < kPre; ++q) v[q] = pre.ent[q] != kEntPad ? s.wt[pre.ent[q] & 0x3fffu] : 0.0;
+#pragma unroll
+    for (int q = 0; q < kPre; ++q) fold_entry(pre.ent[q], v[q], s.acc, cur, r);
   }
-  if (cur != 0xffffffffu) mine[cur] = r;
+  const uint32_t* mine = to.lent + h.e0 + threadIdx.x;
+  for (uint32_t q0 = kPre; q0 < h.L; q0 += 4) {  // long slices: four list words in flight per round
+    uint32_t ent[4];
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ent[q] = q0 + q < h.L ? __ldg(mine + (size_t)(q0 + q) * kBlock) : kEntPad;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = ent[q] != kEntPad ? s.wt[ent[q] & 0x3fffu] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fold_entry(ent[q], v[q], s.acc, cur, r);
+  }
+  if (cur != kEntPad) s.acc[cur] = r;
 }
 
 struct TileCtx {
@@ -113,23 +157,76 @@ __device__ __forceinline__ void publish_tile_partials(const IncidenceOp& op, con
 // T_u = sum over the G partials in a fixed order (one warp per owned node, lanes stride the CTAs, xor tree)
 __device__ __forceinline__ double tile_node_total(const IncidenceOp& op, const double* Pin, uint32_t u, int lane) {
   double a = 0.0;
-  for (uint32_t c = lane; c < gridDim.x; c += 32) a = __dadd_rn(a, __ldcg(Pin + (size_t)c * op.p + u));
+  for (uint32_t c0 = lane; c0 < gridDim.x; c0 += 256) {  // eight independent loads in flight per lane
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t c = c0 + 32 * q;
+      v[q] = c < gridDim.x ? __ldcg(Pin + (size_t)c * op.p + u) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a = __dadd_rn(a, v[q]);
+  }
   return warp_sum(a);
 }
 
-// node partial sums of an arbitrary arc vector X (init: b) over the CTA's chunk, tile by tile
-__device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp& to, const TileSmem& s, const TileCtx& c,
-                                             const double* X) {
-  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) s.acc[u] = 0.0;
+// Tile loop shared by every phase that produces a new vector.  The chunk is streamed in batches of BATCH arcs (a tile is
+// a whole number of batches): `issue(i0, regs)` starts the global loads of batch [i0, i0 + BATCH), `consume(i0, t0, regs)`
+// computes the new arc values, stores them and writes them to s.wt[i - t0].  The loads of the NEXT batch -- also across a
+// tile boundary -- are issued before the current batch is consumed and before a finished tile is folded into s.acc, so
+// the HBM stream keeps flowing while the CTA synchronises and walks its lists.  The caller has zeroed s.acc.
+template <int BATCH, class REGS, class ISSUE, class CONSUME>
+__device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, const TileCtx& c, ISSUE issue, CONSUME consume) {
+  const uint32_t tile0 = blockIdx.x * to.ntile;
+  if (c.alo >= c.ahi) return;
+  TileHdr hdr = tile_hdr(to, tile0);
+  REGS cur;
+  issue(c.alo, cur);
   for (uint32_t t = 0; t < to.ntile; ++t) {
     const uint32_t t0 = c.alo + t * to.T;
     if (t0 >= c.ahi) break;
     const uint32_t t1 = min(c.ahi, t0 + to.T);
-    for (uint32_t i = t0 + threadIdx.x; i < t1; i += kBlock) s.wt[i - t0] = __ldg(X + i);
+    TilePre pre;
+    tile_pre(to, hdr, pre);
+    TileHdr next = hdr;
+    if (t + 1 < to.ntile && t1 < c.ahi) next = tile_hdr(to, tile0 + t + 1);
+    for (uint32_t i0 = t0; i0 < t1; i0 += BATCH) {
+      REGS nxt;
+      if (i0 + BATCH < c.ahi) issue(i0 + BATCH, nxt);
+      consume(i0, t0, cur);
+      cur = nxt;
+    }
     __syncthreads();
-    tile_node_sums(to, s, blockIdx.x * to.ntile + t);
+    tile_node_sums(to, s, hdr, pre);
     __syncthreads();
+    hdr = next;
   }
+}
+
+// node partial sums of an arbitrary arc vector X (init: b) over the CTA's chunk
+__device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp& to, const TileSmem& s, const TileCtx& c,
+                                             const double* X) {
+  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) s.acc[u] = 0.0;
+  __syncthreads();
+  struct R {
+    double x[kUnroll];
+  };
+  tile_loop<kUnroll * kBlock, R>(
+      to, s, c,
+      [&](uint32_t i0, R& r) {
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = i0 + q * kBlock + threadIdx.x;
+          r.x[q] = i < c.ahi ? __ldg(X + i) : 0.0;
+        }
+      },
+      [&](uint32_t i0, uint32_t t0, const R& r) {
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = i0 + q * kBlock + threadIdx.x;
+          if (i < c.ahi) s.wt[i - t0] = r.x[q];
+        }
+      });
 }
 
 // =============================================================================================
@@ -148,6 +245,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
   unsigned int epoch = a.st->epoch;
   int steps = 0, status = ST_RUNNING, rot = 0;
   double sc = 1.0, sp = 1.0, bp = 0.0, bnorm = 0.0;
+  GridSync gs = a.gs;
   double* const buf0 = a.buf[0];
   double* const buf1 = a.buf[1];
   double* const buf2 = a.buf[2];
@@ -186,10 +284,13 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       const double* Pin = to.partials + (size_t)(j & 1) * pstride;
       double* Pout = to.partials + (size_t)((j + 1) & 1) * pstride;
       double* Vcol = WITH_V ? a.V + (size_t)j * a.ldv : nullptr;
+      gs.trace_step = j;
+      trace_mark(gs.trace, j, 0);
 
       // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
       for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.node[u] = __dmul_rn(__ldcg(Xnode + u), sc);
       __syncthreads();
+      trace_mark(gs.trace, j, 1);
       double acc = 0.0;
       for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
         const double t = __dmul_rn(sc, tile_node_total(op, Pin, u, lane));
@@ -202,6 +303,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
           if (WITH_V) __stcs(Vcol + m + u, v);
         }
       }
+      trace_mark(gs.trace, j, 2);
       for (uint32_t base = c.alo; base < c.ahi; base += kUnroll * kBlock) {
         double wc[kUnroll], wp[kUnroll], dd[kUnroll];
         uint32_t tl[kUnroll], hd[kUnroll];
@@ -229,7 +331,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
           }
         }
       }
-      const double alpha = grid_sync<true>(acc, a.gs, epoch, sh);
+      trace_mark(gs.trace, j, 3);
+      gs.trace_base = 4;
+      const double alpha = grid_sync<true>(acc, gs, epoch, sh);
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
       acc = 0.0;
@@ -241,37 +345,38 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
         __stcg(Nout + u, w);
         acc = fma(w, w, acc);
       }
-      for (uint32_t t = 0; t < to.ntile; ++t) {
-        const uint32_t t0 = c.alo + t * to.T;
-        if (t0 >= c.ahi) break;
-        const uint32_t t1 = min(c.ahi, t0 + to.T);
-        for (uint32_t base = t0; base < t1; base += kUnroll * kBlock) {
-          double wn[kUnroll], wc[kUnroll];
+      __syncthreads();  // accumulators are zero before the first fold
+      struct RB {
+        double wn[kUnroll], wc[kUnroll];
+      };
+      tile_loop<kUnroll * kBlock, RB>(
+          to, s, c,
+          [&](uint32_t i0, RB& r) {
 #pragma unroll
-          for (int q = 0; q < kUnroll; ++q) {
-            const uint32_t i = base + q * kBlock + threadIdx.x;
-            if (i < t1) {
-              wn[q] = __ldcg(Wn + i);
-              wc[q] = __ldcg(Wc + i);
+            for (int q = 0; q < kUnroll; ++q) {
+              const uint32_t i = i0 + q * kBlock + threadIdx.x;
+              if (i < c.ahi) {
+                r.wn[q] = __ldcg(Wn + i);
+                r.wc[q] = __ldcg(Wc + i);
+              }
             }
-          }
+          },
+          [&](uint32_t i0, uint32_t t0, const RB& r) {
 #pragma unroll
-          for (int q = 0; q < kUnroll; ++q) {
-            const uint32_t i = base + q * kBlock + threadIdx.x;
-            if (i < t1) {
-              const double w = rec_sub(wn[q], alpha, __dmul_rn(wc[q], sc));
-              __stcg(Wn + i, w);
-              s.wt[i - t0] = w;
-              acc = fma(w, w, acc);
+            for (int q = 0; q < kUnroll; ++q) {
+              const uint32_t i = i0 + q * kBlock + threadIdx.x;
+              if (i < c.ahi) {
+                const double w = rec_sub(r.wn[q], alpha, __dmul_rn(r.wc[q], sc));
+                __stcg(Wn + i, w);
+                s.wt[i - t0] = w;
+                acc = fma(w, w, acc);
+              }
             }
-          }
-        }
-        __syncthreads();
-        tile_node_sums(to, s, blockIdx.x * to.ntile + t);
-        __syncthreads();
-      }
+          });
+      trace_mark(gs.trace, j, 8);
       publish_tile_partials(op, s, Pout);
-      const double beta = sqrt(grid_sync<true>(acc, a.gs, epoch, sh));
+      gs.trace_base = 9;
+      const double beta = sqrt(grid_sync<true>(acc, gs, epoch, sh));
 
       if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.alphas[j] = alpha;
@@ -336,22 +441,16 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
       __stcg(a.x + m + u, __dmul_rn(v, y0));
       if (WITH_V) __stcs(a.V + m + u, v);
     }
-    for (uint32_t t = 0; t < to.ntile; ++t) {
-      const uint32_t t0 = c.alo + t * to.T;
-      if (t0 >= c.ahi) break;
-      const uint32_t t1 = min(c.ahi, t0 + to.T);
-      for (uint32_t i = t0 + threadIdx.x; i < t1; i += kBlock) {
-        const double v = __dmul_rn(__ldg(a.b + i), inv);
-        __stcg(Vc + i, v);
-        __stcg(Vp + i, 0.0);
-        __stcg(a.x + i, __dmul_rn(v, y0));
-        if (WITH_V) __stcs(a.V + i, v);
-        s.wt[i - t0] = __ldg(a.b + i);  // node sums are taken over the UN-normalised vector and scaled afterwards,
-      }                                  // exactly as pass 1 does with its lazily scaled w (bit-identical node rows)
-      __syncthreads();
-      tile_node_sums(to, s, blockIdx.x * to.ntile + t);
-      __syncthreads();
+    for (uint32_t i = c.alo + threadIdx.x; i < c.ahi; i += kBlock) {
+      const double v = __dmul_rn(__ldg(a.b + i), inv);
+      __stcg(Vc + i, v);
+      __stcg(Vp + i, 0.0);
+      __stcg(a.x + i, __dmul_rn(v, y0));
+      if (WITH_V) __stcs(a.V + i, v);
     }
+    // node sums are taken over the UN-normalised vector and scaled afterwards, exactly as pass 1 does with its lazily
+    // scaled w (bit-identical node rows)
+    tile_sums_of(op, to, s, c, a.b);
     publish_tile_partials(op, s, to.partials);
     grid_sync<false>(0.0, a.gs, epoch, sh);
   }
@@ -386,44 +485,43 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
         if (WITH_V) __stcs(Vcol + m + u, vn);
       }
     }
-    for (uint32_t t = 0; t < to.ntile; ++t) {
-      const uint32_t t0 = c.alo + t * to.T;
-      if (t0 >= c.ahi) break;
-      const uint32_t t1 = min(c.ahi, t0 + to.T);
-      for (uint32_t base = t0; base < t1; base += kUnroll * kBlock) {
-        double vc[kUnroll], vp[kUnroll], dd[kUnroll], xx[kUnroll];
-        uint32_t tl[kUnroll], hd[kUnroll];
+    __syncthreads();  // node rows are done with s.node reads of other warps; accumulators are zero
+    struct R2 {
+      double vc[kUnroll2], vp[kUnroll2], dd[kUnroll2], xx[kUnroll2];
+      uint32_t tl[kUnroll2], hd[kUnroll2];
+    };
+    tile_loop<kUnroll2 * kBlock, R2>(
+        to, s, c,
+        [&](uint32_t i0, R2& r) {
 #pragma unroll
-        for (int q = 0; q < kUnroll; ++q) {
-          const uint32_t i = base + q * kBlock + threadIdx.x;
-          if (i < t1) {
-            vc[q] = __ldcg(Vc + i);
-            vp[q] = __ldcg(Vp + i);
-            xx[q] = __ldcg(a.x + i);
-            dd[q] = __ldg(op.d + i);
-            tl[q] = __ldg(op.tail + i);
-            hd[q] = __ldg(op.head + i);
+          for (int q = 0; q < kUnroll2; ++q) {
+            const uint32_t i = i0 + q * kBlock + threadIdx.x;
+            if (i < c.ahi) {
+              r.vc[q] = __ldcg(Vc + i);
+              r.vp[q] = __ldcg(Vp + i);
+              r.xx[q] = __ldcg(a.x + i);
+              r.dd[q] = __ldg(op.d + i);
+              r.tl[q] = __ldg(op.tail + i);
+              r.hd[q] = __ldg(op.head + i);
+            }
           }
-        }
+        },
+        [&](uint32_t i0, uint32_t t0, const R2& r) {
 #pragma unroll
-        for (int q = 0; q < kUnroll; ++q) {
-          const uint32_t i = base + q * kBlock + threadIdx.x;
-          if (i < t1) {
-            const double v = vc[q];
-            const double w =
-                rec_sub(rec_sub(arc_row(dd[q], v, tl[q], hd[q], s.node[tl[q]], s.node[hd[q]]), bp, vp[q]), alpha, v);
-            const double vn = __dmul_rn(w, sinv);
-            __stcg(Vn + i, vn);
-            __stcg(a.x + i, __dadd_rn(xx[q], __dmul_rn(yj, vn)));
-            if (WITH_V) __stcs(Vcol + i, vn);
-            s.wt[i - t0] = w;
+          for (int q = 0; q < kUnroll2; ++q) {
+            const uint32_t i = i0 + q * kBlock + threadIdx.x;
+            if (i < c.ahi) {
+              const double v = r.vc[q];
+              const double w = rec_sub(
+                  rec_sub(arc_row(r.dd[q], v, r.tl[q], r.hd[q], s.node[r.tl[q]], s.node[r.hd[q]]), bp, r.vp[q]), alpha, v);
+              const double vn = __dmul_rn(w, sinv);
+              __stcg(Vn + i, vn);
+              __stcg(a.x + i, __dadd_rn(r.xx[q], __dmul_rn(yj, vn)));
+              if (WITH_V) __stcs(Vcol + i, vn);
+              s.wt[i - t0] = w;
+            }
           }
-        }
-      }
-      __syncthreads();
-      tile_node_sums(to, s, blockIdx.x * to.ntile + t);
-      __syncthreads();
-    }
+        });
     publish_tile_partials(op, s, Pout);
     grid_sync<false>(0.0, a.gs, epoch, sh);
     rot = (rot + 1) % 3;
