@@ -34,9 +34,9 @@ def report(name, tr, marks, labels):
         prev = v.mean()
     step_len = (tr[:, 9:k - 2, 0] - tr[:, 8:k - 3, 0]).mean()
     print(f"  step length {step_len:.0f} cycles")
-    g = tr[:, steps, 15]
+    g = tr[:, steps, -1]
     print(f"  globaltimer skew of step start across CTAs: mean {np.mean(g.max(axis=0) - g.min(axis=0)):.0f} ns")
-    gl = (tr[0, 9:k - 2, 15] - tr[0, 8:k - 3, 15]).mean()
+    gl = (tr[0, 9:k - 2, -1] - tr[0, 8:k - 3, -1]).mean()
     print(f"  step length by globaltimer {gl:.0f} ns -> SM clock {step_len / gl:.3f} GHz")
 
 
@@ -50,6 +50,10 @@ y = np.ones(dec.steps_taken)
 alg.lanczos_pass_two(op, b, dec, y)
 t2 = op.trace_read()
 if mode != 0 or arcs > 1_000_000:
+    tt = t1.astype(np.int64)[:, 8:k - 2, 16:20]
+    for nm, col in zip(("stream", "sync1", "fold(thread 0)", "sync2"), range(4)):
+        v = tt[:, :, col].mean(axis=1)
+        print(f"  phase B {nm:16s} {v.mean():9.0f} | {v.min():9.0f} | {v.max():9.0f}")
     sys.exit(0)
 report("pass 2 resident", t2, [0, 1, 2, 3, 4, 5, 6, 7],
        ["step start", "gather issued+reduced", "after sync", "arcs+rows done", "sync: after bar", "published",

@@ -72,10 +72,10 @@ struct State {  // persists in HBM between launches of the same handle
 };
 
 struct Trace {  // optional per-CTA phase timestamps (diagnostics; buf == nullptr in production)
-  unsigned long long* buf;  // [G][max_steps][16] SM clock (globaltimer in slot 15)
+  unsigned long long* buf;  // [G][max_steps][kTraceMarks] SM clock (globaltimer in the last slot)
   int max_steps;
 };
-constexpr int kTraceMarks = 16;
+constexpr int kTraceMarks = 24;
 
 struct GridSync {
   uint4* slots;  // [2][G] {payload lo, epoch, payload hi, epoch}, double-buffered by epoch parity
@@ -94,6 +94,11 @@ __device__ __forceinline__ void trace_mark(const Trace& t, int step, int m) {
       p[kTraceMarks - 1] = g;
     }
   }
+}
+
+__device__ __forceinline__ void trace_value(const Trace& t, int step, int m, unsigned long long v) {
+  if (t.buf != nullptr && threadIdx.x == 0 && step >= 0 && step < t.max_steps)
+    t.buf[((size_t)blockIdx.x * t.max_steps + step) * kTraceMarks + m] = v;
 }
 
 struct Pass1Args {

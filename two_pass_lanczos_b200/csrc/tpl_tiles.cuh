@@ -24,7 +24,7 @@
 namespace tpl {
 
 constexpr uint32_t kPieceMin = 32;     // shortest same-tail run summed as a piece
-constexpr uint32_t kPieceMax = 1024;   // longest piece (longer runs are split at fixed offsets)
+constexpr uint32_t kPieceMax = 256;    // longest piece (longer runs are split at fixed offsets)
 constexpr uint32_t kMaxPieces = 512;   // per tile (shared-memory slots after the T arc values); T + kMaxPieces <= 16384
 constexpr int kUnroll = 4;             // arcs per thread per batch of the streaming loops
 constexpr int kUnroll2 = 2;            // pass 2: six loads per arc, two batches of registers in flight
@@ -47,20 +47,34 @@ struct TileOp {
 };
 constexpr uint32_t kEntPad = 0xffffffffu;
 
+// Shared-memory arrays are addressed through 32-bit shared-window addresses and explicit ld/st.shared: with generic
+// `double*` members the compiler re-derives the window base (S2UR SR_CgaCtaId + address arithmetic) inside divergent code.
+struct SmArr {
+  uint32_t a;  // shared-window byte address of element 0
+};
+__device__ __forceinline__ double sm_ld(SmArr arr, uint32_t i) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(arr.a + i * 8u) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sm_st(SmArr arr, uint32_t i, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(arr.a + i * 8u), "d"(v) : "memory");
+}
 struct TileSmem {
-  double* node;  // [p]  scaled node segment of the current vector (phases that form arc rows)
-  double* acc;   // [p]  partial node sums of this CTA            (phases that produce a new vector)
-  double* wt;    // [T + kMaxPieces] arc values of the current tile + piece sums
+  SmArr node;  // [p]  scaled node segment of the current vector (phases that form arc rows)
+  SmArr acc;   // [p]  partial node sums of this CTA            (phases that produce a new vector)
+  SmArr wt;    // [T + kMaxPieces] arc values of the current tile + piece sums
 };
 // pass 1 never needs node and acc at the same time (they alias); pass 2 needs both.
 __host__ __device__ inline size_t tile_smem_bytes(uint32_t p, uint32_t T, bool pass2) {
   return ((pass2 ? 2 : 1) * (size_t)p + T + kMaxPieces) * sizeof(double);
 }
 __device__ __forceinline__ TileSmem carve_tiles(double* base, uint32_t p, bool pass2) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(base);
   TileSmem s;
-  s.node = base;
-  s.acc = pass2 ? base + p : base;
-  s.wt = s.acc + p;
+  s.node.a = b;
+  s.acc.a = pass2 ? b + p * 8u : b;
+  s.wt.a = s.acc.a + p * 8u;
   return s;
 }
 
@@ -75,28 +89,40 @@ struct TilePre {
   uint32_t ent[kPre];
   uint32_t pc;
 };
+// The prefetching loads are volatile asm: the compiler must issue them HERE (it otherwise sinks them to their first use
+// after the stream, which exposes a full HBM latency per tile -- 23 % of all stall samples in the first ncu capture).
+__device__ __forceinline__ uint32_t ld_nc_early(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ TileHdr tile_hdr(const TileOp& to, uint32_t tile_id) {
-  const uint4 h = __ldg(to.thdr + tile_id);
-  return TileHdr{h.x, h.y, h.z, h.w};
+  TileHdr h;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(h.e0), "=r"(h.L), "=r"(h.q0), "=r"(h.q1)
+               : "l"(to.thdr + tile_id));
+  return h;
 }
 __device__ __forceinline__ void tile_pre(const TileOp& to, const TileHdr& h, TilePre& pre) {
   const uint32_t* mine = to.lent + h.e0 + threadIdx.x;
 #pragma unroll
-  for (int q = 0; q < kPre; ++q) pre.ent[q] = (uint32_t)q < h.L ? __ldg(mine + (size_t)q * kBlock) : kEntPad;
+  for (int q = 0; q < kPre; ++q) {
+    pre.ent[q] = kEntPad;
+    if ((uint32_t)q < h.L) pre.ent[q] = ld_nc_early(mine + (size_t)q * kBlock);  // uniform predicate
+  }
   const uint32_t q = h.q0 + (threadIdx.x >> 5);
-  pre.pc = q < h.q1 ? __ldg(to.piece + q) : 0u;
+  pre.pc = 0u;
+  if (q < h.q1) pre.pc = ld_nc_early(to.piece + q);
 }
 
-// one list entry: acc[node] +- wt[index]; `cur` / `r` carry the accumulator of the node being folded
-__device__ __forceinline__ void fold_entry(uint32_t ent, double v, double* acc, uint32_t& cur, double& r) {
-  if (ent == kEntPad) return;
+// One list entry: acc[node] += (+-) wt[index], a plain read-modify-write (a thread's entries are folded in list order, so
+// repeated nodes need no special care).  The sign is applied by flipping the sign bit of the tile value: a - x and
+// a + (-x) are the same IEEE operation.  The fold is instruction-issue bound (one entry per arc per step), hence the
+// minimal instruction count per entry.
+__device__ __forceinline__ void fold_entry(uint32_t ent, SmArr wt, SmArr acc) {
   const uint32_t node = ent >> 15;
-  if (node != cur) {
-    if (cur != kEntPad) acc[cur] = r;
-    cur = node;
-    r = acc[node];
-  }
-  r = (ent & 0x4000u) ? __dsub_rn(r, v) : __dadd_rn(r, v);
+  const long long x = __double_as_longlong(sm_ld(wt, ent & 0x3fffu)) ^ ((long long)(ent & 0x4000u) << 49);
+  sm_st(acc, node, __dadd_rn(sm_ld(acc, node), __longlong_as_double(x)));
 }
 
 // Adds the node sums of the tile held in s.wt[0 .. n_arcs) into s.acc.  Caller has synchronised after filling s.wt and
@@ -107,34 +133,33 @@ __device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem&
     for (uint32_t q = h.q0 + warp; q < h.q1; q += kWarps) {
       const uint32_t pc = q == h.q0 + warp ? pre.pc : __ldg(to.piece + q);
       const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
-      double a = 0.0;
-      for (uint32_t e = lane; e < len; e += 32) a = __dadd_rn(a, s.wt[first + e]);
-      a = warp_sum(a);
-      if (lane == 0) s.wt[to.T + (q - h.q0)] = a;
+      const SmArr w{s.wt.a + first * 8u};
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent lane-strided chains, combined in a fixed order
+      for (uint32_t e = lane; e < len; e += 128) {
+        const double x0 = sm_ld(w, e);
+        const double x1 = e + 32 < len ? sm_ld(w, e + 32) : 0.0;
+        const double x2 = e + 64 < len ? sm_ld(w, e + 64) : 0.0;
+        const double x3 = e + 96 < len ? sm_ld(w, e + 96) : 0.0;
+        a0 = __dadd_rn(a0, x0);
+        a1 = __dadd_rn(a1, x1);
+        a2 = __dadd_rn(a2, x2);
+        a3 = __dadd_rn(a3, x3);
+      }
+      const double a = warp_sum(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)));
+      if (lane == 0) sm_st(s.wt, to.T + (q - h.q0), a);
     }
     __syncthreads();
   }
-  uint32_t cur = kEntPad;
-  double r = 0.0;
-  {
-    double v[kPre];
 #pragma unroll
-    for (int q = 0; q < kPre; ++q) v[q] = pre.ent[q] != kEntPad ? s.wt[pre.ent[q] & 0x3fffu] : 0.0;
-#pragma unroll
-    for (int q = 0; q < kPre; ++q) fold_entry(pre.ent[q], v[q], s.acc, cur, r);
+  for (int q = 0; q < kPre; ++q) {
+    if ((uint32_t)q >= h.L) break;  // uniform: every thread of the tile carries L words (the last ones may be padding)
+    if (pre.ent[q] != kEntPad) fold_entry(pre.ent[q], s.wt, s.acc);
   }
   const uint32_t* mine = to.lent + h.e0 + threadIdx.x;
-  for (uint32_t q0 = kPre; q0 < h.L; q0 += 4) {  // long slices: four list words in flight per round
-    uint32_t ent[4];
-    double v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ent[q] = q0 + q < h.L ? __ldg(mine + (size_t)(q0 + q) * kBlock) : kEntPad;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = ent[q] != kEntPad ? s.wt[ent[q] & 0x3fffu] : 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) fold_entry(ent[q], v[q], s.acc, cur, r);
+  for (uint32_t q = kPre; q < h.L; ++q) {  // long slices (hub nodes): the rest straight from the list
+    const uint32_t ent = __ldg(mine + (size_t)q * kBlock);
+    if (ent != kEntPad) fold_entry(ent, s.wt, s.acc);
   }
-  if (cur != kEntPad) s.acc[cur] = r;
 }
 
 struct TileCtx {
@@ -152,7 +177,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const IncidenceOp& op, const TileOp&
 // writes this CTA's p partial sums (s.acc) to HBM; caller synchronised before
 __device__ __forceinline__ void publish_tile_partials(const IncidenceOp& op, const TileSmem& s, double* Pout) {
   double* mine = Pout + (size_t)blockIdx.x * op.p;
-  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) __stcg(mine + u, s.acc[u]);
+  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) __stcg(mine + u, sm_ld(s.acc, u));
 }
 // T_u = sum over the G partials in a fixed order (one warp per owned node, lanes stride the CTAs, xor tree)
 __device__ __forceinline__ double tile_node_total(const IncidenceOp& op, const double* Pin, uint32_t u, int lane) {
@@ -176,9 +201,12 @@ __device__ __forceinline__ double tile_node_total(const IncidenceOp& op, const d
 // tile boundary -- are issued before the current batch is consumed and before a finished tile is folded into s.acc, so
 // the HBM stream keeps flowing while the CTA synchronises and walks its lists.  The caller has zeroed s.acc.
 template <int BATCH, class REGS, class ISSUE, class CONSUME>
-__device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, const TileCtx& c, ISSUE issue, CONSUME consume) {
+__device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, const TileCtx& c, ISSUE issue, CONSUME consume,
+                                          const Trace* tr = nullptr, int tr_step = -1) {
   const uint32_t tile0 = blockIdx.x * to.ntile;
   if (c.alo >= c.ahi) return;
+  long long c_stream = 0, c_sync1 = 0, c_fold = 0, c_sync2 = 0, t_a = 0, t_b = 0;
+  const bool timed = tr != nullptr && tr->buf != nullptr;
   TileHdr hdr = tile_hdr(to, tile0);
   REGS cur;
   issue(c.alo, cur);
@@ -190,23 +218,34 @@ __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, c
     tile_pre(to, hdr, pre);
     TileHdr next = hdr;
     if (t + 1 < to.ntile && t1 < c.ahi) next = tile_hdr(to, tile0 + t + 1);
+    if (timed) t_a = clock64();
     for (uint32_t i0 = t0; i0 < t1; i0 += BATCH) {
       REGS nxt;
       if (i0 + BATCH < c.ahi) issue(i0 + BATCH, nxt);
       consume(i0, t0, cur);
       cur = nxt;
     }
+    if (timed) { t_b = clock64(); c_stream += t_b - t_a; }
     __syncthreads();
+    if (timed) { t_a = clock64(); c_sync1 += t_a - t_b; }
     tile_node_sums(to, s, hdr, pre);
+    if (timed) { t_b = clock64(); c_fold += t_b - t_a; }
     __syncthreads();
+    if (timed) { t_a = clock64(); c_sync2 += t_a - t_b; }
     hdr = next;
+  }
+  if (timed) {
+    trace_value(*tr, tr_step, 16, c_stream);
+    trace_value(*tr, tr_step, 17, c_sync1);
+    trace_value(*tr, tr_step, 18, c_fold);
+    trace_value(*tr, tr_step, 19, c_sync2);
   }
 }
 
 // node partial sums of an arbitrary arc vector X (init: b) over the CTA's chunk
 __device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp& to, const TileSmem& s, const TileCtx& c,
                                              const double* X) {
-  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) s.acc[u] = 0.0;
+  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) sm_st(s.acc, u, 0.0);
   __syncthreads();
   struct R {
     double x[kUnroll];
@@ -224,7 +263,7 @@ __device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
           const uint32_t i = i0 + q * kBlock + threadIdx.x;
-          if (i < c.ahi) s.wt[i - t0] = r.x[q];
+          if (i < c.ahi) sm_st(s.wt, i - t0, r.x[q]);
         }
       });
 }
@@ -288,14 +327,14 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       trace_mark(gs.trace, j, 0);
 
       // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
-      for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.node[u] = __dmul_rn(__ldcg(Xnode + u), sc);
+      for (uint32_t u = threadIdx.x; u < p; u += kBlock) sm_st(s.node, u, __dmul_rn(__ldcg(Xnode + u), sc));
       __syncthreads();
       trace_mark(gs.trace, j, 1);
       double acc = 0.0;
       for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
         const double t = __dmul_rn(sc, tile_node_total(op, Pin, u, lane));
         if (lane == 0) {
-          const double v = s.node[u];
+          const double v = sm_ld(s.node, u);
           const double vp = __dmul_rn(__ldcg(Wp + m + u), sp);
           const double wt = rec_sub(t, bp, vp);
           acc = fma(v, wt, acc);
@@ -324,7 +363,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
           if (i < c.ahi) {
             const double v = __dmul_rn(wc[q], sc);
             const double vp = __dmul_rn(wp[q], sp);
-            const double wt = rec_sub(arc_row(dd[q], v, tl[q], hd[q], s.node[tl[q]], s.node[hd[q]]), bp, vp);
+            const double wt = rec_sub(arc_row(dd[q], v, tl[q], hd[q], sm_ld(s.node, tl[q]), sm_ld(s.node, hd[q])), bp, vp);
             acc = fma(v, wt, acc);
             __stcg(Wn + i, wt);
             if (WITH_V) __stcs(Vcol + i, v);
@@ -337,7 +376,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
       acc = 0.0;
-      for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.acc[u] = 0.0;  // (aliases s.node: phase A is over)
+      for (uint32_t u = threadIdx.x; u < p; u += kBlock) sm_st(s.acc, u, 0.0);  // (aliases s.node: phase A is over)
       for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
         const double v = __dmul_rn(__ldcg(Wc + m + u), sc);
         const double w = rec_sub(__ldcg(Wn + m + u), alpha, v);
@@ -368,11 +407,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
               if (i < c.ahi) {
                 const double w = rec_sub(r.wn[q], alpha, __dmul_rn(r.wc[q], sc));
                 __stcg(Wn + i, w);
-                s.wt[i - t0] = w;
+                sm_st(s.wt, i - t0, w);
                 acc = fma(w, w, acc);
               }
             }
-          });
+          },
+          &gs.trace, j);
       trace_mark(gs.trace, j, 8);
       publish_tile_partials(op, s, Pout);
       gs.trace_base = 9;
@@ -432,7 +472,6 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
     const double y0 = __ldg(a.y);
     double* Vp = buf0;
     double* Vc = buf1;
-    for (uint32_t u = threadIdx.x; u < p; u += kBlock) s.acc[u] = 0.0;
     for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
       const double v = __dmul_rn(__ldg(a.b + m + u), inv);
       __stcg(Vc + m + u, v);
@@ -470,14 +509,14 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
     const double yj = __ldg(a.y + j + 1);
 
     for (uint32_t u = threadIdx.x; u < p; u += kBlock) {
-      s.node[u] = __ldcg(Xnode + u);
-      s.acc[u] = 0.0;
+      sm_st(s.node, u, __ldcg(Xnode + u));
+      sm_st(s.acc, u, 0.0);
     }
     __syncthreads();
     for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
       const double t = __dmul_rn(sc_cur, tile_node_total(op, Pin, u, lane));
       if (lane == 0) {
-        const double w = rec_sub(rec_sub(t, bp, __ldcg(Vp + m + u)), alpha, s.node[u]);
+        const double w = rec_sub(rec_sub(t, bp, __ldcg(Vp + m + u)), alpha, sm_ld(s.node, u));
         const double vn = __dmul_rn(w, sinv);
         __stcg(Vn + m + u, vn);
         __stcg(Nout + u, vn);
@@ -513,12 +552,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
             if (i < c.ahi) {
               const double v = r.vc[q];
               const double w = rec_sub(
-                  rec_sub(arc_row(r.dd[q], v, r.tl[q], r.hd[q], s.node[r.tl[q]], s.node[r.hd[q]]), bp, r.vp[q]), alpha, v);
+                  rec_sub(arc_row(r.dd[q], v, r.tl[q], r.hd[q], sm_ld(s.node, r.tl[q]), sm_ld(s.node, r.hd[q])), bp, r.vp[q]), alpha, v);
               const double vn = __dmul_rn(w, sinv);
               __stcg(Vn + i, vn);
               __stcg(a.x + i, __dadd_rn(r.xx[q], __dmul_rn(yj, vn)));
               if (WITH_V) __stcs(Vcol + i, vn);
-              s.wt[i - t0] = w;
+              sm_st(s.wt, i - t0, w);
             }
           }
         });
