@@ -120,10 +120,19 @@ uint64_t tpl_op_kernel_launches(const tpl_op* op);
 uint64_t tpl_op_matrix_bytes(const tpl_op* op);
 uint64_t tpl_op_device_bytes(const tpl_op* op);
 /* Execution mode: 0 = automatic (default): persistent cooperative kernels, shared-memory-resident when the
- * per-SM slice of the operator fits, streaming otherwise; 1 = one cooperative launch per Lanczos step
- * (streaming kernels; what a step callback uses); 2 = persistent streaming kernels even when the resident
- * shape would fit.  All modes run the same per-element arithmetic and give bit-identical results. */
+ * per-SM slice of the operator fits (2-D cell partition first, contiguous chunks second), streaming otherwise;
+ * 1 = one cooperative launch per Lanczos step (streaming kernels; what a step callback uses); 2 = persistent streaming
+ * kernels with tiled node sums even when a resident shape would fit; 3 = streaming kernels with gathered node rows;
+ * 4 = chunk-resident kernels even when the cell partition would fit.  All modes run the same per-element arithmetic;
+ * they differ in the (fixed) order in which a node row is summed, i.e. by rounding only. */
 int tpl_op_set_mode(tpl_op* op, int mode);
+/* Diagnostics (host only, no device needed): builds the 2-D cell partition the resident kernels would use on a grid
+ * of `ctas` CTAs with `smem_limit` bytes of shared memory each and checks its tables on the host.
+ * stats = {fits, tail blocks, head blocks, arc slots per cell, node lines, most entry rows, most node-sum groups,
+ * most touched lines, most pushed lines, owned lines per CTA, inbox atoms, largest cell, smallest cell,
+ * shared-memory bytes (pass 2), consistency code (0 = consistent), 0}. */
+int tpl_cells_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, size_t smem_limit,
+                   uint64_t stats[16]);
 /* Diagnostics: per-CTA, per-step phase timestamps (SM clock) of the resident kernels.  enable(max_steps > 0)
  * allocates ctas x max_steps x marks 64-bit words in HBM, enable(0) frees them; read() copies them out (row-major
  * [cta][step][mark]) and clears the buffer.  Off by default; costs one predicated store per mark when on. */

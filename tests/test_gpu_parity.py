@@ -24,15 +24,16 @@ def golden_instances():
     return sorted(glob.glob(os.path.join(helpers.GOLDEN, "netgen1000", "*.dmx")))
 
 
-# incidence operator in its three execution shapes (tpl_op_set_mode): shared-memory resident (default at these sizes),
-# streaming with tiled node sums (what large instances use), streaming with gathered node rows (generic fallback)
-FORMATS = ["incidence", "incidence-tiled", "incidence-gather", "csr"]
+# incidence operator in its four execution shapes (tpl_op_set_mode): shared-memory resident on the 2-D cell partition
+# (default at these sizes), resident on contiguous chunks, streaming with tiled node sums (what large instances use),
+# streaming with gathered node rows (generic fallback)
+FORMATS = ["incidence", "incidence-chunks", "incidence-tiled", "incidence-gather", "csr"]
 
 
 def gpu_ops(inst):
     cp, ri, va = datagen.kkt_csc(inst)
     ops = {"csr": tpl.LinOp.from_csc(inst.n, cp, ri, va)}
-    for name, mode in (("incidence", 0), ("incidence-tiled", 2), ("incidence-gather", 3)):
+    for name, mode in (("incidence", 0), ("incidence-chunks", 4), ("incidence-tiled", 2), ("incidence-gather", 3)):
         ops[name] = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d)
         ops[name].set_mode(mode)
     return ops
@@ -162,7 +163,7 @@ def test_golden_fixtures_through_the_loader(dmx, flavour, ext, fmt, golden_dir):
     key = f"{os.path.basename(dmx)[:-4]}.{flavour}"
     kkt = data_loader.load_kkt_system(dmx, dmx[:-3] + ext, fmt=fmt.split("-")[0])
     assert kkt.a.format == fmt.split("-")[0]
-    kkt.a.set_mode({"incidence-tiled": 2, "incidence-gather": 3}.get(fmt, 0))
+    kkt.a.set_mode({"incidence-chunks": 4, "incidence-tiled": 2, "incidence-gather": 3}.get(fmt, 0))
     assert [kkt.num_nodes, kkt.num_arcs] == list(g[key + ".nnz"][1:])
     b = g[key + ".b"]
     dec = alg.lanczos_pass_one(kkt.a, b, 30)

@@ -8,11 +8,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "tpl_internal.h"
+#include "tpl_cells_host.h"
 #include "tpl_kernels.cuh"
 #include "tpl_sharded.cuh"
 #include "tpl_tiles.cuh"
@@ -156,6 +158,11 @@ struct tpl_op {
   bool resident_ok = false;    // the per-CTA slice of the incidence operator fits in shared memory
   tpl::ResidentOp res{};
   size_t smem_res1 = 0, smem_res2 = 0;
+  bool cells_ok = false;       // 2-D cell partition fits in shared memory (tpl_cells.cuh)
+  tpl::CellOp cell{};
+  size_t smem_cell1 = 0, smem_cell2 = 0;
+  void* cell_xchg = nullptr;   // inbox | gather | all-reduce atoms, cleared before every pass
+  size_t cell_xchg_bytes = 0;
   bool tiled_ok = false;       // streaming kernels with tiled node sums are usable (shared-memory budget)
   tpl::TileOp tile{};
   size_t smem_tile1 = 0, smem_tile2 = 0;
@@ -462,6 +469,18 @@ int finish_setup(tpl_op* op) {
                                                              op->smem_res2));
       if (r1 < 1 || r2 < 1) op->resident_ok = false;
     }
+    if (op->cells_ok) {
+      op->smem_cell1 = tpl::cell_smem_bytes(op->cell, false);
+      op->smem_cell2 = tpl::cell_smem_bytes(op->cell, true);
+      if (int rc = set_smem(tpl::pass1_cell_kernel<false>, op->smem_cell1)) return rc;
+      if (int rc = set_smem(tpl::pass1_cell_kernel<true>, op->smem_cell1)) return rc;
+      if (int rc = set_smem(tpl::pass2_cell_kernel<false>, op->smem_cell2)) return rc;
+      if (int rc = set_smem(tpl::pass2_cell_kernel<true>, op->smem_cell2)) return rc;
+      int c1 = 0, c2 = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c1, tpl::pass1_cell_kernel<true>, tpl::kBlock, op->smem_cell1));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c2, tpl::pass2_cell_kernel<true>, tpl::kBlock, op->smem_cell2));
+      if (c1 < 1 || c2 < 1) op->cells_ok = false;
+    }
     if (op->tiled_ok) {
       if (int rc = set_smem(tpl::pass1_tiled_kernel<false>, op->smem_tile1)) return rc;
       if (int rc = set_smem(tpl::pass1_tiled_kernel<true>, op->smem_tile1)) return rc;
@@ -668,6 +687,37 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       op->resident_ok = !rc;
     }
   }
+  // cell shape: 2-D partition of the arcs, per-cell jagged-diagonal tail lists and head lists, tagged-atom exchange buffers
+  if (!rc) {
+    int max_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
+    tpl::HostCells hc;
+    tpl::build_cells(m, p, tail, head, op->G, (size_t)max_optin, hc);
+    if (hc.ok) {
+      tpl::CellOp& co = op->cell;
+      co = tpl::cells_probe(hc);
+      if (const char* f = std::getenv("TPL_CELL_FLAGS")) co.flags = (uint32_t)std::strtoul(f, nullptr, 0);
+      rc = dev_upload(op, &co.hdr, hc.hdr);
+      if (!rc) rc = dev_upload(op, &co.gidx, hc.gidx);
+      if (!rc) rc = dev_upload(op, &co.lth, hc.lth);
+      if (!rc) rc = dev_upload(op, &co.lines, hc.lines);
+      if (!rc) rc = dev_upload(op, &co.push, hc.push);
+      if (!rc) rc = dev_upload(op, &co.walk, hc.walk);
+      if (!rc) rc = dev_upload(op, &co.ent4, hc.ent4);
+      if (!rc) rc = dev_upload(op, &co.slot_base, hc.slot_base);
+      const size_t atoms = 2 * ((size_t)co.inbox_atoms + (size_t)co.L * tpl::kLine + (size_t)co.Gc * tpl::kLine);
+      uint4* xchg = nullptr;
+      if (!rc) rc = dev_alloc(op, &xchg, atoms);
+      if (!rc) {
+        op->cell_xchg = xchg;
+        op->cell_xchg_bytes = atoms * sizeof(uint4);
+        co.inbox = xchg;
+        co.gather = xchg + 2 * (size_t)co.inbox_atoms;
+        co.ar = co.gather + 2 * (size_t)co.L * tpl::kLine;
+        op->cells_ok = true;
+      }
+    }
+  }
   // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of kUnroll * kBlock arcs, at most
   // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
   if (!rc && p >= 1 && p < (1u << 17)) {
@@ -773,8 +823,45 @@ int tpl_op_trace_read(tpl_op* op, uint64_t* out, size_t capacity, size_t* ctas, 
   return TPL_OK;
 }
 
+int tpl_cells_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, size_t smem_limit,
+                   uint64_t stats[16]) {
+  tpl::clear_error();
+  if (!tail || !head || !stats) return fail(TPL_ERR_PANIC, "null argument");
+  for (size_t j = 0; j < m; ++j)
+    if (tail[j] >= p || head[j] >= p)
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  tpl::HostCells hc;
+  tpl::build_cells(m, p, tail, head, ctas, smem_limit, hc);
+  std::fill(stats, stats + 16, 0ull);
+  stats[0] = hc.ok;
+  stats[1] = hc.GR;
+  stats[2] = hc.GC;
+  stats[3] = hc.Amax;
+  stats[4] = hc.L;
+  stats[5] = hc.max_rows;
+  stats[6] = hc.max_groups;
+  stats[7] = hc.max_lines;
+  stats[8] = hc.max_slots;
+  stats[9] = hc.max_own;
+  stats[10] = hc.inbox_atoms;
+  if (!hc.hdr.empty()) {
+    uint64_t amax = 0, amin = ~0ull;
+    for (uint32_t c = 0; c < hc.Gc; ++c) {
+      amax = std::max<uint64_t>(amax, hc.hdr[(size_t)c * 8]);
+      amin = std::min<uint64_t>(amin, hc.hdr[(size_t)c * 8]);
+    }
+    stats[11] = amax;
+    stats[12] = amin;
+  }
+  if (hc.ok) {
+    stats[13] = tpl::cell_smem_bytes(tpl::cells_probe(hc), true);
+    stats[14] = (uint64_t)tpl::check_cells(m, p, tail, head, hc);
+  }
+  return TPL_OK;
+}
+
 int tpl_op_set_mode(tpl_op* op, int mode) {
-  if (!op || mode < 0 || mode > 3) return fail(TPL_ERR_PANIC, "invalid mode");
+  if (!op || mode < 0 || mode > 4) return fail(TPL_ERR_PANIC, "invalid mode");
   op->mode = mode;
   return TPL_OK;
 }
@@ -818,9 +905,21 @@ int launch_coop(tpl_op* op, KERNEL kernel, const OP& dop, const ARGS& args, size
   return TPL_OK;
 }
 
-// mode 0: resident kernels whenever the slice fits and the whole pass runs in one launch; otherwise (and in mode 2) the
-// streaming kernels with tiled node sums; mode 3 (and any operator the tiles do not fit) the gather kernels
-bool use_resident(const tpl_op* op) { return op->format == 2 && op->resident_ok && op->mode == 0; }
+// mode 0: cell kernels (2-D partition, shared-memory resident) whenever a cell fits and the whole pass runs in one
+// launch, else the chunk-resident kernels (mode 4 forces these), else (and in mode 2) the streaming kernels with tiled
+// node sums; mode 3 (and any operator the tiles do not fit) the gather kernels
+bool use_cells(const tpl_op* op) { return op->format == 2 && op->cells_ok && op->mode == 0; }
+bool use_resident(const tpl_op* op) { return op->format == 2 && op->resident_ok && (op->mode == 0 || op->mode == 4); }
+
+template <class KERNEL, class ARGS>
+int launch_cells(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
+  CUDA_TRY(cudaMemsetAsync(op->cell_xchg, 0, op->cell_xchg_bytes, op->stream));
+  void* params[] = {&op->inc, &op->cell, const_cast<ARGS*>(&args)};
+  CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->cell.Gc), dim3(tpl::kBlock), params,
+                                       smem, op->stream));
+  op->launches += 1;
+  return TPL_OK;
+}
 bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op->mode == 0 || op->mode == 2); }
 
 template <class KERNEL, class ARGS>
@@ -834,6 +933,9 @@ int launch_tiled(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
 
 int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   const bool with_v = a.V != nullptr;
+  if (whole_pass && use_cells(op))
+    return with_v ? launch_cells(op, tpl::pass1_cell_kernel<true>, a, op->smem_cell1)
+                  : launch_cells(op, tpl::pass1_cell_kernel<false>, a, op->smem_cell1);
   if (whole_pass && use_resident(op))
     return with_v ? launch_resident(op, tpl::pass1_resident_kernel<true>, a, op->smem_res1)
                   : launch_resident(op, tpl::pass1_resident_kernel<false>, a, op->smem_res1);
@@ -848,6 +950,9 @@ int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
 }
 int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   const bool with_v = a.V != nullptr;
+  if (use_cells(op))
+    return with_v ? launch_cells(op, tpl::pass2_cell_kernel<true>, a, op->smem_cell2)
+                  : launch_cells(op, tpl::pass2_cell_kernel<false>, a, op->smem_cell2);
   if (use_resident(op))
     return with_v ? launch_resident(op, tpl::pass2_resident_kernel<true>, a, op->smem_res2)
                   : launch_resident(op, tpl::pass2_resident_kernel<false>, a, op->smem_res2);

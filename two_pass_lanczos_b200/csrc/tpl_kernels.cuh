@@ -75,7 +75,7 @@ struct Trace {  // optional per-CTA phase timestamps (diagnostics; buf == nullpt
   unsigned long long* buf;  // [G][max_steps][kTraceMarks] SM clock (globaltimer in the last slot)
   int max_steps;
 };
-constexpr int kTraceMarks = 24;
+constexpr int kTraceMarks = 64;  // 0..31 thread 0 of the CTA, 32..47 / 48..62 lane 0 of warp w (two stamps), 63 globaltimer
 
 struct GridSync {
   uint4* slots;  // [2][G] {payload lo, epoch, payload hi, epoch}, double-buffered by epoch parity
@@ -94,6 +94,13 @@ __device__ __forceinline__ void trace_mark(const Trace& t, int step, int m) {
       p[kTraceMarks - 1] = g;
     }
   }
+}
+
+// stamp of warp w (lane 0) in slot base + w
+__device__ __forceinline__ void trace_mark_warp(const Trace& t, int step, int base) {
+  const int w = threadIdx.x >> 5;
+  if (t.buf != nullptr && (threadIdx.x & 31) == 0 && step >= 0 && step < t.max_steps && base + w < kTraceMarks - 1)
+    t.buf[((size_t)blockIdx.x * t.max_steps + step) * kTraceMarks + base + w] = clock64();
 }
 
 __device__ __forceinline__ void trace_value(const Trace& t, int step, int m, unsigned long long v) {
