@@ -34,7 +34,7 @@ alg.lanczos_pass_two(op, b, dec, np.ones(dec.steps_taken))
 t2 = op.trace_read().astype(np.int64)
 
 
-def report(name, tr, labels):
+def report(name, tr, labels, extra):
     tr = tr[:144]
     steps = slice(8, k - 3)
     relc = tr[:, steps, :] - tr[:, steps, 0:1]
@@ -45,13 +45,34 @@ def report(name, tr, labels):
         print(f"  mark {mk:2d} {lab:28s} {v.mean():8.0f} | {v.min():8.0f} | {v.max():8.0f}  delta {v.mean() - prev:8.0f}")
         prev = v.mean()
     step_len = (tr[:, 9:k - 3, 0] - tr[:, 8:k - 4, 0]).mean()
-    print(f"  step length {step_len:.0f} cycles")
+    print(f"  step length {step_len:.0f} cycles; node sums done + barrier at {relc[:, :, extra].mean():.0f}")
     for base, lab in ((32, "polls done, by warp"), (48, "sums pushed, by warp")):
         v = relc[:, :, base:base + 15].mean(axis=(0, 1))
         mx = relc[:, :, base:base + 15].max(axis=2).mean()
         print(f"  {lab:22s} " + " ".join(f"{x:6.0f}" for x in v) + f"   mean of the per-step max {mx:.0f}")
 
 
+if "--grid" in sys.argv:
+    for name, tr, mk in (("pass 1 after-sync (mark 2)", t1, 2), ("pass 1 inbox warp 5 polls done", t1, 37),
+                         ("pass 2 inbox warp 0 polls done", t2, 32)):
+        v = (tr[:144, 8:k - 3, mk] - tr[:144, 8:k - 3, 0]).mean(axis=1)
+        print(f"== {name}: per-CTA mean, 12 x 12 (row = tail block)")
+        for a in range(12):
+            print("   " + " ".join(f"{x:6.0f}" for x in v[a * 12:(a + 1) * 12]))
+if "--skew" in sys.argv:
+    for name, tr, push_mark, poll_mark in (("pass 1", t1, 9, 37), ("pass 2", t2, 5, 32)):
+        tr = tr[:144]
+        g0 = tr[:, :, 63].astype(np.float64)                       # ns, globaltimer at step start (same clock on every SM)
+        ghz = 1.965
+        push = g0 + (tr[:, :, push_mark] - tr[:, :, 0]) / ghz      # ns
+        poll = g0 + (tr[:, :, poll_mark] - tr[:, :, 0]) / ghz
+        st = slice(8, k - 4)
+        start_skew = (g0[:, st].max(axis=0) - g0[:, st].min(axis=0)).mean()
+        push_spread = (push[:, st].max(axis=0) - push[:, st].min(axis=0)).mean()
+        lat_after_last = (poll[:, 9:k - 3] - push[:, st].max(axis=0)[None, :]).mean()
+        lat_after_mean = (poll[:, 9:k - 3] - push[:, st].mean(axis=0)[None, :]).mean()
+        print(f"== {name}: step-start skew across CTAs {start_skew:.0f} ns, push spread {push_spread:.0f} ns, inbox poll done "
+              f"{lat_after_last:.0f} ns after the LAST push of the grid ({lat_after_mean:.0f} ns after the mean push)")
 report("pass 1 cells", t1, ["step start", "polls done (thread 0)", "after sync", "phase A done", "alpha published",
-                            "alpha polled", "alpha known", "phase B done", "beta published", "sums pushed"])
-report("pass 2 cells", t2, ["step start", "polls done (thread 0)", "after sync", "rows done", "after sync", "sums pushed"])
+                            "alpha polled", "alpha known", "phase B done", "beta published", "sums pushed"], 10)
+report("pass 2 cells", t2, ["step start", "polls done (thread 0)", "after sync", "rows done", "after sync", "sums pushed"], 6)

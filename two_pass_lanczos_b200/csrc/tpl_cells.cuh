@@ -29,8 +29,10 @@
 namespace tpl {
 
 constexpr uint32_t kLine = 8;        // nodes per line = atoms per 128-byte line
-constexpr int kArcRegs = 8;          // arcs per thread; the arc part of the vectors, D and x live in REGISTERS for a whole pass
-constexpr uint32_t kCellArcs = kArcRegs * kBlock;  // arc slots of a cell (4096)
+constexpr int kArcRegs = 9;          // arcs per worker thread; the arc part of the vectors and of x lives in REGISTERS for a whole pass
+constexpr uint32_t kWorkers = kBlock - 32;         // warps 0..14 work on the arcs; warp 15 is the OWNER warp (node rows of the owned lines)
+constexpr uint32_t kWorkerWarps = kWorkers / 32;
+constexpr uint32_t kCellArcs = kArcRegs * kWorkers;  // arc slots of a cell (4320)
 
 struct CellOp {
   uint32_t GR, GC, Gc;   // cell grid; Gc = GR * GC CTAs
@@ -59,6 +61,7 @@ struct CellOp {
 
 struct CellSmem {
   double* w;                    // [Amax + 8] arc part of the newest vector (what the node sums are formed from); w[Amax] = 0
+  double* d;                    // [Amax] D of the cell's arcs
   double* nodev;                // [8 * max_lines] node values of the current vector
   double* sums;                 // [8 * max_slots] node sums of this cell in push order
   double *n0, *n1, *nx, *T;     // [8 * max_own] owned node rows: current / previous vector, x (pass 2), node sums
@@ -72,7 +75,7 @@ struct CellSmem {
 };
 
 __host__ __device__ inline size_t cell_smem_bytes(const CellOp& co, bool pass2) {
-  size_t dbl = (size_t)co.Amax + 8 + kLine * co.max_lines + kLine * co.max_slots + (size_t)kLine * co.max_own * (pass2 ? 4 : 3) +
+  size_t dbl = 2 * (size_t)co.Amax + 8 + kLine * co.max_lines + kLine * co.max_slots + (size_t)kLine * co.max_own * (pass2 ? 4 : 3) +
                co.Gc + kWarps;
   dbl = (dbl + 1) & ~(size_t)1;
   const size_t u32 = (size_t)co.max_lines + co.max_slots + 2 * (size_t)co.max_own;
@@ -84,6 +87,7 @@ __device__ __forceinline__ CellSmem carve_cell(double* base, const CellOp& co) {
   CellSmem s;
   double* d = base;
   s.w = d; d += co.Amax + 8;
+  s.d = d; d += co.Amax;
   s.nodev = d; d += kLine * co.max_lines;
   s.sums = d; d += kLine * co.max_slots;
   s.n0 = d; d += kLine * co.max_own;
@@ -147,16 +151,39 @@ __device__ __forceinline__ uint4 atom_pack(double v, uint32_t tag) {
 __device__ __forceinline__ double atom_value(uint4 f) {
   return __longlong_as_double((long long)(((unsigned long long)f.z << 32) | f.x));
 }
-__device__ __forceinline__ double atom_poll(const uint4* p, uint32_t tag, bool backoff = false) {
-  uint4 f = ld_relaxed_gpu_v4(p);
+__device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// polling load: flags 8 = ld.global.cg, 16 = ld.volatile, else ld.relaxed.gpu
+__device__ __forceinline__ uint4 ld_atom(const uint4* p, uint32_t flags) {
+  if (flags & 8u) return ld_cg_v4(p);
+  if (flags & 16u) return ld_volatile_v4(p);
+  return ld_relaxed_gpu_v4(p);
+}
+__device__ __forceinline__ double atom_poll(const uint4* p, uint32_t tag, uint32_t flags = 0) {
+  uint4 f = ld_atom(p, flags);
   uint32_t spins = 0;
   while (f.y != tag || f.w != tag) {
     if (++spins > kSpinLimit) __trap();
-    if (backoff) __nanosleep(100);
-    f = ld_relaxed_gpu_v4(p);
+    if (flags & 2u) __nanosleep(100);
+    f = ld_atom(p, flags);
   }
   return atom_value(f);
 }
+
+// ----------------------------------------------------------------------------- named barriers
+// barrier 0 (__syncthreads): all 16 warps; barrier 1: the 15 worker warps; barrier 2: the workers ARRIVE (without waiting)
+// once the all-reduce values of the top of a step are in shared memory, the owner warp waits for them.
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
+__device__ __forceinline__ void bar_arrive_top() { asm volatile("bar.arrive 2, %0;" ::"n"(kBlock) : "memory"); }
+__device__ __forceinline__ void bar_wait_top() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 
 // ----------------------------------------------------------------------------- exchange steps
 // Node sums of the arc values s.w of this cell -> s.sums.  One warp per group of 16 lists; lane l (< 16) adds the even
@@ -166,7 +193,7 @@ __device__ __forceinline__ double atom_poll(const uint4* p, uint32_t tag, bool b
 // Caller syncs before cell_push_lines.
 __device__ __forceinline__ void cell_node_sums(const CellSmem& s, const CellCtx& c) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t g = warp; g < c.ngroups; g += kWarps) {
+  for (uint32_t g = warp; g < c.ngroups; g += kWorkerWarps) {
     const uint4 d = s.walk[g * 32 + lane];
     const uint2* row = s.ent4 + (size_t)d.z * 32 + lane;
     double acc = 0.0;
@@ -184,62 +211,60 @@ __device__ __forceinline__ void cell_node_sums(const CellSmem& s, const CellCtx&
     if (lane < 16 && d.x != 0xffffffffu) s.sums[d.x] = acc;
   }
 }
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // s.sums -> the owners' inboxes as generation `gen`, one whole line per 8 adjacent lanes.
 __device__ __forceinline__ void cell_push_lines(const CellOp& co, const CellSmem& s, const CellCtx& c, uint32_t gen) {
   uint4* box = co.inbox + (size_t)(gen & 1u) * co.inbox_atoms;
   const uint32_t tag = gen + 1;
-  for (uint32_t t = threadIdx.x; t < c.nslots * kLine; t += kBlock)
-    st_relaxed_gpu_v4(box + (size_t)s.push[t >> 3] * kLine + (t & 7), atom_pack(s.sums[t], tag));
+  for (uint32_t t = threadIdx.x; t < c.nslots * kLine; t += kWorkers) {
+    uint4* dst = box + (size_t)s.push[t >> 3] * kLine + (t & 7);
+    if (co.flags & 4u) st_volatile_v4(dst, atom_pack(s.sums[t], tag));
+    else st_relaxed_gpu_v4(dst, atom_pack(s.sums[t], tag));
+  }
 }
 
-// Owner side: T[o*8 + r] = sum of the contributions to node r of owned line o, generation `gen`.  One warp per line,
-// lane = r + 8 q sums slots q, q+4, ... in order; the four partial sums are combined by a fixed xor tree.
-__device__ __forceinline__ void cell_poll_inbox(const CellOp& co, const CellSmem& s, const CellCtx& c, uint32_t gen,
-                                                uint32_t warp0, uint32_t nwarps) {
+// Owner side: the sum of the contributions to node r = lane & 7 of owned line o, generation `gen` (same value in the
+// four lanes of a node).  Lane = r + 8 q adds slots q, q+4, ... in order; the four partial sums are combined by a fixed xor tree.
+__device__ __forceinline__ double cell_poll_inbox(const CellOp& co, const CellSmem& s, uint32_t o, uint32_t gen) {
   const uint4* box = co.inbox + (size_t)(gen & 1u) * co.inbox_atoms;
   const uint32_t tag = gen + 1;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
   const uint32_t r = lane & 7, q = lane >> 3;
-  for (uint32_t o = warp - warp0; o < c.nown; o += nwarps) {
-    const uint32_t b0 = s.own[2 * o], K = s.own[2 * o + 1];
-    const uint4* mine = box + (size_t)b0 * kLine + r;
-    double t = 0.0;
-    if (co.flags & 1u) {
-      for (uint32_t k = q; k < K; k += 4) t = __dadd_rn(t, atom_poll(mine + (size_t)k * kLine, tag, co.flags & 2u));
-    } else {
-      for (uint32_t k0 = 0; k0 < K; k0 += 32) {
-        // all of a lane's atoms are requested together and re-requested together until every one carries the tag: one L2
-        // round trip per attempt, not one per atom
-        uint4 f[8];
-        uint32_t spins = 0;
-        bool pending = true;
-        while (pending) {
+  const uint32_t b0 = s.own[2 * o], K = s.own[2 * o + 1];
+  const uint4* mine = box + (size_t)b0 * kLine + r;
+  double t = 0.0;
+  for (uint32_t k0 = 0; k0 < K; k0 += 32) {
+    // all of a lane's atoms are requested together and re-requested together until every one carries the tag: one L2
+    // round trip per attempt, not one per atom
+    uint4 f[8];
+    uint32_t spins = 0;
+    bool pending = true;
+    while (pending) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t k = k0 + q + 4 * i;
-            if (k < K) f[i] = ld_relaxed_gpu_v4(mine + (size_t)k * kLine);
-          }
-          pending = false;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t k = k0 + q + 4 * i;
-            if (k < K) pending |= (f[i].y != tag) | (f[i].w != tag);
-          }
-          if (++spins > kSpinLimit) __trap();
-          if (pending && (co.flags & 2u)) __nanosleep(100);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t k = k0 + q + 4 * i;
-          if (k < K) t = __dadd_rn(t, atom_value(f[i]));
-        }
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t k = k0 + q + 4 * i;
+        if (k < K) f[i] = ld_atom(mine + (size_t)k * kLine, co.flags);
       }
+      pending = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t k = k0 + q + 4 * i;
+        if (k < K) pending |= (f[i].y != tag) | (f[i].w != tag);
+      }
+      if (++spins > kSpinLimit) __trap();
     }
-    __syncwarp();
-    t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 8));
-    t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 16));
-    if (q == 0) s.T[o * kLine + r] = t;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t k = k0 + q + 4 * i;
+      if (k < K) t = __dadd_rn(t, atom_value(f[i]));
+    }
   }
+  __syncwarp();
+  t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 8));
+  t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 16));
+  return t;
 }
 
 // Node values of the touched lines, generation `gen`, times `scale` -> nodev.
@@ -248,7 +273,7 @@ __device__ __forceinline__ void cell_poll_gather(const CellOp& co, const CellSme
   const uint4* g = co.gather + (size_t)(gen & 1u) * co.L * kLine;
   const uint32_t tag = gen + 1;
   for (uint32_t a = threadIdx.x - warp0 * 32; a < c.nlines * kLine; a += nwarps * 32)
-    s.nodev[a] = __dmul_rn(atom_poll(g + (size_t)s.lines[a >> 3] * kLine + (a & 7), tag, co.flags & 2u), scale);
+    s.nodev[a] = __dmul_rn(atom_poll(g + (size_t)s.lines[a >> 3] * kLine + (a & 7), tag, co.flags), scale);
 }
 
 __device__ __forceinline__ void cell_publish_node(const CellOp& co, uint32_t line, uint32_t r, double v, uint32_t gen) {
@@ -258,11 +283,11 @@ __device__ __forceinline__ void cell_publish_node(const CellOp& co, uint32_t lin
 // All-reduce, publishing half: the CTA's partial (already summed over the warps into wpart, caller synced) goes out as
 // one whole line (eight copies of the atom, lanes 0..7).
 __device__ __forceinline__ void cell_ar_publish(const CellOp& co, const CellSmem& s, uint32_t epoch) {
-  if (threadIdx.x < 32) {
-    double t = threadIdx.x < kWarps ? s.wpart[threadIdx.x] : 0.0;
+  if (threadIdx.x >= kBlock - 32) {  // the last warp: the first ones own the longest node-sum lists
+    const uint32_t lane = threadIdx.x & 31;
+    double t = lane < kWarps ? s.wpart[lane] : 0.0;
     t = warp_sum(t);
-    if (threadIdx.x < kLine)
-      st_relaxed_gpu_v4(co.ar + ((size_t)(epoch & 1u) * co.Gc + blockIdx.x) * kLine + threadIdx.x, atom_pack(t, epoch));
+    if (lane < kLine) st_relaxed_gpu_v4(co.ar + ((size_t)(epoch & 1u) * co.Gc + blockIdx.x) * kLine + lane, atom_pack(t, epoch));
   }
 }
 // All-reduce, polling half: thread t of the first ceil(Gc / 32) warps polls the line of CTA (t + cta) % Gc (rotated so
@@ -271,7 +296,7 @@ __device__ __forceinline__ void cell_ar_poll(const CellOp& co, const CellSmem& s
   if (threadIdx.x < co.Gc) {
     uint32_t slot = threadIdx.x + blockIdx.x;
     slot = slot >= co.Gc ? slot - co.Gc : slot;
-    s.arv[slot] = atom_poll(co.ar + ((size_t)(epoch & 1u) * co.Gc + slot) * kLine + (blockIdx.x & 7u), epoch, co.flags & 2u);
+    s.arv[slot] = atom_poll(co.ar + ((size_t)(epoch & 1u) * co.Gc + slot) * kLine + (blockIdx.x & 7u), epoch, co.flags);
   }
 }
 __device__ __forceinline__ double cell_ar_total(const CellOp& co, const CellSmem& s) {
@@ -284,12 +309,12 @@ __device__ __forceinline__ void cell_block_partial(const CellSmem& s, double acc
   if ((threadIdx.x & 31) == 0) s.wpart[threadIdx.x >> 5] = acc;
 }
 
-// The arcs of a cell are spread over the threads, arc r of thread t sitting at position t + r * kBlock of the cell's
-// (jagged-diagonal) order.  A thread keeps its arcs' D, tail / head, the current vector W (un-normalised, v = W * sc), the
-// previous vector v_{j-1} (normalised) and, in pass 2, x in registers for the whole pass.
+// The arcs of a cell are spread over the worker threads, arc r of thread t sitting at position t + r * kWorkers of the
+// cell's (jagged-diagonal) order.  A thread keeps its arcs' tail / head, the current vector W (un-normalised, v = W * sc),
+// the previous vector v_{j-1} (normalised) and, in pass 2, x in registers for the whole pass; D stays in shared memory.
 template <bool PASS2>
 struct ArcRegs {
-  double W[kArcRegs], P[kArcRegs], D[kArcRegs], X[PASS2 ? kArcRegs : 1];
+  double W[kArcRegs], P[kArcRegs], X[PASS2 ? kArcRegs : 1];
   uint32_t TH[kArcRegs];
 };
 
@@ -301,16 +326,15 @@ __device__ __forceinline__ double cell_load_arcs(const IncidenceOp& op, const Ce
   double acc = 0.0;
 #pragma unroll
   for (int r = 0; r < kArcRegs; ++r) {
-    const uint32_t i = threadIdx.x + r * kBlock;
+    const uint32_t i = threadIdx.x + r * kWorkers;
     R.W[r] = 0.0;
     R.P[r] = 0.0;
-    R.D[r] = 0.0;
     R.TH[r] = 0u;
     if (i < c.nA) {
       const uint32_t g = __ldg(c.gidx + i);
       R.W[r] = __ldg(b + g);
-      R.D[r] = __ldg(op.d + g);
       R.TH[r] = __ldg(lth + i);
+      s.d[i] = __ldg(op.d + g);
       s.w[i] = R.W[r];
       acc = fma(R.W[r], R.W[r], acc);
     }
@@ -328,13 +352,14 @@ __device__ __forceinline__ double cell_arc_rows(const CellSmem& s, const CellCtx
   double acc = 0.0;
 #pragma unroll
   for (int r = 0; r < kArcRegs; ++r) {
-    if (r * kBlock < c.nA) {  // uniform: rows of arc slots beyond the cell's last arc are skipped
-      const uint32_t i = threadIdx.x + r * kBlock;
+    if (r * kWorkers < c.nA) {  // uniform: rows of arc slots beyond the cell's last arc are skipped
+      const uint32_t i = threadIdx.x + r * kWorkers;
+      const uint32_t ii = i < c.nA ? i : 0;
       const uint32_t t = R.TH[r] & 0xffffu, h = R.TH[r] >> 16;
       const double v = __dmul_rn(R.W[r], sc);
       // pass 2 scales the node values once when it polls them; pass 1 only learns sc together with them
       const double xt = PASS2 ? s.nodev[t] : __dmul_rn(s.nodev[t], sc), xh = PASS2 ? s.nodev[h] : __dmul_rn(s.nodev[h], sc);
-      const double wt = rec_sub(arc_row(R.D[r], v, t, h, xt, xh), bp, R.P[r]);
+      const double wt = rec_sub(arc_row(s.d[ii], v, t, h, xt, xh), bp, R.P[r]);
       R.P[r] = v;
       if (PASS2) {
         const double w = rec_sub(wt, alpha, v);
@@ -357,14 +382,16 @@ __device__ __forceinline__ double cell_arc_rows(const CellSmem& s, const CellCtx
 
 // Replaces lanczos_pass_one (src/algorithms/lanczos_two_pass.rs:65-110) and, with WITH_V, the basis generation of
 // lanczos_standard (src/algorithms/lanczos.rs:55-156) for a cell-partitioned incidence operator; whole pass per launch.
+// Warps 0..14 hold the arcs; warp 15 owns the node rows of the CTA's lines: it waits for their node sums while the
+// workers are busy with the arc rows, so that the exchange started at the end of a step is off the critical path.
 template <bool WITH_V>
 __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp op, const CellOp co, const Pass1Args a) {
   extern __shared__ double smem[];
   const CellSmem s = carve_cell<false>(smem, co);
   const CellCtx c = load_cell(co, s);
-  const uint32_t tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t ar_warps = (co.Gc + 31) / 32;  // polling roles of the warps at the top of a step
-  const uint32_t in_warps = 2;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool owner = warp == kWorkerWarps;
+  const uint32_t ar_warps = (co.Gc + 31) / 32;  // polling roles of the worker warps at the top of a step
   const Trace& tr = a.gs.trace;
   ArcRegs<false> R;
 
@@ -374,34 +401,50 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
   {
     // K0: ||b||; the cell's arcs / the owned node rows of b become the current vector, the previous one is zero; node
     // values and node sums of b are published as generation 0
-    double acc = cell_load_arcs<false>(op, co, s, c, a.b, R);
-    for (uint32_t t = tid; t < c.nown * kLine; t += kBlock) {
-      const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
-      const double bi = u < op.p ? __ldg(a.b + op.m + u) : 0.0;
-      s.n0[t] = bi;
-      s.n1[t] = 0.0;
-      acc = fma(bi, bi, acc);
-      cell_publish_node(co, line, t & 7, bi, 0);
+    double acc = 0.0;
+    if (!owner) {
+      acc = cell_load_arcs<false>(op, co, s, c, a.b, R);
+    } else {
+      for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
+        const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
+        const double bi = u < op.p ? __ldg(a.b + op.m + u) : 0.0;
+        s.n0[t] = bi;
+        s.n1[t] = 0.0;
+        acc = fma(bi, bi, acc);
+        cell_publish_node(co, line, t & 7, bi, 0);
+      }
     }
     cell_block_partial(s, acc);
     __syncthreads();
     cell_ar_publish(co, s, ++epoch);
-    cell_node_sums(s, c);
-    __syncthreads();
-    cell_push_lines(co, s, c, 0);
+    if (!owner) {
+      cell_node_sums(s, c);
+      bar_workers();
+      cell_push_lines(co, s, c, 0);
+    }
   }
   for (int j = 0; j < a.j_end; ++j) {
     double* Vcol = WITH_V ? a.V + (size_t)j * a.ldv : nullptr;
     trace_mark(tr, j, 0);
 
-    // ---------------- top of the step: ||b||^2 or beta_{j-1}^2, node values and node sums of the current vector
-    if (warp < ar_warps) cell_ar_poll(co, s, epoch);
-    else if (warp < ar_warps + in_warps) cell_poll_inbox(co, s, c, (uint32_t)j, ar_warps, in_warps);
-    else cell_poll_gather(co, s, c, (uint32_t)j, ar_warps + in_warps, kWarps - ar_warps - in_warps, 1.0);
-    trace_mark(tr, j, 1);
-    trace_mark_warp(tr, j, 32);
-    __syncthreads();
-    trace_mark(tr, j, 2);
+    // ---------------- top of the step: ||b||^2 or beta_{j-1}^2 and the node values of the current vector (workers);
+    // the owner warp meanwhile waits for the node sums of its lines
+    if (!owner) {
+      if (warp < ar_warps) cell_ar_poll(co, s, epoch);
+      else cell_poll_gather(co, s, c, (uint32_t)j, ar_warps, kWorkerWarps - ar_warps, 1.0);
+      trace_mark(tr, j, 1);
+      trace_mark_warp(tr, j, 32);
+      bar_workers();
+      bar_arrive_top();
+      trace_mark(tr, j, 2);
+    } else {
+      for (uint32_t o = 0; o < c.nown; ++o) {
+        const double t = cell_poll_inbox(co, s, o, (uint32_t)j);
+        if (lane < kLine) s.T[o * kLine + lane] = t;
+      }
+      trace_mark_warp(tr, j, 32);
+      bar_wait_top();
+    }
     const double tot = cell_ar_total(co, s);
     if (j == 0) {
       bnorm = sqrt(tot);
@@ -422,20 +465,25 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
     }
 
     // ---------------- phase A: v = W sc, w~ = A v - beta_{j-1} v_{j-1}, alpha partial
-    // owned node rows: n0 holds W (then w~, then the next W), n1 the previous (normalised) vector
     double acc = 0.0;
-    for (uint32_t t = tid; t < c.nown * kLine; t += kBlock) {
-      const uint32_t u = (blockIdx.x + (t >> 3) * co.Gc) * kLine + (t & 7);
-      const double v = __dmul_rn(s.n0[t], sc);
-      const double wt = rec_sub(__dmul_rn(sc, s.T[t]), bp, s.n1[t]);
-      acc = fma(v, wt, acc);
-      s.n0[t] = wt;
-      s.n1[t] = v;
-      if (WITH_V && u < op.p) __stcs(Vcol + op.m + u, v);
+    if (owner) {
+      // owned node rows: n0 holds W (then w~, then the next W), n1 the previous (normalised) vector
+      __syncwarp();
+      for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
+        const uint32_t u = (blockIdx.x + (t >> 3) * co.Gc) * kLine + (t & 7);
+        const double v = __dmul_rn(s.n0[t], sc);
+        const double wt = rec_sub(__dmul_rn(sc, s.T[t]), bp, s.n1[t]);
+        acc = fma(v, wt, acc);
+        s.n0[t] = wt;
+        s.n1[t] = v;
+        if (WITH_V && u < op.p) __stcs(Vcol + op.m + u, v);
+      }
+    } else {
+      acc = cell_arc_rows<false, WITH_V>(s, c, R, sc, bp, 0.0, 0.0, 0.0, Vcol);
     }
-    acc += cell_arc_rows<false, WITH_V>(s, c, R, sc, bp, 0.0, 0.0, 0.0, Vcol);
     cell_block_partial(s, acc);
     trace_mark(tr, j, 3);
+    trace_mark_warp(tr, j, 48);
     __syncthreads();
     cell_ar_publish(co, s, ++epoch);
     trace_mark(tr, j, 4);
@@ -447,20 +495,23 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
 
     // ---------------- phase B: w = w~ - alpha v; node values, node sums of w and the beta partial are published
     acc = 0.0;
-    for (uint32_t t = tid; t < c.nown * kLine; t += kBlock) {
-      const double w = rec_sub(s.n0[t], alpha, s.n1[t]);
-      s.n0[t] = w;
-      acc = fma(w, w, acc);
-      cell_publish_node(co, blockIdx.x + (t >> 3) * co.Gc, t & 7, w, (uint32_t)j + 1);
-    }
-#pragma unroll
-    for (int r = 0; r < kArcRegs; ++r) {
-      if (r * kBlock < c.nA) {
-        const uint32_t i = tid + r * kBlock;
-        const double w = rec_sub(R.W[r], alpha, R.P[r]);
-        R.W[r] = w;
+    if (owner) {
+      for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
+        const double w = rec_sub(s.n0[t], alpha, s.n1[t]);
+        s.n0[t] = w;
         acc = fma(w, w, acc);
-        if (i < c.nA) s.w[i] = w;
+        cell_publish_node(co, blockIdx.x + (t >> 3) * co.Gc, t & 7, w, (uint32_t)j + 1);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kArcRegs; ++r) {
+        if (r * kWorkers < c.nA) {
+          const uint32_t i = tid + r * kWorkers;
+          const double w = rec_sub(R.W[r], alpha, R.P[r]);
+          R.W[r] = w;
+          acc = fma(w, w, acc);
+          if (i < c.nA) s.w[i] = w;
+        }
       }
     }
     cell_block_partial(s, acc);
@@ -468,13 +519,15 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
     __syncthreads();
     cell_ar_publish(co, s, ++epoch);
     trace_mark(tr, j, 8);
-    cell_node_sums(s, c);
-    trace_mark_warp(tr, j, 48);
-    __syncthreads();
-    cell_push_lines(co, s, c, (uint32_t)j + 1);
+    if (!owner) {
+      cell_node_sums(s, c);
+      bar_workers();
+      trace_mark(tr, j, 10);
+      cell_push_lines(co, s, c, (uint32_t)j + 1);
+    }
     trace_mark(tr, j, 9);
     if (blockIdx.x == 0 && tid == 0) a.alphas[j] = alpha;
-    steps = j + 1;  // (s.w is rewritten by the next phase B, two barriers after these node sums)
+    steps = j + 1;
   }
   if (blockIdx.x == 0 && tid == 0) {
     State st;
@@ -490,14 +543,16 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
   }
 }
 
-// Replaces lanczos_pass_two_impl (src/algorithms/lanczos_two_pass.rs:206-312) for a cell-partitioned operator.
+// Replaces lanczos_pass_two_impl (src/algorithms/lanczos_two_pass.rs:206-312) for a cell-partitioned operator.  The owner
+// warp runs on its own: node sums of generation j in, node values of generation j + 1 out; the workers only ever wait for
+// node values, which were published a whole step earlier.
 template <bool WITH_V>
 __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp op, const CellOp co, const Pass2Args a) {
   extern __shared__ double smem[];
   const CellSmem s = carve_cell<true>(smem, co);
   const CellCtx c = load_cell(co, s);
-  const uint32_t tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t in_warps = 2;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool owner = warp == kWorkerWarps;
   const Trace& tr = a.gs.trace;
   ArcRegs<true> R;
   // coefficients are loaded one step ahead of their use so that no step starts with a dependent load
@@ -511,28 +566,33 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp
   {
     // v_1 = b * (1/||b||) held lazily as (b, 1/||b||); x = y_0 v_1   (lanczos_two_pass.rs:247-258)
     const double y0 = __ldg(a.y);
-    cell_load_arcs<true>(op, co, s, c, a.b, R);
+    if (!owner) {
+      cell_load_arcs<true>(op, co, s, c, a.b, R);
 #pragma unroll
-    for (int r = 0; r < kArcRegs; ++r) {
-      const uint32_t i = tid + r * kBlock;
-      const double v = __dmul_rn(R.W[r], sc);
-      R.X[r] = __dmul_rn(v, y0);
-      if (WITH_V && i < c.nA) __stcs(a.V + __ldg(c.gidx + i), v);
-    }
-    for (uint32_t t = tid; t < c.nown * kLine; t += kBlock) {
-      const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
-      const double bi = u < op.p ? __ldg(a.b + op.m + u) : 0.0;
-      const double v = __dmul_rn(bi, sc);
-      s.n0[t] = bi;
-      s.n1[t] = 0.0;
-      s.nx[t] = __dmul_rn(v, y0);
-      cell_publish_node(co, line, t & 7, bi, 0);
-      if (WITH_V && u < op.p) __stcs(a.V + op.m + u, v);
+      for (int r = 0; r < kArcRegs; ++r) {
+        const uint32_t i = tid + r * kWorkers;
+        const double v = __dmul_rn(R.W[r], sc);
+        R.X[r] = __dmul_rn(v, y0);
+        if (WITH_V && i < c.nA) __stcs(a.V + __ldg(c.gidx + i), v);
+      }
+    } else {
+      for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
+        const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
+        const double bi = u < op.p ? __ldg(a.b + op.m + u) : 0.0;
+        const double v = __dmul_rn(bi, sc);
+        s.n0[t] = bi;
+        s.n1[t] = 0.0;
+        s.nx[t] = __dmul_rn(v, y0);
+        cell_publish_node(co, line, t & 7, bi, 0);
+        if (WITH_V && u < op.p) __stcs(a.V + op.m + u, v);
+      }
     }
     __syncthreads();
-    cell_node_sums(s, c);
-    __syncthreads();
-    cell_push_lines(co, s, c, 0);
+    if (!owner) {
+      cell_node_sums(s, c);
+      bar_workers();
+      cell_push_lines(co, s, c, 0);
+    }
   }
   for (int j = 0; j + 1 < a.steps; ++j) {
     double* Vcol = WITH_V ? a.V + (size_t)(j + 1) * a.ldv : nullptr;
@@ -543,44 +603,55 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp
       c_beta = __ldg(a.betas + j + 1);
       c_y = __ldg(a.y + j + 2);
     }
-    trace_mark(tr, j, 0);
-    if (warp < in_warps) cell_poll_inbox(co, s, c, (uint32_t)j, 0, in_warps);
-    else cell_poll_gather(co, s, c, (uint32_t)j, in_warps, kWarps - in_warps, sc);
-    trace_mark(tr, j, 1);
-    trace_mark_warp(tr, j, 32);
-    __syncthreads();  // also: every warp has finished the node sums of the previous step, s.w may be rewritten
-    trace_mark(tr, j, 2);
-    for (uint32_t t = tid; t < c.nown * kLine; t += kBlock) {
-      const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
-      const double v = __dmul_rn(s.n0[t], sc);
-      const double w = rec_sub(rec_sub(__dmul_rn(sc, s.T[t]), bp, s.n1[t]), alpha, v);
-      const double vn = __dmul_rn(w, sinv);
-      s.n0[t] = w;
-      s.n1[t] = v;
-      cell_publish_node(co, line, t & 7, w, (uint32_t)j + 1);
-      s.nx[t] = __dadd_rn(s.nx[t], __dmul_rn(yj, vn));
-      if (WITH_V && u < op.p) __stcs(Vcol + op.m + u, vn);
+    if (owner) {
+      for (uint32_t o = 0; o < c.nown; ++o) {
+        const double T = cell_poll_inbox(co, s, o, (uint32_t)j);
+        if (lane < kLine) {
+          const uint32_t t = o * kLine + lane, line = blockIdx.x + o * co.Gc, u = line * kLine + lane;
+          const double v = __dmul_rn(s.n0[t], sc);
+          const double w = rec_sub(rec_sub(__dmul_rn(sc, T), bp, s.n1[t]), alpha, v);
+          const double vn = __dmul_rn(w, sinv);
+          s.n0[t] = w;
+          s.n1[t] = v;
+          cell_publish_node(co, line, lane, w, (uint32_t)j + 1);
+          s.nx[t] = __dadd_rn(s.nx[t], __dmul_rn(yj, vn));
+          if (WITH_V && u < op.p) __stcs(Vcol + op.m + u, vn);
+        }
+        __syncwarp();
+      }
+      trace_mark_warp(tr, j, 32);
+    } else {
+      trace_mark(tr, j, 0);
+      cell_poll_gather(co, s, c, (uint32_t)j, 0, kWorkerWarps, sc);
+      trace_mark(tr, j, 1);
+      trace_mark_warp(tr, j, 32);
+      bar_workers();  // also: every warp has finished the node sums of the previous step, s.w may be rewritten
+      trace_mark(tr, j, 2);
+      cell_arc_rows<true, WITH_V>(s, c, R, sc, bp, alpha, sinv, yj, Vcol);
+      trace_mark(tr, j, 3);
+      bar_workers();
+      trace_mark(tr, j, 4);
+      cell_node_sums(s, c);
+      trace_mark_warp(tr, j, 48);
+      bar_workers();
+      trace_mark(tr, j, 6);
+      cell_push_lines(co, s, c, (uint32_t)j + 1);
+      trace_mark(tr, j, 5);
     }
-    cell_arc_rows<true, WITH_V>(s, c, R, sc, bp, alpha, sinv, yj, Vcol);
-    trace_mark(tr, j, 3);
-    __syncthreads();
-    trace_mark(tr, j, 4);
-    cell_node_sums(s, c);
-    trace_mark_warp(tr, j, 48);
-    __syncthreads();
-    cell_push_lines(co, s, c, (uint32_t)j + 1);
-    trace_mark(tr, j, 5);
     sc = sinv;
     bp = beta;
   }
+  if (!owner) {
 #pragma unroll
-  for (int r = 0; r < kArcRegs; ++r) {
-    const uint32_t i = tid + r * kBlock;
-    if (i < c.nA) a.x[__ldg(c.gidx + i)] = R.X[r];
-  }
-  for (uint32_t t = tid; t < c.nown * kLine; t += kBlock) {
-    const uint32_t u = (blockIdx.x + (t >> 3) * co.Gc) * kLine + (t & 7);
-    if (u < op.p) a.x[op.m + u] = s.nx[t];
+    for (int r = 0; r < kArcRegs; ++r) {
+      const uint32_t i = tid + r * kWorkers;
+      if (i < c.nA) a.x[__ldg(c.gidx + i)] = R.X[r];
+    }
+  } else {
+    for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
+      const uint32_t u = (blockIdx.x + (t >> 3) * co.Gc) * kLine + (t & 7);
+      if (u < op.p) a.x[op.m + u] = s.nx[t];
+    }
   }
 }
 
