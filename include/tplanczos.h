@@ -130,7 +130,8 @@ int tpl_op_set_mode(tpl_op* op, int mode);
  * of `ctas` CTAs with `smem_limit` bytes of shared memory each and checks its tables on the host.
  * stats = {fits, tail blocks, head blocks, arc slots per cell, node lines, most entry rows, most node-sum groups,
  * most touched lines, most pushed lines, owned lines per CTA, inbox atoms, largest cell, smallest cell,
- * shared-memory bytes (pass 2), consistency code (0 = consistent), 0}. */
+ * shared-memory bytes (pass 2), consistency code (0 = consistent), shared-memory wavefronts per half-warp gather x1000
+ * (arc rows in the low, node sums in the high 32 bits)}. */
 int tpl_cells_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, size_t smem_limit,
                    uint64_t stats[16]);
 /* Diagnostics: per-CTA, per-step phase timestamps (SM clock) of the resident kernels.  enable(max_steps > 0)

@@ -19,7 +19,10 @@ def plan(m, p, tail, head, ctas=148, smem=SMEM):
                                           stats))
     keys = ["fits", "GR", "GC", "Amax", "L", "max_rows", "max_groups", "max_lines", "max_slots", "max_own", "inbox_atoms",
             "largest", "smallest", "smem", "code"]
-    return dict(zip(keys, list(stats)))
+    out = dict(zip(keys, list(stats)))
+    out["conflicts_arc_rows"] = (stats[15] & 0xffffffff) / 1000.0
+    out["conflicts_node_sums"] = (stats[15] >> 32) / 1000.0
+    return out
 
 
 @pytest.mark.parametrize("m,rho", [(1000, 1), (1000, 3), (5000, 3), (50_000, 3), (50_000, 1), (500_000, 3)])
@@ -31,6 +34,8 @@ def test_netgen_shaped_instances(m, rho):
     assert st["smem"] <= SMEM
     if m >= 50_000:  # balanced: the largest cell stays close to the mean
         assert st["largest"] <= 1.25 * m / (st["GR"] * st["GC"])
+    if m >= 500_000:  # the placement keeps the gathers close to conflict-free (random placement: ~3 wavefronts)
+        assert st["conflicts_arc_rows"] < 1.6 and st["conflicts_node_sums"] < 1.6, st
 
 
 @pytest.mark.parametrize("ctas", [2, 7, 16, 132, 148])

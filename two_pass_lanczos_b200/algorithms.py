@@ -98,8 +98,8 @@ def lanczos_standard(operator: LinOp, b, k: int, callback=None) -> LanczosOutput
     steps, bn = C.c_size_t(), C.c_double()
 
     def _cb(s, vdev, ld, ap, bp_, _u):
-        view = TridiagonalSystemView(np.ctypeslib.as_array(ap, shape=(s,)).copy(),
-                                     np.ctypeslib.as_array(bp_, shape=(max(s - 1, 1),))[:s - 1].copy(), s)
+        betas = np.ctypeslib.as_array(bp_, shape=(s - 1,)).copy() if s > 1 and bp_ else np.zeros(0)
+        view = TridiagonalSystemView(np.ctypeslib.as_array(ap, shape=(s,)).copy(), betas, s)
         return 1 if callback(s, DeviceBasisView(vdev, ld, n, s), view) else 0
 
     cb = STEP_CB(_cb) if callback is not None else C.cast(None, STEP_CB)

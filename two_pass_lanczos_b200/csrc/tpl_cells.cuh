@@ -43,11 +43,13 @@ struct CellOp {
   uint32_t max_groups;   // most node-sum groups (16 lists, one warp) of any cell
   uint32_t max_rows;     // most entry rows (32 lanes x 4 entries) of any cell
   uint32_t max_own;      // owned lines per CTA = ceil(L / Gc)
+  uint32_t max_tl;       // most tail lists of any cell
   uint32_t inbox_atoms;  // atoms per inbox parity
   uint32_t flags;        // experiment switches (TPL_CELL_FLAGS): 1 serial inbox polls, 2 back-off in spin loops
   const uint32_t* hdr;        // [Gc][8] {arcs, lines, slots, groups, entry rows, 0, 0, 0}
   const uint32_t* gidx;       // [Gc][Amax] arc index in the caller's order
-  const uint32_t* lth;        // [Gc][Amax] local tail node | local head node << 16 (equal for a self-loop)
+  const uint32_t* lth;        // [Gc][Amax] tail slot | tail-first << 15 | head slot << 16: indices into the cell's node-value array
+  const uint16_t* tmap;       // [Gc][8 * max_lines] tail slot a polled node value is mirrored into (0xffff: none)
   const uint32_t* lines;      // [Gc][max_lines] touched lines, ascending (local node = 8 * position + node % 8)
   const uint32_t* push;       // [Gc][max_slots] inbox slot of every pushed line
   // node sums: group g (one warp) sums 16 lists, lanes l and l + 16 taking the even / odd entries of list l:
@@ -62,7 +64,10 @@ struct CellOp {
 struct CellSmem {
   double* w;                    // [Amax + 8] arc part of the newest vector (what the node sums are formed from); w[Amax] = 0
   double* d;                    // [Amax] D of the cell's arcs
-  double* nodev;                // [8 * max_lines] node values of the current vector
+  // node values of the current vector: [8 * max_lines by local node | max_tl by tail rank (the arcs of a half-warp have
+  // consecutive ranks: conflict-free) | zero slot (self-loops, empty arc slots)]
+  double* nodev;
+  uint16_t* tmap;               // [8 * max_lines]
   double* sums;                 // [8 * max_slots] node sums of this cell in push order
   double *n0, *n1, *nx, *T;     // [8 * max_own] owned node rows: current / previous vector, x (pass 2), node sums
   double* arv;                  // [Gc] all-reduce values by slot
@@ -75,11 +80,11 @@ struct CellSmem {
 };
 
 __host__ __device__ inline size_t cell_smem_bytes(const CellOp& co, bool pass2) {
-  size_t dbl = 2 * (size_t)co.Amax + 8 + kLine * co.max_lines + kLine * co.max_slots + (size_t)kLine * co.max_own * (pass2 ? 4 : 3) +
+  size_t dbl = 2 * (size_t)co.Amax + 8 + kLine * co.max_lines + co.max_tl + 8 + kLine * co.max_slots + (size_t)kLine * co.max_own * (pass2 ? 4 : 3) +
                co.Gc + kWarps;
   dbl = (dbl + 1) & ~(size_t)1;
   const size_t u32 = (size_t)co.max_lines + co.max_slots + 2 * (size_t)co.max_own;
-  return dbl * 8 + (size_t)co.max_groups * 32 * 16 + (size_t)co.max_rows * 32 * 8 + u32 * 4 + 16;
+  return dbl * 8 + (size_t)co.max_groups * 32 * 16 + (size_t)co.max_rows * 32 * 8 + u32 * 4 + (size_t)kLine * co.max_lines * 2 + 16;
 }
 
 template <bool PASS2>
@@ -88,7 +93,7 @@ __device__ __forceinline__ CellSmem carve_cell(double* base, const CellOp& co) {
   double* d = base;
   s.w = d; d += co.Amax + 8;
   s.d = d; d += co.Amax;
-  s.nodev = d; d += kLine * co.max_lines;
+  s.nodev = d; d += kLine * co.max_lines + co.max_tl + 8;
   s.sums = d; d += kLine * co.max_slots;
   s.n0 = d; d += kLine * co.max_own;
   s.n1 = d; d += kLine * co.max_own;
@@ -103,7 +108,8 @@ __device__ __forceinline__ CellSmem carve_cell(double* base, const CellOp& co) {
   uint32_t* u = reinterpret_cast<uint32_t*>(s.ent4 + (size_t)co.max_rows * 32);
   s.lines = u; u += co.max_lines;
   s.push = u; u += co.max_slots;
-  s.own = u;
+  s.own = u; u += 2 * co.max_own;
+  s.tmap = reinterpret_cast<uint16_t*>(u);
   return s;
 }
 
@@ -126,6 +132,9 @@ __device__ __forceinline__ CellCtx load_cell(const CellOp& co, const CellSmem& s
   x.gidx = co.gidx + (size_t)c * co.Amax;
   const uint32_t* ln = co.lines + (size_t)c * co.max_lines;
   for (uint32_t i = threadIdx.x; i < x.nlines; i += kBlock) s.lines[i] = __ldg(ln + i);
+  const uint16_t* tm = co.tmap + (size_t)c * kLine * co.max_lines;
+  for (uint32_t i = threadIdx.x; i < x.nlines * kLine; i += kBlock) s.tmap[i] = __ldg(tm + i);
+  for (uint32_t i = threadIdx.x; i < kLine * co.max_lines + co.max_tl + 8; i += kBlock) s.nodev[i] = 0.0;
   const uint32_t* ps = co.push + (size_t)c * co.max_slots;
   for (uint32_t i = threadIdx.x; i < x.nslots; i += kBlock) s.push[i] = __ldg(ps + i);
   const uint4* wk = co.walk + (size_t)c * co.max_groups * 32;
@@ -272,8 +281,12 @@ __device__ __forceinline__ void cell_poll_gather(const CellOp& co, const CellSme
                                                  uint32_t warp0, uint32_t nwarps, double scale) {
   const uint4* g = co.gather + (size_t)(gen & 1u) * co.L * kLine;
   const uint32_t tag = gen + 1;
-  for (uint32_t a = threadIdx.x - warp0 * 32; a < c.nlines * kLine; a += nwarps * 32)
-    s.nodev[a] = __dmul_rn(atom_poll(g + (size_t)s.lines[a >> 3] * kLine + (a & 7), tag, co.flags), scale);
+  for (uint32_t a = threadIdx.x - warp0 * 32; a < c.nlines * kLine; a += nwarps * 32) {
+    const double v = __dmul_rn(atom_poll(g + (size_t)s.lines[a >> 3] * kLine + (a & 7), tag, co.flags), scale);
+    const uint32_t mirror = s.tmap[a];
+    s.nodev[a] = v;
+    if (mirror != 0xffffu) s.nodev[mirror] = v;
+  }
 }
 
 __device__ __forceinline__ void cell_publish_node(const CellOp& co, uint32_t line, uint32_t r, double v, uint32_t gen) {
@@ -323,13 +336,14 @@ template <bool PASS2>
 __device__ __forceinline__ double cell_load_arcs(const IncidenceOp& op, const CellOp& co, const CellSmem& s, const CellCtx& c,
                                                  const double* b, ArcRegs<PASS2>& R) {
   const uint32_t* lth = co.lth + (size_t)blockIdx.x * co.Amax;
+  const uint32_t zero_slot = kLine * co.max_lines + co.max_tl;
   double acc = 0.0;
 #pragma unroll
   for (int r = 0; r < kArcRegs; ++r) {
     const uint32_t i = threadIdx.x + r * kWorkers;
     R.W[r] = 0.0;
     R.P[r] = 0.0;
-    R.TH[r] = 0u;
+    R.TH[r] = zero_slot | (zero_slot << 16);
     if (i < c.nA) {
       const uint32_t g = __ldg(c.gidx + i);
       R.W[r] = __ldg(b + g);
@@ -355,11 +369,21 @@ __device__ __forceinline__ double cell_arc_rows(const CellSmem& s, const CellCtx
     if (r * kWorkers < c.nA) {  // uniform: rows of arc slots beyond the cell's last arc are skipped
       const uint32_t i = threadIdx.x + r * kWorkers;
       const uint32_t ii = i < c.nA ? i : 0;
-      const uint32_t t = R.TH[r] & 0xffffu, h = R.TH[r] >> 16;
+      const uint32_t t = R.TH[r] & 0x7fffu, h = R.TH[r] >> 16;
       const double v = __dmul_rn(R.W[r], sc);
       // pass 2 scales the node values once when it polls them; pass 1 only learns sc together with them
       const double xt = PASS2 ? s.nodev[t] : __dmul_rn(s.nodev[t], sc), xh = PASS2 ? s.nodev[h] : __dmul_rn(s.nodev[h], sc);
-      const double wt = rec_sub(arc_row(s.d[ii], v, t, h, xt, xh), bp, R.P[r]);
+      // (A v)_arc in the reference's CSC accumulation order: D v first, then the two node columns by ascending node index
+      // (bit 15: the tail comes first); a self-loop reads the zero slot twice
+      double row = __dmul_rn(s.d[ii], v);
+      if (R.TH[r] & 0x8000u) {
+        row = __dadd_rn(row, xt);
+        row = __dsub_rn(row, xh);
+      } else {
+        row = __dsub_rn(row, xh);
+        row = __dadd_rn(row, xt);
+      }
+      const double wt = rec_sub(row, bp, R.P[r]);
       R.P[r] = v;
       if (PASS2) {
         const double w = rec_sub(wt, alpha, v);

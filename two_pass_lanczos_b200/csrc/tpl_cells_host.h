@@ -15,8 +15,9 @@ namespace tpl {
 struct HostCells {
   bool ok = false;
   uint32_t GR = 0, GC = 0, Gc = 0, Amax = 0, L = 0;
-  uint32_t max_lines = 0, max_slots = 0, max_groups = 0, max_rows = 0, max_own = 0, inbox_atoms = 0;
+  uint32_t max_lines = 0, max_slots = 0, max_groups = 0, max_rows = 0, max_own = 0, max_tl = 0, inbox_atoms = 0;
   std::vector<uint32_t> hdr, gidx, lth, lines, push, slot_base;
+  std::vector<uint16_t> tmap;
   std::vector<uint4> walk;
   std::vector<uint2> ent4;
 };
@@ -26,7 +27,7 @@ inline CellOp cells_probe(const HostCells& h) {
   CellOp co{};
   co.GR = h.GR; co.GC = h.GC; co.Gc = h.Gc; co.Amax = h.Amax; co.L = h.L;
   co.max_lines = h.max_lines; co.max_slots = h.max_slots; co.max_groups = h.max_groups; co.max_rows = h.max_rows;
-  co.max_own = h.max_own; co.inbox_atoms = h.inbox_atoms;
+  co.max_own = h.max_own; co.max_tl = h.max_tl; co.inbox_atoms = h.inbox_atoms;
   return co;
 }
 
@@ -97,6 +98,8 @@ inline void build_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t
   struct Cell {
     std::vector<List> lists;                  // tail lists by rank (longest first), then head lists (longest first)
     std::vector<uint32_t> tlines, hlines, lines;
+    std::vector<uint32_t> tnode;              // tail node of every rank
+    std::vector<uint32_t> arc_code;           // per position: tail rank | tail-first flag << 15 | local head << 16; ~0 = self-loop / empty
     uint32_t nA = 0, njds = 0, nrows = 0;
   };
   std::vector<Cell> cells(Gc);
@@ -152,28 +155,49 @@ inline void build_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t
                    ce.lines.end());
     for (size_t i = 0; i < ce.lines.size(); ++i) local_of_line[ce.lines[i]] = (uint32_t)i;
     auto local = [&](uint32_t u) { return local_of_line[u / kLine] * kLine + u % kLine; };
-    // arc positions: the e-th arc (ascending arc index) of the tail list with rank q sits at rowstart[e] + q; self-loops
-    // follow the lists
+    // Arc positions: row e of the jagged-diagonal order holds one arc of every tail list longer than e, at rowstart[e] + q.
+    // WHICH arc of list q goes to row e is free, and is chosen so that the 16 arcs of an aligned block of positions (the 16
+    // lanes of a half-warp in the arc rows) read their head node values from 16 different shared-memory banks whenever the
+    // list still has such an arc.  Self-loops follow the lists.
     uint32_t* gi = h.gidx.data() + (size_t)c * h.Amax;
-    uint32_t* lt = h.lth.data() + (size_t)c * h.Amax;
     std::vector<uint32_t> pos_of(nA);
+    ce.tnode = tnodes;
+    ce.arc_code.assign(h.Amax, 0xffffffffu);
     {
-      std::vector<uint32_t> seen(tnodes.size(), 0);
+      std::vector<std::vector<uint32_t>> remaining(tnodes.size());
       uint32_t loops = ce.njds;
       for (uint32_t i = 0; i < nA; ++i) {
         const uint32_t j = arcs[i];
-        uint32_t pos;
         if (tail[j] == head[j]) {
-          pos = loops++;
-          lt[pos] = 0;
+          gi[loops] = j;
+          pos_of[i] = loops++;
         } else {
-          const uint32_t q = trank[tail[j]];
-          pos = rs[seen[q]++] + q;
-          lt[pos] = local(tail[j]) | (local(head[j]) << 16);
+          remaining[trank[tail[j]]].push_back(i);
         }
-        gi[pos] = j;
-        pos_of[i] = pos;
       }
+      uint32_t used = 0, block = 0xffffffffu;
+      for (uint32_t e = 0; e < ce.nrows; ++e)
+        for (uint32_t q = 0; q < rs[e + 1] - rs[e]; ++q) {
+          const uint32_t pos = rs[e] + q;
+          if (pos / 16 != block) {
+            block = pos / 16;
+            used = 0;
+          }
+          std::vector<uint32_t>& rem = remaining[q];
+          size_t pick = 0;
+          for (size_t x = 0; x < rem.size(); ++x)
+            if (!(used >> (local(head[arcs[rem[x]]]) & 15u) & 1u)) {
+              pick = x;
+              break;
+            }
+          const uint32_t i = rem[pick];
+          rem.erase(rem.begin() + (long)pick);
+          const uint32_t j = arcs[i], lh = local(head[j]);
+          used |= 1u << (lh & 15u);
+          gi[pos] = j;
+          pos_of[i] = pos;
+          ce.arc_code[pos] = q | (tail[j] < head[j] ? 0x8000u : 0u) | (lh << 16);
+        }
     }
     // the lists: tail list q = positions rowstart[e] + q, head lists = positions of the in-arcs, ascending arc index
     ce.lists.resize(tnodes.size() + hnodes.size());
@@ -196,7 +220,8 @@ inline void build_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t
       const uint32_t j = arcs[i];
       if (tail[j] != head[j]) ce.lists[hfill[head[j]]].pos.push_back((uint16_t)pos_of[i]);
     }
-    if (ce.lines.size() * kLine > 65535u) return;
+    if (ce.lines.size() * kLine > 0x7fffu || tnodes.size() > 0x3fffu) return;
+    h.max_tl = std::max<uint32_t>(h.max_tl, (uint32_t)tnodes.size());
     // reset the scratch arrays for the next cell
     for (uint32_t l : ce.lines) local_of_line[l] = 0xffffffffu;
     for (uint32_t u : tnodes) tcount[u] = 0;
@@ -248,12 +273,35 @@ inline void build_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t
           const size_t slot = (size_t)(std::lower_bound(lv.begin(), lv.end(), line) - lv.begin()) + (li.head ? ntl : 0);
           d.x = (uint32_t)(slot * kLine + li.node % kLine);
           d.y = li.head ? 0x80000000u : 0u;
-          uint16_t* e16 = reinterpret_cast<uint16_t*>(tb.ent4.data() + (size_t)row0 * 32);
-          uint32_t n = 0;
-          for (size_t e = lane >> 4; e < li.pos.size(); e += 2, ++n)  // entry n of this lane: row n / 4, field n % 4
-            e16[((size_t)(n / 4) * 32 + lane) * 4 + n % 4] = li.pos[e];
         }
         tb.walk.push_back(d);
+      }
+      // entries: lane l < 16 takes entries 0, 2, 4, ... of list l, lane l + 16 entries 1, 3, 5, ...  A tail list keeps its row
+      // order (the 16 lists of a group then read consecutive words); the entries of a HEAD list may be taken in any fixed
+      // order, and are ordered so that the 16 lanes of a half-warp hit different banks whenever possible.
+      {
+        uint16_t* e16 = reinterpret_cast<uint16_t*>(tb.ent4.data() + (size_t)row0 * 32);
+        std::vector<std::vector<uint16_t>> rem(16);
+        for (uint32_t l = 0; l < 16; ++l)
+          if (g * 16 + l < nlists) rem[l] = ce.lists[g * 16 + l].pos;
+        for (uint32_t n = 0; n < rows * 4; ++n)
+          for (uint32_t sub = 0; sub < 2; ++sub) {
+            uint32_t used = 0;
+            for (uint32_t l = 0; l < 16; ++l) {
+              if (rem[l].empty()) continue;
+              size_t pick = 0;
+              if (ce.lists[g * 16 + l].head)
+                for (size_t x = 0; x < rem[l].size(); ++x)
+                  if (!(used >> (rem[l][x] & 15u) & 1u)) {
+                    pick = x;
+                    break;
+                  }
+              const uint16_t pos = rem[l][pick];
+              rem[l].erase(rem[l].begin() + (long)pick);
+              used |= 1u << (pos & 15u);
+              e16[((size_t)(n / 4) * 32 + sub * 16 + l) * 4 + n % 4] = pos;
+            }
+          }
       }
       row0 += rows;
     }
@@ -266,6 +314,24 @@ inline void build_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t
   h.max_slots = std::max<uint32_t>(h.max_slots, 1);
   h.max_groups = std::max<uint32_t>(h.max_groups, 1);
   h.max_rows = std::max<uint32_t>(h.max_rows, 1);
+  h.max_tl = std::max<uint32_t>(h.max_tl, 1);
+  // node values live in one shared-memory array: [local node (8 per touched line) | tail value by rank | zero slot]
+  const uint32_t NB = kLine * h.max_lines, ZERO = NB + h.max_tl;
+  if (ZERO > 0x7fffu) return;
+  h.tmap.assign((size_t)Gc * NB, 0xffffu);
+  for (uint32_t c = 0; c < Gc; ++c) {
+    const Cell& ce = cells[c];
+    uint32_t* lt = h.lth.data() + (size_t)c * h.Amax;
+    for (uint32_t i = 0; i < h.Amax; ++i) {
+      const uint32_t code = ce.arc_code.empty() ? 0xffffffffu : ce.arc_code[i];
+      lt[i] = code == 0xffffffffu ? (ZERO | (ZERO << 16)) : ((NB + (code & 0x3fffu)) | (code & 0x8000u) | (code & 0xffff0000u));
+    }
+    for (size_t q = 0; q < ce.tnode.size(); ++q) {
+      const uint32_t u = ce.tnode[q];
+      const size_t li = (size_t)(std::lower_bound(ce.lines.begin(), ce.lines.end(), u / kLine) - ce.lines.begin());
+      h.tmap[(size_t)c * NB + li * kLine + u % kLine] = (uint16_t)(NB + q);
+    }
+  }
   h.lines.assign((size_t)Gc * h.max_lines, 0);
   h.push.assign((size_t)Gc * h.max_slots, 0);
   h.walk.assign((size_t)Gc * h.max_groups * 32, make_uint4(0xffffffffu, 0, 0, 0));
@@ -287,6 +353,50 @@ inline void build_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t
   // shared-memory fit (pass 2 is the larger layout)
   if (cell_smem_bytes(cells_probe(h), true) + 1024 > smem_limit) return;
   h.ok = true;
+}
+
+// Bank-conflict statistics of a partition (diagnostic): average number of shared-memory wavefronts per half-warp access
+// (1.0 = conflict-free), x1000, of (a) the head node values gathered by the arc rows and (b) the arc values gathered by
+// the node sums.
+inline void cell_conflicts(const HostCells& h, uint32_t& arc_rows_x1000, uint32_t& node_sums_x1000) {
+  uint64_t wa = 0, na = 0, wb = 0, nb = 0;
+  auto wavefronts = [](const uint32_t* addr, int n) {
+    int cnt[16] = {0}, mx = 0;
+    for (int i = 0; i < n; ++i) {
+      bool dup = false;
+      for (int k = 0; k < i; ++k) dup |= addr[k] == addr[i];  // same word: broadcast
+      if (!dup) mx = std::max(mx, ++cnt[addr[i] & 15u]);
+    }
+    return mx;
+  };
+  for (uint32_t c = 0; c < h.Gc; ++c) {
+    const uint32_t* hd = h.hdr.data() + (size_t)c * 8;
+    const uint32_t* lt = h.lth.data() + (size_t)c * h.Amax;
+    for (uint32_t b0 = 0; b0 < hd[0]; b0 += 16) {
+      uint32_t a[16];
+      int n = 0;
+      for (uint32_t i = b0; i < std::min(hd[0], b0 + 16); ++i) a[n++] = lt[i] >> 16;
+      wa += wavefronts(a, n);
+      ++na;
+    }
+    const uint4* wk = h.walk.data() + (size_t)c * h.max_groups * 32;
+    const uint2* e4 = h.ent4.data() + (size_t)c * h.max_rows * 32;
+    for (uint32_t g = 0; g < hd[3]; ++g)
+      for (uint32_t k = 0; k < wk[g * 32].w; ++k)
+        for (uint32_t f = 0; f < 4; ++f)
+          for (uint32_t half = 0; half < 2; ++half) {
+            uint32_t a[16];
+            for (uint32_t l = 0; l < 16; ++l) {
+              const uint2 e = e4[(size_t)(wk[g * 32].z + k) * 32 + half * 16 + l];
+              const uint32_t w = f < 2 ? e.x : e.y;
+              a[l] = (f & 1) ? w >> 16 : w & 0xffffu;
+            }
+            wb += wavefronts(a, 16);
+            ++nb;
+          }
+  }
+  arc_rows_x1000 = na ? (uint32_t)(wa * 1000 / na) : 0;
+  node_sums_x1000 = nb ? (uint32_t)(wb * 1000 / nb) : 0;
 }
 
 // Host-side consistency check of a partition (diagnostic, also run by the CPU test-suite): every arc sits in exactly
@@ -318,13 +428,20 @@ inline int check_cells(size_t m, size_t p, const uint32_t* tail, const uint32_t*
       if (j >= m || seen[j]) return 3;
       seen[j] = 1;
       wl[i] = w[j];
-      const uint32_t t = lt[i] & 0xffffu, hh = lt[i] >> 16;
+      const uint32_t NB = kLine * h.max_lines, ZERO = NB + h.max_tl;
+      const uint32_t t = lt[i] & 0x7fffu, hh = lt[i] >> 16;
       if (tail[j] == head[j]) {
-        if (t != hh) return 4;
+        if (t != ZERO || hh != ZERO) return 4;
         continue;
       }
-      if (t / kLine >= nlines || hh / kLine >= nlines) return 5;
-      if (ln[t / kLine] * kLine + t % kLine != tail[j] || ln[hh / kLine] * kLine + hh % kLine != head[j]) return 6;
+      if (t < NB || t >= ZERO || hh / kLine >= nlines) return 5;
+      const uint16_t* tm = h.tmap.data() + (size_t)c * NB;
+      uint32_t tl = 0xffffffffu;  // the local node whose value is mirrored into tail slot t
+      for (uint32_t a = 0; a < nlines * kLine; ++a)
+        if (tm[a] == t) tl = a;
+      if (tl == 0xffffffffu) return 15;
+      if (ln[tl / kLine] * kLine + tl % kLine != tail[j] || ln[hh / kLine] * kLine + hh % kLine != head[j]) return 6;
+      if (((lt[i] >> 15) & 1u) != (tail[j] < head[j] ? 1u : 0u)) return 16;
     }
     std::vector<double> sums((size_t)nslots * kLine, 0.0);
     std::vector<uint8_t> sset(sums.size(), 0);

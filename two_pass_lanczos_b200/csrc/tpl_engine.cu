@@ -701,6 +701,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       if (!rc) rc = dev_upload(op, &co.gidx, hc.gidx);
       if (!rc) rc = dev_upload(op, &co.lth, hc.lth);
       if (!rc) rc = dev_upload(op, &co.lines, hc.lines);
+      if (!rc) rc = dev_upload(op, &co.tmap, hc.tmap);
       if (!rc) rc = dev_upload(op, &co.push, hc.push);
       if (!rc) rc = dev_upload(op, &co.walk, hc.walk);
       if (!rc) rc = dev_upload(op, &co.ent4, hc.ent4);
@@ -856,6 +857,9 @@ int tpl_cells_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* hea
   if (hc.ok) {
     stats[13] = tpl::cell_smem_bytes(tpl::cells_probe(hc), true);
     stats[14] = (uint64_t)tpl::check_cells(m, p, tail, head, hc);
+    uint32_t ca = 0, cb = 0;
+    tpl::cell_conflicts(hc, ca, cb);
+    stats[15] = (uint64_t)ca | ((uint64_t)cb << 32);
   }
   return TPL_OK;
 }
