@@ -46,6 +46,8 @@ def report(name, tr, labels, extra):
         prev = v.mean()
     step_len = (tr[:, 9:k - 3, 0] - tr[:, 8:k - 4, 0]).mean()
     print(f"  step length {step_len:.0f} cycles; node sums done + barrier at {relc[:, :, extra].mean():.0f}")
+    if extra == 10:
+        print(f"  phase A: scalars known at {relc[:, :, 11].mean():.0f}, arc rows done (thread 0) at {relc[:, :, 12].mean():.0f}")
     for base, lab in ((32, "polls done, by warp"), (48, "sums pushed, by warp")):
         v = relc[:, :, base:base + 15].mean(axis=(0, 1))
         mx = relc[:, :, base:base + 15].max(axis=2).mean()

@@ -30,6 +30,8 @@ namespace tpl {
 
 constexpr uint32_t kLine = 8;        // nodes per line = atoms per 128-byte line
 constexpr int kArcRegs = 9;          // arcs per worker thread; the arc part of the vectors and of x lives in REGISTERS for a whole pass
+constexpr int kArcBatch = 3;         // arcs whose shared-memory operands are requested together
+constexpr uint32_t kArCopies = 12;   // copies of every all-reduce line
 constexpr uint32_t kWorkers = kBlock - 32;         // warps 0..14 work on the arcs; warp 15 is the OWNER warp (node rows of the owned lines)
 constexpr uint32_t kWorkerWarps = kWorkers / 32;
 constexpr uint32_t kCellArcs = kArcRegs * kWorkers;  // arc slots of a cell (4320)
@@ -45,7 +47,6 @@ struct CellOp {
   uint32_t max_own;      // owned lines per CTA = ceil(L / Gc)
   uint32_t max_tl;       // most tail lists of any cell
   uint32_t inbox_atoms;  // atoms per inbox parity
-  uint32_t flags;        // experiment switches (TPL_CELL_FLAGS): 1 serial inbox polls, 2 back-off in spin loops
   const uint32_t* hdr;        // [Gc][8] {arcs, lines, slots, groups, entry rows, 0, 0, 0}
   const uint32_t* gidx;       // [Gc][Amax] arc index in the caller's order
   const uint32_t* lth;        // [Gc][Amax] tail slot | tail-first << 15 | head slot << 16: indices into the cell's node-value array
@@ -61,55 +62,93 @@ struct CellOp {
   uint4* ar;
 };
 
-struct CellSmem {
-  double* w;                    // [Amax + 8] arc part of the newest vector (what the node sums are formed from); w[Amax] = 0
-  double* d;                    // [Amax] D of the cell's arcs
+// ----------------------------------------------------------------------------- shared memory
+// Every array is addressed through its 32-bit shared-window byte address with explicit ld/st.shared: with generic pointers
+// the compiler re-derives the window base (S2UR SR_CgaCtaId + ULEA) and 64-bit addresses at every access (measured: ~15 of
+// the ~40 instructions per arc row in the first version of these kernels).
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct CellSmem {  // shared-window byte addresses
+  uint32_t w;      // f64 [Amax + 8] arc part of the newest vector (what the node sums are formed from); w[Amax] = 0
+  uint32_t d;      // f64 [Amax] D of the cell's arcs
   // node values of the current vector: [8 * max_lines by local node | max_tl by tail rank (the arcs of a half-warp have
   // consecutive ranks: conflict-free) | zero slot (self-loops, empty arc slots)]
-  double* nodev;
-  uint16_t* tmap;               // [8 * max_lines]
-  double* sums;                 // [8 * max_slots] node sums of this cell in push order
-  double *n0, *n1, *nx, *T;     // [8 * max_own] owned node rows: current / previous vector, x (pass 2), node sums
-  double* arv;                  // [Gc] all-reduce values by slot
-  double* wpart;                // [kWarps]
-  uint4* walk;                  // [max_groups * 32]
-  uint2* ent4;                  // [max_rows * 32]
-  uint32_t* lines;              // [max_lines]
-  uint32_t* push;               // [max_slots]
-  uint32_t* own;                // [2 * max_own] {first slot, slots} of the owned lines
+  uint32_t nodev;
+  uint32_t sums;   // f64 [8 * max_slots] node sums of this cell in push order
+  uint32_t n0, n1, nx, T;  // f64 [8 * max_own] owned node rows: current / previous vector, x (pass 2), node sums
+  uint32_t arv;    // f64 [Gc] all-reduce values by slot
+  uint32_t wpart;  // f64 [kWarps]
+  uint32_t walk;   // uint4 [max_groups * 32]
+  uint32_t ent4;   // uint2 [max_rows * 32]
+  uint32_t lines;  // u32 [max_lines]
+  uint32_t push;   // u32 [max_slots]
+  uint32_t own;    // u32 [2 * max_own] {first slot, slots} of the owned lines
+  uint32_t tmap;   // u16 [8 * max_lines]
+  uint32_t th;     // u32 [Amax] tail / head slots of the arcs (pass 2 only: pass 1 has the registers to keep them)
 };
 
 __host__ __device__ inline size_t cell_smem_bytes(const CellOp& co, bool pass2) {
-  size_t dbl = 2 * (size_t)co.Amax + 8 + kLine * co.max_lines + co.max_tl + 8 + kLine * co.max_slots + (size_t)kLine * co.max_own * (pass2 ? 4 : 3) +
-               co.Gc + kWarps;
+  size_t dbl = 2 * (size_t)co.Amax + 8 + kLine * co.max_lines + co.max_tl + 8 + kLine * co.max_slots +
+               (size_t)kLine * co.max_own * (pass2 ? 4 : 3) + co.Gc + kWarps;
   dbl = (dbl + 1) & ~(size_t)1;
   const size_t u32 = (size_t)co.max_lines + co.max_slots + 2 * (size_t)co.max_own;
-  return dbl * 8 + (size_t)co.max_groups * 32 * 16 + (size_t)co.max_rows * 32 * 8 + u32 * 4 + (size_t)kLine * co.max_lines * 2 + 16;
+  return dbl * 8 + (size_t)co.max_groups * 32 * 16 + (size_t)co.max_rows * 32 * 8 + u32 * 4 + (size_t)kLine * co.max_lines * 2 + 16 +
+         (pass2 ? (size_t)co.Amax * 4 + 4 : 0);
 }
 
 template <bool PASS2>
 __device__ __forceinline__ CellSmem carve_cell(double* base, const CellOp& co) {
   CellSmem s;
-  double* d = base;
-  s.w = d; d += co.Amax + 8;
-  s.d = d; d += co.Amax;
-  s.nodev = d; d += kLine * co.max_lines + co.max_tl + 8;
-  s.sums = d; d += kLine * co.max_slots;
-  s.n0 = d; d += kLine * co.max_own;
-  s.n1 = d; d += kLine * co.max_own;
-  s.nx = d; d += PASS2 ? kLine * co.max_own : 0;
-  s.T = d; d += kLine * co.max_own;
-  s.arv = d; d += co.Gc;
-  s.wpart = d; d += kWarps;
-  size_t off = (size_t)(d - base);
-  off = (off + 1) & ~(size_t)1;  // 16-byte alignment
-  s.walk = reinterpret_cast<uint4*>(base + off);
-  s.ent4 = reinterpret_cast<uint2*>(s.walk + (size_t)co.max_groups * 32);
-  uint32_t* u = reinterpret_cast<uint32_t*>(s.ent4 + (size_t)co.max_rows * 32);
-  s.lines = u; u += co.max_lines;
-  s.push = u; u += co.max_slots;
-  s.own = u; u += 2 * co.max_own;
-  s.tmap = reinterpret_cast<uint16_t*>(u);
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(base);
+  s.w = a; a += (co.Amax + 8) * 8;
+  s.d = a; a += co.Amax * 8;
+  s.nodev = a; a += (kLine * co.max_lines + co.max_tl + 8) * 8;
+  s.sums = a; a += kLine * co.max_slots * 8;
+  s.n0 = a; a += kLine * co.max_own * 8;
+  s.n1 = a; a += kLine * co.max_own * 8;
+  s.nx = a; a += PASS2 ? kLine * co.max_own * 8 : 0;
+  s.T = a; a += kLine * co.max_own * 8;
+  s.arv = a; a += co.Gc * 8;
+  s.wpart = a; a += kWarps * 8;
+  a = (a + 15u) & ~15u;
+  s.walk = a; a += co.max_groups * 32 * 16;
+  s.ent4 = a; a += co.max_rows * 32 * 8;
+  s.lines = a; a += co.max_lines * 4;
+  s.push = a; a += co.max_slots * 4;
+  s.own = a; a += 2 * co.max_own * 4;
+  s.tmap = a; a += kLine * co.max_lines * 2;
+  s.th = (a + 3u) & ~3u;
   return s;
 }
 
@@ -131,23 +170,23 @@ __device__ __forceinline__ CellCtx load_cell(const CellOp& co, const CellSmem& s
   x.nown = co.L > c ? (co.L - c + co.Gc - 1) / co.Gc : 0;
   x.gidx = co.gidx + (size_t)c * co.Amax;
   const uint32_t* ln = co.lines + (size_t)c * co.max_lines;
-  for (uint32_t i = threadIdx.x; i < x.nlines; i += kBlock) s.lines[i] = __ldg(ln + i);
+  for (uint32_t i = threadIdx.x; i < x.nlines; i += kBlock) sts_u32(s.lines + i * 4, __ldg(ln + i));
   const uint16_t* tm = co.tmap + (size_t)c * kLine * co.max_lines;
-  for (uint32_t i = threadIdx.x; i < x.nlines * kLine; i += kBlock) s.tmap[i] = __ldg(tm + i);
-  for (uint32_t i = threadIdx.x; i < kLine * co.max_lines + co.max_tl + 8; i += kBlock) s.nodev[i] = 0.0;
+  for (uint32_t i = threadIdx.x; i < x.nlines * kLine; i += kBlock) sts_u16(s.tmap + i * 2, __ldg(tm + i));
+  for (uint32_t i = threadIdx.x; i < kLine * co.max_lines + co.max_tl + 8; i += kBlock) sts_f64(s.nodev + i * 8, 0.0);
   const uint32_t* ps = co.push + (size_t)c * co.max_slots;
-  for (uint32_t i = threadIdx.x; i < x.nslots; i += kBlock) s.push[i] = __ldg(ps + i);
+  for (uint32_t i = threadIdx.x; i < x.nslots; i += kBlock) sts_u32(s.push + i * 4, __ldg(ps + i));
   const uint4* wk = co.walk + (size_t)c * co.max_groups * 32;
-  for (uint32_t i = threadIdx.x; i < x.ngroups * 32; i += kBlock) s.walk[i] = __ldg(wk + i);
+  for (uint32_t i = threadIdx.x; i < x.ngroups * 32; i += kBlock) sts_v4(s.walk + i * 16, __ldg(wk + i));
   const uint2* e4 = co.ent4 + (size_t)c * co.max_rows * 32;
-  for (uint32_t i = threadIdx.x; i < nrows * 32; i += kBlock) s.ent4[i] = __ldg(e4 + i);
-  for (uint32_t i = threadIdx.x; i < x.nslots * kLine; i += kBlock) s.sums[i] = 0.0;  // atoms without a list stay zero
-  for (uint32_t i = threadIdx.x; i < 8; i += kBlock) s.w[co.Amax + i] = 0.0;          // the zero slot padding entries point at
+  for (uint32_t i = threadIdx.x; i < nrows * 32; i += kBlock) sts_v2(s.ent4 + i * 8, __ldg(e4 + i));
+  for (uint32_t i = threadIdx.x; i < x.nslots * kLine; i += kBlock) sts_f64(s.sums + i * 8, 0.0);  // atoms without a list stay zero
+  for (uint32_t i = threadIdx.x; i < 8; i += kBlock) sts_f64(s.w + (co.Amax + i) * 8, 0.0);        // the zero slot padding entries point at
   for (uint32_t o = threadIdx.x; o < x.nown; o += kBlock) {
     const uint32_t l = c + o * co.Gc;
     const uint32_t b0 = __ldg(co.slot_base + l);
-    s.own[2 * o] = b0;
-    s.own[2 * o + 1] = __ldg(co.slot_base + l + 1) - b0;
+    sts_u32(s.own + (2 * o) * 4, b0);
+    sts_u32(s.own + (2 * o + 1) * 4, __ldg(co.slot_base + l + 1) - b0);
   }
   return x;
 }
@@ -160,29 +199,12 @@ __device__ __forceinline__ uint4 atom_pack(double v, uint32_t tag) {
 __device__ __forceinline__ double atom_value(uint4 f) {
   return __longlong_as_double((long long)(((unsigned long long)f.z << 32) | f.x));
 }
-__device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-// polling load: flags 8 = ld.global.cg, 16 = ld.volatile, else ld.relaxed.gpu
-__device__ __forceinline__ uint4 ld_atom(const uint4* p, uint32_t flags) {
-  if (flags & 8u) return ld_cg_v4(p);
-  if (flags & 16u) return ld_volatile_v4(p);
-  return ld_relaxed_gpu_v4(p);
-}
-__device__ __forceinline__ double atom_poll(const uint4* p, uint32_t tag, uint32_t flags = 0) {
-  uint4 f = ld_atom(p, flags);
+__device__ __forceinline__ double atom_poll(const uint4* p, uint32_t tag) {
+  uint4 f = ld_relaxed_gpu_v4(p);
   uint32_t spins = 0;
   while (f.y != tag || f.w != tag) {
     if (++spins > kSpinLimit) __trap();
-    if (flags & 2u) __nanosleep(100);
-    f = ld_atom(p, flags);
+    f = ld_relaxed_gpu_v4(p);
   }
   return atom_value(f);
 }
@@ -195,43 +217,43 @@ __device__ __forceinline__ void bar_arrive_top() { asm volatile("bar.arrive 2, %
 __device__ __forceinline__ void bar_wait_top() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
 
 // ----------------------------------------------------------------------------- exchange steps
+__device__ __forceinline__ double flip_sign(double v, uint32_t mask) {
+  return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+}
 // Node sums of the arc values s.w of this cell -> s.sums.  One warp per group of 16 lists; lane l (< 16) adds the even
 // entries of list l in order, lane l + 16 the odd ones, then the two halves are added.  A row of entries is one 8-byte
-// word per lane (four 16-bit positions), rows of a group are 32 words apart: every load below is conflict-free except the
-// gathers of the head lists.  The sign (tail +, head -) is applied by flipping the sign bit (a - x == a + (-x) exactly).
-// Caller syncs before cell_push_lines.
+// word per lane (four 16-bit positions), rows of a group are 32 words apart.  The sign (tail +, head -) is applied by
+// flipping the sign bit (a - x == a + (-x) exactly).  Caller syncs before cell_push_lines.
 __device__ __forceinline__ void cell_node_sums(const CellSmem& s, const CellCtx& c) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t g = warp; g < c.ngroups; g += kWorkerWarps) {
-    const uint4 d = s.walk[g * 32 + lane];
-    const uint2* row = s.ent4 + (size_t)d.z * 32 + lane;
+    const uint4 d = lds_v4(s.walk + (g * 32 + lane) * 16);
+    uint32_t row = s.ent4 + (d.z * 32 + lane) * 8;
     double acc = 0.0;
-    uint2 e = d.w ? row[0] : make_uint2(0, 0);
+    uint2 e = make_uint2(0, 0);
+    if (d.w) e = lds_v2(row);
     for (uint32_t k = 0; k < d.w; ++k) {
-      const uint2 nxt = k + 1 < d.w ? row[(k + 1) * 32] : e;  // the next row is requested before this one is consumed
-      const double v0 = s.w[e.x & 0xffffu], v1 = s.w[e.x >> 16], v2 = s.w[e.y & 0xffffu], v3 = s.w[e.y >> 16];
-      acc = __dadd_rn(acc, __hiloint2double(__double2hiint(v0) ^ (int)d.y, __double2loint(v0)));
-      acc = __dadd_rn(acc, __hiloint2double(__double2hiint(v1) ^ (int)d.y, __double2loint(v1)));
-      acc = __dadd_rn(acc, __hiloint2double(__double2hiint(v2) ^ (int)d.y, __double2loint(v2)));
-      acc = __dadd_rn(acc, __hiloint2double(__double2hiint(v3) ^ (int)d.y, __double2loint(v3)));
+      row += 32 * 8;
+      uint2 nxt = e;
+      if (k + 1 < d.w) nxt = lds_v2(row);  // the next row is requested before this one is consumed
+      const double v0 = lds_f64(s.w + (e.x & 0xffffu) * 8), v1 = lds_f64(s.w + (e.x >> 16) * 8);
+      const double v2 = lds_f64(s.w + (e.y & 0xffffu) * 8), v3 = lds_f64(s.w + (e.y >> 16) * 8);
+      acc = __dadd_rn(acc, flip_sign(v0, d.y));
+      acc = __dadd_rn(acc, flip_sign(v1, d.y));
+      acc = __dadd_rn(acc, flip_sign(v2, d.y));
+      acc = __dadd_rn(acc, flip_sign(v3, d.y));
       e = nxt;
     }
     acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
-    if (lane < 16 && d.x != 0xffffffffu) s.sums[d.x] = acc;
+    if (lane < 16 && d.x != 0xffffffffu) sts_f64(s.sums + d.x * 8, acc);
   }
-}
-__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // s.sums -> the owners' inboxes as generation `gen`, one whole line per 8 adjacent lanes.
 __device__ __forceinline__ void cell_push_lines(const CellOp& co, const CellSmem& s, const CellCtx& c, uint32_t gen) {
   uint4* box = co.inbox + (size_t)(gen & 1u) * co.inbox_atoms;
   const uint32_t tag = gen + 1;
-  for (uint32_t t = threadIdx.x; t < c.nslots * kLine; t += kWorkers) {
-    uint4* dst = box + (size_t)s.push[t >> 3] * kLine + (t & 7);
-    if (co.flags & 4u) st_volatile_v4(dst, atom_pack(s.sums[t], tag));
-    else st_relaxed_gpu_v4(dst, atom_pack(s.sums[t], tag));
-  }
+  for (uint32_t t = threadIdx.x; t < c.nslots * kLine; t += kWorkers)
+    st_relaxed_gpu_v4(box + (size_t)lds_u32(s.push + (t >> 3) * 4) * kLine + (t & 7), atom_pack(lds_f64(s.sums + t * 8), tag));
 }
 
 // Owner side: the sum of the contributions to node r = lane & 7 of owned line o, generation `gen` (same value in the
@@ -241,7 +263,7 @@ __device__ __forceinline__ double cell_poll_inbox(const CellOp& co, const CellSm
   const uint32_t tag = gen + 1;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t r = lane & 7, q = lane >> 3;
-  const uint32_t b0 = s.own[2 * o], K = s.own[2 * o + 1];
+  const uint32_t b0 = lds_u32(s.own + (2 * o) * 4), K = lds_u32(s.own + (2 * o + 1) * 4);
   const uint4* mine = box + (size_t)b0 * kLine + r;
   double t = 0.0;
   for (uint32_t k0 = 0; k0 < K; k0 += 32) {
@@ -254,7 +276,7 @@ __device__ __forceinline__ double cell_poll_inbox(const CellOp& co, const CellSm
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t k = k0 + q + 4 * i;
-        if (k < K) f[i] = ld_atom(mine + (size_t)k * kLine, co.flags);
+        if (k < K) f[i] = ld_relaxed_gpu_v4(mine + (size_t)k * kLine);
       }
       pending = false;
 #pragma unroll
@@ -276,16 +298,16 @@ __device__ __forceinline__ double cell_poll_inbox(const CellOp& co, const CellSm
   return t;
 }
 
-// Node values of the touched lines, generation `gen`, times `scale` -> nodev.
+// Node values of the touched lines, generation `gen`, times `scale` -> nodev (and the by-rank mirror of the tails).
 __device__ __forceinline__ void cell_poll_gather(const CellOp& co, const CellSmem& s, const CellCtx& c, uint32_t gen,
                                                  uint32_t warp0, uint32_t nwarps, double scale) {
   const uint4* g = co.gather + (size_t)(gen & 1u) * co.L * kLine;
   const uint32_t tag = gen + 1;
   for (uint32_t a = threadIdx.x - warp0 * 32; a < c.nlines * kLine; a += nwarps * 32) {
-    const double v = __dmul_rn(atom_poll(g + (size_t)s.lines[a >> 3] * kLine + (a & 7), tag, co.flags), scale);
-    const uint32_t mirror = s.tmap[a];
-    s.nodev[a] = v;
-    if (mirror != 0xffffu) s.nodev[mirror] = v;
+    const double v = __dmul_rn(atom_poll(g + (size_t)lds_u32(s.lines + (a >> 3) * 4) * kLine + (a & 7), tag), scale);
+    const uint32_t mirror = lds_u16(s.tmap + a * 2);
+    sts_f64(s.nodev + a * 8, v);
+    if (mirror != 0xffffu) sts_f64(s.nodev + mirror * 8, v);
   }
 }
 
@@ -293,15 +315,16 @@ __device__ __forceinline__ void cell_publish_node(const CellOp& co, uint32_t lin
   st_relaxed_gpu_v4(co.gather + ((size_t)(gen & 1u) * co.L + line) * kLine + r, atom_pack(v, gen + 1));
 }
 
-// All-reduce, publishing half: the CTA's partial (already summed over the warps into wpart, caller synced) goes out as
-// one whole line (eight copies of the atom, lanes 0..7).
+// All-reduce, publishing half (owner warp): the CTA's partial (already summed over the warps into wpart, caller synced)
+// goes out as one whole line (eight copies of the atom, lanes 0..7).
 __device__ __forceinline__ void cell_ar_publish(const CellOp& co, const CellSmem& s, uint32_t epoch) {
-  if (threadIdx.x >= kBlock - 32) {  // the last warp: the first ones own the longest node-sum lists
-    const uint32_t lane = threadIdx.x & 31;
-    double t = lane < kWarps ? s.wpart[lane] : 0.0;
-    t = warp_sum(t);
-    if (lane < kLine) st_relaxed_gpu_v4(co.ar + ((size_t)(epoch & 1u) * co.Gc + blockIdx.x) * kLine + lane, atom_pack(t, epoch));
-  }
+  const uint32_t lane = threadIdx.x & 31;
+  double t = lane < kWarps ? lds_f64(s.wpart + lane * 8) : 0.0;
+  t = warp_sum(t);
+  // kArCopies copies of the line: a copy is polled by Gc / kArCopies CTAs instead of all of them
+  const uint4 atom = atom_pack(t, epoch);
+  for (uint32_t q = lane; q < kArCopies * kLine; q += 32)
+    st_relaxed_gpu_v4(co.ar + (((size_t)(epoch & 1u) * kArCopies + (q >> 3)) * co.Gc + blockIdx.x) * kLine + (q & 7), atom);
 }
 // All-reduce, polling half: thread t of the first ceil(Gc / 32) warps polls the line of CTA (t + cta) % Gc (rotated so
 // that the CTAs do not all start on the same line).  Caller syncs, then every warp calls cell_ar_total.
@@ -309,17 +332,28 @@ __device__ __forceinline__ void cell_ar_poll(const CellOp& co, const CellSmem& s
   if (threadIdx.x < co.Gc) {
     uint32_t slot = threadIdx.x + blockIdx.x;
     slot = slot >= co.Gc ? slot - co.Gc : slot;
-    s.arv[slot] = atom_poll(co.ar + ((size_t)(epoch & 1u) * co.Gc + slot) * kLine + (blockIdx.x & 7u), epoch, co.flags);
+    sts_f64(s.arv + slot * 8, atom_poll(co.ar + (((size_t)(epoch & 1u) * kArCopies + blockIdx.x % kArCopies) * co.Gc + slot) * kLine + ((blockIdx.x / kArCopies) & 7u), epoch));
   }
 }
 __device__ __forceinline__ double cell_ar_total(const CellOp& co, const CellSmem& s) {
+  const uint32_t lane = threadIdx.x & 31;
   double t = 0.0;
-  for (uint32_t i = threadIdx.x & 31; i < co.Gc; i += 32) t = __dadd_rn(t, s.arv[i]);
+  for (uint32_t i0 = 0; i0 < co.Gc; i0 += 32 * 6) {  // one trip for any grid of up to 192 CTAs: six loads in flight, then the adds
+    double v[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const uint32_t i = i0 + lane + 32 * u;
+      v[u] = i < co.Gc ? lds_f64(s.arv + i * 8) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u)
+      if (i0 + lane + 32 * u < co.Gc) t = __dadd_rn(t, v[u]);
+  }
   return warp_sum(t);
 }
 __device__ __forceinline__ void cell_block_partial(const CellSmem& s, double acc) {
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) s.wpart[threadIdx.x >> 5] = acc;
+  if ((threadIdx.x & 31) == 0) sts_f64(s.wpart + (threadIdx.x >> 5) * 8, acc);
 }
 
 // The arcs of a cell are spread over the worker threads, arc r of thread t sitting at position t + r * kWorkers of the
@@ -328,7 +362,7 @@ __device__ __forceinline__ void cell_block_partial(const CellSmem& s, double acc
 template <bool PASS2>
 struct ArcRegs {
   double W[kArcRegs], P[kArcRegs], X[PASS2 ? kArcRegs : 1];
-  uint32_t TH[kArcRegs];
+  uint32_t TH[PASS2 ? 1 : kArcRegs];  // pass 2 reads them from shared memory (s.th)
 };
 
 // W = b, previous vector = 0; also writes b to s.w for the first node sums.  Returns the partial of ||b||^2.
@@ -343,13 +377,14 @@ __device__ __forceinline__ double cell_load_arcs(const IncidenceOp& op, const Ce
     const uint32_t i = threadIdx.x + r * kWorkers;
     R.W[r] = 0.0;
     R.P[r] = 0.0;
-    R.TH[r] = zero_slot | (zero_slot << 16);
+    if (!PASS2) R.TH[r] = zero_slot | (zero_slot << 16);
     if (i < c.nA) {
       const uint32_t g = __ldg(c.gidx + i);
       R.W[r] = __ldg(b + g);
-      R.TH[r] = __ldg(lth + i);
-      s.d[i] = __ldg(op.d + g);
-      s.w[i] = R.W[r];
+      if (PASS2) sts_u32(s.th + i * 4, __ldg(lth + i));
+      else R.TH[r] = __ldg(lth + i);
+      sts_f64(s.d + i * 8, __ldg(op.d + g));
+      sts_f64(s.w + i * 8, R.W[r]);
       acc = fma(R.W[r], R.W[r], acc);
     }
   }
@@ -360,44 +395,59 @@ __device__ __forceinline__ double cell_load_arcs(const IncidenceOp& op, const Ce
 // scales w in place, mod.rs:312-315) and W becomes
 //   pass 1 (PASS2 = false): w~ = A v - beta_{j-1} v_{j-1}; returns the partial of alpha = <v, w~>
 //   pass 2 (PASS2 = true):  w  = w~ - alpha v, written to s.w, and x += y_{j+1} (w / beta_j)
+// (A v)_arc follows the reference's CSC accumulation order: D v first, then the two node columns by ascending node index
+// (bit 15 of TH: the tail comes first); a self-loop or an empty arc slot reads the zero slot twice.
 template <bool PASS2, bool WITH_V>
-__device__ __forceinline__ double cell_arc_rows(const CellSmem& s, const CellCtx& c, ArcRegs<PASS2>& R, double sc, double bp,
-                                                double alpha, double sinv, double yj, double* Vcol) {
+__device__ __forceinline__ double cell_arc_rows(const CellOp& co, const CellSmem& s, const CellCtx& c, ArcRegs<PASS2>& R, double sc,
+                                                double bp, double alpha, double sinv, double yj, double* Vcol) {
+  const uint32_t zero_slot = kLine * co.max_lines + co.max_tl;
   double acc = 0.0;
+  const uint32_t dbase = s.d + threadIdx.x * 8, wbase = s.w + threadIdx.x * 8;
 #pragma unroll
-  for (int r = 0; r < kArcRegs; ++r) {
-    if (r * kWorkers < c.nA) {  // uniform: rows of arc slots beyond the cell's last arc are skipped
-      const uint32_t i = threadIdx.x + r * kWorkers;
-      const uint32_t ii = i < c.nA ? i : 0;
-      const uint32_t t = R.TH[r] & 0x7fffu, h = R.TH[r] >> 16;
-      const double v = __dmul_rn(R.W[r], sc);
-      // pass 2 scales the node values once when it polls them; pass 1 only learns sc together with them
-      const double xt = PASS2 ? s.nodev[t] : __dmul_rn(s.nodev[t], sc), xh = PASS2 ? s.nodev[h] : __dmul_rn(s.nodev[h], sc);
-      // (A v)_arc in the reference's CSC accumulation order: D v first, then the two node columns by ascending node index
-      // (bit 15: the tail comes first); a self-loop reads the zero slot twice
-      double row = __dmul_rn(s.d[ii], v);
-      if (R.TH[r] & 0x8000u) {
-        row = __dadd_rn(row, xt);
-        row = __dsub_rn(row, xh);
-      } else {
-        row = __dsub_rn(row, xh);
-        row = __dadd_rn(row, xt);
+  for (int r0 = 0; r0 < kArcRegs; r0 += kArcBatch) {
+    if (r0 * kWorkers < c.nA) {  // uniform: batches of arc slots beyond the cell's last arc are skipped
+      double dd[kArcBatch], xt[kArcBatch], xh[kArcBatch];
+      uint32_t th[kArcBatch];
+#pragma unroll
+      for (int u = 0; u < kArcBatch; ++u) {
+        const int r = r0 + u;
+        const bool live = threadIdx.x + r * kWorkers < c.nA;
+        if (PASS2) th[u] = live ? lds_u32(s.th + (threadIdx.x + r * kWorkers) * 4) : (zero_slot | (zero_slot << 16));
+        else th[u] = R.TH[r];
+        dd[u] = live ? lds_f64(dbase + r * kWorkers * 8) : 0.0;
       }
-      const double wt = rec_sub(row, bp, R.P[r]);
-      R.P[r] = v;
-      if (PASS2) {
-        const double w = rec_sub(wt, alpha, v);
-        const double vn = __dmul_rn(w, sinv);
-        R.W[r] = w;
-        R.X[r] = __dadd_rn(R.X[r], __dmul_rn(yj, vn));
-        if (i < c.nA) {
-          s.w[i] = w;
-          if (WITH_V) __stcs(Vcol + __ldg(c.gidx + i), vn);
+#pragma unroll
+      for (int u = 0; u < kArcBatch; ++u) {
+        xt[u] = lds_f64(s.nodev + (th[u] & 0x7fffu) * 8);
+        xh[u] = lds_f64(s.nodev + (th[u] >> 16) * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < kArcBatch; ++u) {
+        const int r = r0 + u;
+        const uint32_t i = threadIdx.x + r * kWorkers;
+        const double v = __dmul_rn(R.W[r], sc);
+        // pass 2 scales the node values once when it polls them; pass 1 only learns sc together with them
+        const double a = PASS2 ? xt[u] : __dmul_rn(xt[u], sc), nb = flip_sign(PASS2 ? xh[u] : __dmul_rn(xh[u], sc), 0x80000000u);
+        const bool tail_first = th[u] & 0x8000u;
+        double row = __dmul_rn(dd[u], v);
+        row = __dadd_rn(row, tail_first ? a : nb);
+        row = __dadd_rn(row, tail_first ? nb : a);
+        const double wt = rec_sub(row, bp, R.P[r]);
+        R.P[r] = v;
+        if (PASS2) {
+          const double w = rec_sub(wt, alpha, v);
+          const double vn = __dmul_rn(w, sinv);
+          R.W[r] = w;
+          R.X[r] = __dadd_rn(R.X[r], __dmul_rn(yj, vn));
+          if (i < c.nA) {
+            sts_f64(wbase + r * kWorkers * 8, w);
+            if (WITH_V) __stcs(Vcol + __ldg(c.gidx + i), vn);
+          }
+        } else {
+          acc = fma(v, wt, acc);
+          R.W[r] = wt;
+          if (WITH_V && i < c.nA) __stcs(Vcol + __ldg(c.gidx + i), v);
         }
-      } else {
-        acc = fma(v, wt, acc);
-        R.W[r] = wt;
-        if (WITH_V && i < c.nA) __stcs(Vcol + __ldg(c.gidx + i), v);
       }
     }
   }
@@ -432,16 +482,18 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
       for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
         const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
         const double bi = u < op.p ? __ldg(a.b + op.m + u) : 0.0;
-        s.n0[t] = bi;
-        s.n1[t] = 0.0;
+        sts_f64(s.n0 + t * 8, bi);
+        sts_f64(s.n1 + t * 8, 0.0);
         acc = fma(bi, bi, acc);
         cell_publish_node(co, line, t & 7, bi, 0);
       }
     }
     cell_block_partial(s, acc);
     __syncthreads();
-    cell_ar_publish(co, s, ++epoch);
-    if (!owner) {
+    ++epoch;
+    if (owner) {
+      cell_ar_publish(co, s, epoch);
+    } else {
       cell_node_sums(s, c);
       bar_workers();
       cell_push_lines(co, s, c, 0);
@@ -464,7 +516,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
     } else {
       for (uint32_t o = 0; o < c.nown; ++o) {
         const double t = cell_poll_inbox(co, s, o, (uint32_t)j);
-        if (lane < kLine) s.T[o * kLine + lane] = t;
+        if (lane < kLine) sts_f64(s.T + (o * kLine + lane) * 8, t);
       }
       trace_mark_warp(tr, j, 32);
       bar_wait_top();
@@ -489,27 +541,29 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
     }
 
     // ---------------- phase A: v = W sc, w~ = A v - beta_{j-1} v_{j-1}, alpha partial
+    trace_mark(tr, j, 11);
     double acc = 0.0;
     if (owner) {
       // owned node rows: n0 holds W (then w~, then the next W), n1 the previous (normalised) vector
       __syncwarp();
       for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
         const uint32_t u = (blockIdx.x + (t >> 3) * co.Gc) * kLine + (t & 7);
-        const double v = __dmul_rn(s.n0[t], sc);
-        const double wt = rec_sub(__dmul_rn(sc, s.T[t]), bp, s.n1[t]);
+        const double v = __dmul_rn(lds_f64(s.n0 + t * 8), sc);
+        const double wt = rec_sub(__dmul_rn(sc, lds_f64(s.T + t * 8)), bp, lds_f64(s.n1 + t * 8));
         acc = fma(v, wt, acc);
-        s.n0[t] = wt;
-        s.n1[t] = v;
+        sts_f64(s.n0 + t * 8, wt);
+        sts_f64(s.n1 + t * 8, v);
         if (WITH_V && u < op.p) __stcs(Vcol + op.m + u, v);
       }
     } else {
-      acc = cell_arc_rows<false, WITH_V>(s, c, R, sc, bp, 0.0, 0.0, 0.0, Vcol);
+      acc = cell_arc_rows<false, WITH_V>(co, s, c, R, sc, bp, 0.0, 0.0, 0.0, Vcol);
     }
+    trace_mark(tr, j, 12);
     cell_block_partial(s, acc);
     trace_mark(tr, j, 3);
-    trace_mark_warp(tr, j, 48);
     __syncthreads();
-    cell_ar_publish(co, s, ++epoch);
+    ++epoch;
+    if (owner) cell_ar_publish(co, s, epoch);
     trace_mark(tr, j, 4);
     if (warp < ar_warps) cell_ar_poll(co, s, epoch);
     trace_mark(tr, j, 5);
@@ -521,8 +575,8 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
     acc = 0.0;
     if (owner) {
       for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
-        const double w = rec_sub(s.n0[t], alpha, s.n1[t]);
-        s.n0[t] = w;
+        const double w = rec_sub(lds_f64(s.n0 + t * 8), alpha, lds_f64(s.n1 + t * 8));
+        sts_f64(s.n0 + t * 8, w);
         acc = fma(w, w, acc);
         cell_publish_node(co, blockIdx.x + (t >> 3) * co.Gc, t & 7, w, (uint32_t)j + 1);
       }
@@ -530,21 +584,22 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
 #pragma unroll
       for (int r = 0; r < kArcRegs; ++r) {
         if (r * kWorkers < c.nA) {
-          const uint32_t i = tid + r * kWorkers;
           const double w = rec_sub(R.W[r], alpha, R.P[r]);
           R.W[r] = w;
           acc = fma(w, w, acc);
-          if (i < c.nA) s.w[i] = w;
+          if (tid + r * kWorkers < c.nA) sts_f64(s.w + (tid + r * kWorkers) * 8, w);
         }
       }
     }
     cell_block_partial(s, acc);
     trace_mark(tr, j, 7);
     __syncthreads();
-    cell_ar_publish(co, s, ++epoch);
+    ++epoch;
+    if (owner) cell_ar_publish(co, s, epoch);
     trace_mark(tr, j, 8);
     if (!owner) {
       cell_node_sums(s, c);
+      trace_mark_warp(tr, j, 48);
       bar_workers();
       trace_mark(tr, j, 10);
       cell_push_lines(co, s, c, (uint32_t)j + 1);
@@ -604,9 +659,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp
         const uint32_t line = blockIdx.x + (t >> 3) * co.Gc, u = line * kLine + (t & 7);
         const double bi = u < op.p ? __ldg(a.b + op.m + u) : 0.0;
         const double v = __dmul_rn(bi, sc);
-        s.n0[t] = bi;
-        s.n1[t] = 0.0;
-        s.nx[t] = __dmul_rn(v, y0);
+        sts_f64(s.n0 + t * 8, bi);
+        sts_f64(s.n1 + t * 8, 0.0);
+        sts_f64(s.nx + t * 8, __dmul_rn(v, y0));
         cell_publish_node(co, line, t & 7, bi, 0);
         if (WITH_V && u < op.p) __stcs(a.V + op.m + u, v);
       }
@@ -632,13 +687,13 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp
         const double T = cell_poll_inbox(co, s, o, (uint32_t)j);
         if (lane < kLine) {
           const uint32_t t = o * kLine + lane, line = blockIdx.x + o * co.Gc, u = line * kLine + lane;
-          const double v = __dmul_rn(s.n0[t], sc);
-          const double w = rec_sub(rec_sub(__dmul_rn(sc, T), bp, s.n1[t]), alpha, v);
+          const double v = __dmul_rn(lds_f64(s.n0 + t * 8), sc);
+          const double w = rec_sub(rec_sub(__dmul_rn(sc, T), bp, lds_f64(s.n1 + t * 8)), alpha, v);
           const double vn = __dmul_rn(w, sinv);
-          s.n0[t] = w;
-          s.n1[t] = v;
+          sts_f64(s.n0 + t * 8, w);
+          sts_f64(s.n1 + t * 8, v);
           cell_publish_node(co, line, lane, w, (uint32_t)j + 1);
-          s.nx[t] = __dadd_rn(s.nx[t], __dmul_rn(yj, vn));
+          sts_f64(s.nx + t * 8, __dadd_rn(lds_f64(s.nx + t * 8), __dmul_rn(yj, vn)));
           if (WITH_V && u < op.p) __stcs(Vcol + op.m + u, vn);
         }
         __syncwarp();
@@ -651,7 +706,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp
       trace_mark_warp(tr, j, 32);
       bar_workers();  // also: every warp has finished the node sums of the previous step, s.w may be rewritten
       trace_mark(tr, j, 2);
-      cell_arc_rows<true, WITH_V>(s, c, R, sc, bp, alpha, sinv, yj, Vcol);
+      cell_arc_rows<true, WITH_V>(co, s, c, R, sc, bp, alpha, sinv, yj, Vcol);
       trace_mark(tr, j, 3);
       bar_workers();
       trace_mark(tr, j, 4);
@@ -674,7 +729,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_cell_kernel(const IncidenceOp
   } else {
     for (uint32_t t = lane; t < c.nown * kLine; t += 32) {
       const uint32_t u = (blockIdx.x + (t >> 3) * co.Gc) * kLine + (t & 7);
-      if (u < op.p) a.x[op.m + u] = s.nx[t];
+      if (u < op.p) a.x[op.m + u] = lds_f64(s.nx + t * 8);
     }
   }
 }

@@ -696,7 +696,6 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
     if (hc.ok) {
       tpl::CellOp& co = op->cell;
       co = tpl::cells_probe(hc);
-      if (const char* f = std::getenv("TPL_CELL_FLAGS")) co.flags = (uint32_t)std::strtoul(f, nullptr, 0);
       rc = dev_upload(op, &co.hdr, hc.hdr);
       if (!rc) rc = dev_upload(op, &co.gidx, hc.gidx);
       if (!rc) rc = dev_upload(op, &co.lth, hc.lth);
@@ -706,7 +705,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       if (!rc) rc = dev_upload(op, &co.walk, hc.walk);
       if (!rc) rc = dev_upload(op, &co.ent4, hc.ent4);
       if (!rc) rc = dev_upload(op, &co.slot_base, hc.slot_base);
-      const size_t atoms = 2 * ((size_t)co.inbox_atoms + (size_t)co.L * tpl::kLine + (size_t)co.Gc * tpl::kLine);
+      const size_t atoms = 2 * ((size_t)co.inbox_atoms + (size_t)co.L * tpl::kLine + (size_t)co.Gc * tpl::kLine * tpl::kArCopies);
       uint4* xchg = nullptr;
       if (!rc) rc = dev_alloc(op, &xchg, atoms);
       if (!rc) {

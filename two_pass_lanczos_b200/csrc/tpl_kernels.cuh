@@ -120,7 +120,6 @@ struct Pass1Args {
   State* st;
   GridSync gs;
   double tol;
-  unsigned int epoch0;  // first tag / epoch this launch may use (host-managed, monotonic per handle)
 };
 
 struct Pass2Args {
@@ -137,7 +136,6 @@ struct Pass2Args {
   double b_norm;
   State* st;
   GridSync gs;
-  unsigned int epoch0;
 };
 
 // ----------------------------------------------------------------------------- primitives
@@ -373,7 +371,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_kernel(const OP op, const Pas
   double* sm_seg = smem + node_smem_doubles(op);
 
   const State st0 = *a.st;
-  unsigned int epoch = a.epoch0;
+  unsigned int epoch = st0.epoch;  // continues across the launches of a step-per-launch pass (slots keep their last tags)
   int rot = st0.rot, steps = st0.steps, status = st0.status;
   double sc = st0.s_cur, sp = st0.s_prev, bp = st0.beta_prev, bnorm = st0.b_norm;
   const LongRows& lr = long_rows(op);
@@ -517,7 +515,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_kernel(const OP op, const Pas
   double* sm_node = smem;
   double* sm_seg = smem + node_smem_doubles(op);
 
-  unsigned int epoch = a.epoch0;
+  unsigned int epoch = a.st->epoch;
   const LongRows& lr = long_rows(op);
   const auto dev0 = make_dev(op, nullptr);
   uint32_t slo, shi;
