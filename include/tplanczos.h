@@ -126,6 +126,9 @@ uint64_t tpl_op_device_bytes(const tpl_op* op);
  * 4 = chunk-resident kernels even when the cell partition would fit.  All modes run the same per-element arithmetic;
  * they differ in the (fixed) order in which a node row is summed, i.e. by rounding only. */
 int tpl_op_set_mode(tpl_op* op, int mode);
+/* Name of the kernel family a whole-pass solve through this handle runs: "cells", "chunks", "tiled", "gather", "csr" or
+ * "sharded" (static string). */
+const char* tpl_op_kernel_shape(const tpl_op* op);
 /* Diagnostics (host only, no device needed): builds the 2-D cell partition the resident kernels would use on a grid
  * of `ctas` CTAs with `smem_limit` bytes of shared memory each and checks its tables on the host.
  * stats = {fits, tail blocks, head blocks, arc slots per cell, node lines, most entry rows, most node-sum groups,

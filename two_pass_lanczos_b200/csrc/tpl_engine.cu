@@ -869,6 +869,10 @@ int tpl_op_set_mode(tpl_op* op, int mode) {
   return TPL_OK;
 }
 
+// which kernels a whole-pass solve through this handle runs (see tpl_op_set_mode)
+static const char* shape_name(const tpl_op* op);
+const char* tpl_op_kernel_shape(const tpl_op* op) { return op ? shape_name(op) : ""; }
+
 int tpl_op_last_timing(const tpl_op* op, double* pass_one_ms, double* pass_two_ms, double* gemv_ms) {
   if (!op) return fail(TPL_ERR_PANIC, "null argument");
   DeviceGuard g(op->device);
@@ -924,6 +928,18 @@ int launch_cells(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
   return TPL_OK;
 }
 bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op->mode == 0 || op->mode == 2); }
+
+}  // namespace
+static const char* shape_name(const tpl_op* op) {
+  if (op->comm) return "sharded";
+  if (op->format != 2) return "csr";
+  if (op->mode == 1) return "gather";
+  if (use_cells(op)) return "cells";
+  if (use_resident(op)) return "chunks";
+  if (use_tiled(op)) return "tiled";
+  return "gather";
+}
+namespace {
 
 template <class KERNEL, class ARGS>
 int launch_tiled(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {

@@ -91,6 +91,10 @@ class LinOp:
     def set_mode(self, mode: int):
         _lib.check(_lib.load().tpl_op_set_mode(self._h, mode))
 
+    def kernel_shape(self) -> str:
+        """kernel family a whole-pass solve runs: cells / chunks / tiled / gather / csr / sharded"""
+        return _lib.load().tpl_op_kernel_shape(self._h).decode()
+
     def trace_enable(self, max_steps: int):
         _lib.check(_lib.load().tpl_op_trace_enable(self._h, max_steps))
 
