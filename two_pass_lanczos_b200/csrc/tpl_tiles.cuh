@@ -87,7 +87,7 @@ struct TileHdr {
 };
 struct TilePre {
   uint32_t ent[kPre];
-  uint32_t pc;
+  uint32_t pc, pc2;  // the warp's first two pieces
 };
 // The prefetching loads are volatile asm: the compiler must issue them HERE (it otherwise sinks them to their first use
 // after the stream, which exposes a full HBM latency per tile -- 23 % of all stall samples in the first ncu capture).
@@ -112,7 +112,9 @@ __device__ __forceinline__ void tile_pre(const TileOp& to, const TileHdr& h, Til
   }
   const uint32_t q = h.q0 + (threadIdx.x >> 5);
   pre.pc = 0u;
+  pre.pc2 = 0u;
   if (q < h.q1) pre.pc = ld_nc_early(to.piece + q);
+  if (q + kWarps < h.q1) pre.pc2 = ld_nc_early(to.piece + q + kWarps);
 }
 
 // One list entry: acc[node] += (+-) wt[index], a plain read-modify-write (a thread's entries are folded in list order, so
@@ -131,7 +133,7 @@ __device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem&
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (h.q1 > h.q0) {
     for (uint32_t q = h.q0 + warp; q < h.q1; q += kWarps) {
-      const uint32_t pc = q == h.q0 + warp ? pre.pc : __ldg(to.piece + q);
+      const uint32_t pc = q == h.q0 + warp ? pre.pc : (q == h.q0 + warp + kWarps ? pre.pc2 : __ldg(to.piece + q));
       const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
       const SmArr w{s.wt.a + first * 8u};
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent lane-strided chains, combined in a fixed order
