@@ -204,7 +204,8 @@ def run_b200(args, rank, world, local_rank):
         from two_pass_lanczos_b200 import sharding
 
         ident = sharding.broadcast_unique_id(dist, rank)
-        op = sharding.sharded_linop(inst.m, inst.p, inst.tail, inst.head, inst.d, rank, world, ident, device=local_rank)
+        op = sharding.sharded_linop(inst.m, inst.p, inst.tail, inst.head, inst.d, rank, world, ident, device=local_rank,
+                                   dist=None if os.environ.get("TPL_SHARDED_NCCL") else dist)
         x_true = torch.full((op.nrows(),), 1.0 / np.sqrt(inst.n), dtype=torch.float64, device=dev)
     else:
         op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d, device=local_rank)

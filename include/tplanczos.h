@@ -207,6 +207,13 @@ int tpl_comm_unique_id(uint8_t id_out[128]);
 int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end, const uint32_t* tail,
                             const uint32_t* head, const double* d, size_t d_len, int device, int rank,
                             int world, const uint8_t nccl_id[128], tpl_op** out);
+/* Fused multi-GPU exchange (one process per GPU of one NVLink domain): every rank exports the CUDA IPC handle of its
+ * exchange block (64 bytes), the caller gathers the handles of all ranks in rank order (any transport) and every rank
+ * imports them.  From then on the passes of a sharded operator run as ONE persistent kernel per rank whose node-sum
+ * exchange, node-value broadcast and alpha / beta all-reduces are peer-memory stores and local polls inside the kernel
+ * (no NCCL call, no per-step launch); tpl_op_set_mode(op, 1) returns to the NCCL phase kernels. */
+int tpl_op_fabric_export(tpl_op* op, uint8_t handle[64]);
+int tpl_op_fabric_import(tpl_op* op, const uint8_t* handles, int count);
 /* rank / world of a handle (0 / 1 for an unsharded one), its local arc count and the node count.  Vectors of a
  * sharded handle are rank-local: [the rank's arc slice | all p node entries (replicated)], nrows() = local_arcs + p. */
 int tpl_op_shard_info(const tpl_op* op, int* rank, int* world, size_t* local_arcs, size_t* nodes);

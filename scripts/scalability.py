@@ -47,7 +47,8 @@ def main():
         inst = datagen.gen_kkt(m, args.rho, 1, "aa")
         if world > 1:
             ident = sharding.broadcast_unique_id(dist, rank)
-            op = sharding.sharded_linop(inst.m, inst.p, inst.tail, inst.head, inst.d, rank, world, ident, device=local)
+            op = sharding.sharded_linop(inst.m, inst.p, inst.tail, inst.head, inst.d, rank, world, ident, device=local,
+                                       dist=None if os.environ.get("TPL_SHARDED_NCCL") else dist)
         else:
             op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d, device=local)
         op.set_stream(torch.cuda.current_stream().cuda_stream)

@@ -20,13 +20,16 @@ def main():
     from two_pass_lanczos_b200 import datagen, sharding
 
     out_path, m, k = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    fused = len(sys.argv) > 4 and sys.argv[4] == "fused"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     inst = datagen.gen_kkt(m, 3, 7, "wc")
     p = inst.p
     ident = sharding.broadcast_unique_id(dist, rank)
-    op = sharding.sharded_linop(m, p, inst.tail, inst.head, inst.d, rank, world, ident, device=local)
+    op = sharding.sharded_linop(m, p, inst.tail, inst.head, inst.d, rank, world, ident, device=local,
+                               dist=dist if fused else None)
+    assert op.kernel_shape() == ("sharded-fused" if fused and world > 1 else "sharded")
     lo, hi = op.arc_lo, op.arc_hi
     info = op.shard_info()
     assert info == {"rank": rank, "world": world, "local_arcs": hi - lo, "nodes": p}

@@ -18,11 +18,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_world(world, m, k, tmp_path):
+def _run_world(world, m, k, tmp_path, fused=False):
     out = str(tmp_path / f"sharded_w{world}.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(29400 + world), os.path.join(ROOT, "tests", "sharded_worker.py"), out, str(m),
-           str(k)]
+           "127.0.0.1", "--master-port", str(29400 + world + (10 if fused else 0)), os.path.join(ROOT, "tests", "sharded_worker.py"),
+           out, str(m), str(k), "fused" if fused else "nccl"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     return np.load(out)
@@ -70,3 +70,14 @@ def test_sharded_world2(tmp_path):
         pytest.skip("needs 2 GPUs")
     m, k = 50_000, 80
     _check(_run_world(2, m, k, tmp_path), m, k)
+
+
+@pytest.mark.parametrize("m,k", [(50_000, 80), (2_000_000, 40)])
+def test_sharded_world2_fused(tmp_path, m, k):
+    """One persistent kernel per rank, node-sum exchange / node broadcast / all-reduces as peer-memory stores over NVLink."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    inst, r = _check(_run_world(2, m, k, tmp_path, fused=True), m, k)
+    assert int(r["launches"]) < 40  # a handful of launches per solve, not two per Lanczos step

@@ -67,6 +67,8 @@ SIGNATURES = {
     "tpl_op_from_kkt_sharded": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, c_u32p, c_u32p, c_dp,
                                           C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8),
                                           C.POINTER(C.c_void_p)]),
+    "tpl_op_fabric_export": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
+    "tpl_op_fabric_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), C.c_int]),
     "tpl_op_shard_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), c_szp, c_szp]),
 }
 

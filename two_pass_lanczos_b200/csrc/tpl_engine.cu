@@ -165,6 +165,11 @@ struct tpl_op {
   size_t cell_xchg_bytes = 0;
   bool tiled_ok = false;       // streaming kernels with tiled node sums are usable (shared-memory budget)
   tpl::TileOp tile{};
+  void* fab_block = nullptr;   // this rank's exchange buffers (partials | node values | slots), one allocation = one IPC handle
+  size_t fab_bytes = 0;
+  std::vector<void*> fab_peers;  // peer blocks opened through CUDA IPC
+  bool fab_connected = false;  // world > 1 and every peer's block is mapped: the persistent tiled kernels span all ranks
+  unsigned fab_epoch = 0;      // barrier epoch the next fused pass starts from (never reset: peers write into our slots)
   size_t smem_tile1 = 0, smem_tile2 = 0;
   double* h_pin = nullptr;  // pinned mirror of coef_d
   double* V_int = nullptr;
@@ -455,6 +460,33 @@ int ensure_coef(tpl_op* op, size_t k) {
   return TPL_OK;
 }
 
+// (Re)allocates this rank's exchange block of the tiled kernels for `world` ranks and points the fabric at it.
+int setup_fabric(tpl_op* op, int rank, int world) {
+  const size_t p = op->inc.p, G = (size_t)op->G;
+  tpl::Fabric& f = op->tile.fab;
+  if (op->fab_block) {
+    if (int rc = dev_free(op, op->fab_block)) return rc;
+    op->fab_block = nullptr;
+  }
+  op->tile.R = (uint32_t)std::max<size_t>(1, (p + (size_t)world * G - 1) / ((size_t)world * G));
+  f = tpl::Fabric{};
+  f.rank = rank;
+  f.world = world;
+  f.Gtot = (uint32_t)(world * G);
+  f.Bp = (uint32_t)(G * op->tile.R);
+  const size_t part = 2 * (size_t)f.Gtot * f.Bp, nodes = 2 * p + 2;
+  const size_t bytes = (part + nodes) * sizeof(double) + 2 * (size_t)f.Gtot * sizeof(uint4);
+  char* block = nullptr;
+  if (int rc = dev_alloc(op, &block, bytes)) return rc;
+  CUDA_TRY(cudaMemset(block, 0, bytes));
+  op->fab_block = block;
+  op->fab_bytes = bytes;
+  f.partials[rank] = reinterpret_cast<double*>(block);
+  f.nodebuf[rank] = f.partials[rank] + part;
+  f.slots[rank] = reinterpret_cast<uint4*>(f.nodebuf[rank] + nodes);
+  return TPL_OK;
+}
+
 int finish_setup(tpl_op* op) {
   const size_t n = op->n;
   for (auto& b : op->buf)
@@ -543,6 +575,7 @@ void tpl_op_free(tpl_op* op) {
   DeviceGuard g(op->device);
   if (op->stream) cudaStreamSynchronize(op->stream);
   if (op->comm) nccl::api().CommDestroy(op->comm);
+  for (void* peer : op->fab_peers) cudaIpcCloseMemHandle(peer);
   for (auto& a : op->allocs) cudaFree(a.first);
   if (op->h_pin) cudaFreeHost(op->h_pin);
   for (auto& ev : op->ev)
@@ -761,12 +794,10 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       if (ht.lent.size() < 0xffffffffull) {
         op->tile.T = ht.T;
         op->tile.ntile = ht.ntile;
-        op->tile.R = (uint32_t)std::max<size_t>(1, (p + op->G - 1) / op->G);
         rc = dev_upload(op, &op->tile.thdr, ht.thdr);
         if (!rc) rc = dev_upload(op, &op->tile.lent, ht.lent);
         if (!rc) rc = dev_upload(op, &op->tile.piece, ht.piece);
-        if (!rc) rc = dev_alloc(op, &op->tile.partials, 2 * (size_t)op->G * p);
-        if (!rc) rc = dev_alloc(op, &op->tile.nodebuf, 2 * p);
+        if (!rc) rc = setup_fabric(op, 0, 1);
         op->smem_tile1 = tpl::tile_smem_bytes((uint32_t)p, T, false);
         op->smem_tile2 = tpl::tile_smem_bytes((uint32_t)p, T, true);
         op->tiled_ok = !rc;
@@ -958,7 +989,7 @@ bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op
 
 }  // namespace
 static const char* shape_name(const tpl_op* op) {
-  if (op->comm) return "sharded";
+  if (op->comm) return op->fab_connected && op->mode == 0 ? "sharded-fused" : "sharded";
   if (op->format != 2) return "csr";
   if (op->mode == 1) return "gather";
   if (use_cells(op)) return "cells";
@@ -1028,6 +1059,7 @@ int reset_sync_state(tpl_op* op) {
   st.s_cur = 1.0;
   st.s_prev = 1.0;
   st.status = tpl::ST_RUNNING;
+  st.epoch = op->fab_connected ? op->fab_epoch : 0;
   std::memcpy(op->h_pin, &st, sizeof st);
   CUDA_TRY(cudaMemsetAsync(op->slots, 0, sizeof(uint4) * 2 * op->G, op->stream));
   CUDA_TRY(cudaMemcpyAsync(op->coef_d, op->h_pin, sizeof st, cudaMemcpyHostToDevice, op->stream));
@@ -1050,6 +1082,7 @@ int fetch_decomp(tpl_op* op, size_t k, Decomp& out, int& status) {
   tpl::State st;
   std::memcpy(&st, op->h_pin, sizeof st);
   status = st.status;
+  if (op->fab_connected) op->fab_epoch = st.epoch;
   out.b_norm = st.b_norm;
   out.steps = (size_t)st.steps;
   const double* al = op->h_pin + kHeaderDoubles;
@@ -1163,8 +1196,8 @@ int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_
   a.tol = tpl::kBreakdownTol;
   int status = tpl::ST_RUNNING;
   CUDA_TRY(cudaEventRecord(op->ev[0], op->stream));
-  if (op->comm) {
-    if (cb) return fail(TPL_ERR_COMM, "step callbacks are not supported on a sharded operator");
+  if (op->comm && cb) return fail(TPL_ERR_COMM, "step callbacks are not supported on a sharded operator");
+  if (op->comm && !(op->fab_connected && op->mode == 0)) {
     if (int rc = run_pass_one_sharded(op, b_dev, k, V_dev, ldv, shard_args(op, b_dev))) return rc;
     CUDA_TRY(cudaEventRecord(op->ev[1], op->stream));
     if (int rc = fetch_decomp(op, k, out, status)) return rc;
@@ -1228,10 +1261,18 @@ int run_pass_two(tpl_op* op, const double* b_dev, const double* alphas, const do
   a.st = op->st_d();
   a.gs = op->gs();
   CUDA_TRY(cudaEventRecord(op->ev[2], op->stream));
-  if (op->comm) {
+  if (op->comm && !(op->fab_connected && op->mode == 0)) {
     if (int rc = run_pass_two_sharded(op, steps, b_norm, x_dev, V_dev, ldv, shard_args(op, b_dev))) return rc;
   } else if (int rc = launch_pass2(op, a)) {
     return rc;
+  }
+  if (op->fab_connected && op->mode == 0) {
+    // the next fused pass continues from the epoch this one ended with (the kernel stored it in the state block)
+    CUDA_TRY(cudaMemcpyAsync(op->h_pin, op->coef_d, sizeof(tpl::State), cudaMemcpyDeviceToHost, op->stream));
+    CUDA_TRY(cudaStreamSynchronize(op->stream));
+    tpl::State st;
+    std::memcpy(&st, op->h_pin, sizeof st);
+    op->fab_epoch = st.epoch;
   }
   CUDA_TRY(cudaEventRecord(op->ev[3], op->stream));
   op->timed[1] = true;
@@ -1475,8 +1516,11 @@ int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end
   if (!op->inc.stage_nodes)
     return bail(fail(TPL_ERR_COMM, "sharded mode needs the node segment (%zu doubles) to fit in shared memory", p));
   op->resident_ok = false;
+  op->cells_ok = false;
   op->rank = rank;
   op->world = world;
+  if (op->tiled_ok && world <= tpl::kMaxRanks)
+    if (int rc = setup_fabric(op, rank, world)) return bail(rc);
   if (int rc = dev_alloc(op, &op->red_d, 2 * (p + 1))) return bail(rc);
   if (int rc = dev_alloc(op, &op->red2_d, 1)) return bail(rc);
   if (cudaMemset(op->red_d, 0, sizeof(double) * 2 * (p + 1)) != cudaSuccess) return bail(fail(TPL_ERR_CUDA, "CUDA error: memset"));
@@ -1488,6 +1532,44 @@ int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end
   nccl::Result r = nccl::api().CommInitRank(&op->comm, world, id, rank);
   if (r != 0) return bail(fail(TPL_ERR_COMM, "NCCL error: %s (ncclCommInitRank)", nccl::api().GetErrorString(r)));
   *out = op;
+  return TPL_OK;
+}
+
+int tpl_op_fabric_export(tpl_op* op, uint8_t handle[64]) {
+  tpl::clear_error();
+  if (!op || !handle) return fail(TPL_ERR_PANIC, "null argument");
+  if (!op->comm || !op->tiled_ok || !op->fab_block || op->world > tpl::kMaxRanks)
+    return fail(TPL_ERR_COMM, "the operator has no exchange block (not sharded, or the tiled kernels do not fit)");
+  DeviceGuard g(op->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, op->fab_block));
+  std::memcpy(handle, &h, 64);
+  return TPL_OK;
+}
+
+int tpl_op_fabric_import(tpl_op* op, const uint8_t* handles, int count) {
+  tpl::clear_error();
+  if (!op || !handles) return fail(TPL_ERR_PANIC, "null argument");
+  if (!op->comm || !op->fab_block) return fail(TPL_ERR_COMM, "the operator has no exchange block");
+  if (count != op->world) return tpl::fail_parameter_mismatch("handles", (size_t)op->world, (size_t)count);
+  if (op->fab_connected) return TPL_OK;
+  DeviceGuard g(op->device);
+  tpl::Fabric& f = op->tile.fab;
+  const size_t part = 2 * (size_t)f.Gtot * f.Bp, nodes = 2 * (size_t)op->inc.p + 2;
+  for (int r = 0; r < op->world; ++r) {
+    if (r == op->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)r * 64, 64);
+    void* peer = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&peer, h, cudaIpcMemLazyEnablePeerAccess));
+    op->fab_peers.push_back(peer);
+    f.partials[r] = reinterpret_cast<double*>(peer);
+    f.nodebuf[r] = f.partials[r] + part;
+    f.slots[r] = reinterpret_cast<uint4*>(f.nodebuf[r] + nodes);
+  }
+  op->fab_connected = true;
+  op->fab_epoch = 0;
   return TPL_OK;
 }
 

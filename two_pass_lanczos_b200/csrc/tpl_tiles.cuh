@@ -30,10 +30,25 @@ constexpr int kUnroll = 4;             // arcs per thread per batch of the strea
 constexpr int kUnroll2 = 2;            // pass 2: six loads per arc, two batches of registers in flight
 constexpr int kPre = 16;               // list entries per thread fetched into registers BEFORE the tile is streamed
 
+// The exchange buffers of every rank of an arc-partitioned multi-GPU operator as seen from THIS rank (peer memory mapped
+// through CUDA IPC over NVLink); world == 1: the local buffers only.  The persistent kernels below write partial node sums,
+// published node values and barrier slots straight into the owners' / every rank's buffers and only ever poll and read
+// local memory: the collective of a Lanczos step is fused into the kernels, no NCCL call and no extra launch on the data path.
+constexpr int kMaxRanks = 8;
+struct Fabric {
+  int rank, world;
+  uint32_t Gtot;  // CTAs of all ranks
+  uint32_t Bp;    // node rows owned by one rank = G * R
+  double* partials[kMaxRanks];  // [2][Gtot][Bp]  partial node sums addressed to the rank's node rows, by source CTA
+  double* nodebuf[kMaxRanks];   // [2][p]         node part of the newest vector (un-normalised), replicated on every rank
+  uint4* slots[kMaxRanks];      // [2][Gtot]      barrier / all-reduce slots, replicated on every rank
+};
+
 struct TileOp {
   uint32_t T;         // arcs per tile
   uint32_t ntile;     // tiles per CTA chunk
-  uint32_t R;         // node rows per owner block = ceil(p / G)
+  uint32_t R;         // node rows per owner block = ceil(p / (world * G))
+  Fabric fab;
   // per tile: {first entry word, entries per thread L, first piece, end piece}
   const uint4* thdr;      // [G * ntile]
   // entries, per tile L x kBlock words, thread-interleaved (word q of thread i at q * kBlock + i => coalesced):
@@ -42,8 +57,6 @@ struct TileOp {
   // node is folded by exactly one thread per tile and all threads carry the same load.
   const uint32_t* lent;
   const uint32_t* piece;  // first | (len - 1) << 16
-  double* partials;       // [2][G][p]  per-CTA partial node sums (double-buffered by step parity)
-  double* nodebuf;        // [2][p]     node part of the newest vector as published by the owners (un-normalised)
 };
 constexpr uint32_t kEntPad = 0xffffffffu;
 
@@ -171,30 +184,128 @@ struct TileCtx {
 __device__ __forceinline__ TileCtx tile_ctx(const IncidenceOp& op, const TileOp& to) {
   TileCtx c;
   cta_chunk(op.m, c.alo, c.ahi);
-  c.ulo = min(op.p, blockIdx.x * to.R);
+  c.ulo = min(op.p, (to.fab.rank * gridDim.x + blockIdx.x) * to.R);
   c.uhi = min(op.p, c.ulo + to.R);
   return c;
 }
 
-// writes this CTA's p partial sums (s.acc) to HBM; caller synchronised before
-__device__ __forceinline__ void publish_tile_partials(const IncidenceOp& op, const TileSmem& s, double* Pout) {
-  double* mine = Pout + (size_t)blockIdx.x * op.p;
-  for (uint32_t u = threadIdx.x; u < op.p; u += kBlock) __stcg(mine + u, sm_ld(s.acc, u));
+// writes this CTA's p partial sums (s.acc) to the owners' buffers (parity `par`); caller synchronised before
+__device__ __forceinline__ void publish_tile_partials(const IncidenceOp& op, const TileOp& to, const TileSmem& s, uint32_t par) {
+  const Fabric& f = to.fab;
+  const uint32_t src = f.rank * gridDim.x + blockIdx.x;
+  for (int r = 0; r < f.world; ++r) {
+    const uint32_t u0 = r * f.Bp, u1 = min(op.p, u0 + f.Bp);
+    double* dst = f.partials[r] + ((size_t)par * f.Gtot + src) * f.Bp;
+    for (uint32_t u = u0 + threadIdx.x; u < u1; u += kBlock) __stcg(dst + (u - u0), sm_ld(s.acc, u));
+  }
 }
-// T_u = sum over the G partials in a fixed order (one warp per owned node, lanes stride the CTAs, xor tree)
-__device__ __forceinline__ double tile_node_total(const IncidenceOp& op, const double* Pin, uint32_t u, int lane) {
+// T_u = sum over the partials of all CTAs of all ranks in a fixed order (one warp per owned node, lanes stride the
+// sources, xor tree)
+__device__ __forceinline__ double tile_node_total(const TileOp& to, uint32_t par, uint32_t u, int lane) {
+  const Fabric& f = to.fab;
+  const double* Pin = f.partials[f.rank] + (size_t)par * f.Gtot * f.Bp + (u - f.rank * f.Bp);
   double a = 0.0;
-  for (uint32_t c0 = lane; c0 < gridDim.x; c0 += 256) {  // eight independent loads in flight per lane
+  for (uint32_t c0 = lane; c0 < f.Gtot; c0 += 256) {  // eight independent loads in flight per lane
     double v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const uint32_t c = c0 + 32 * q;
-      v[q] = c < gridDim.x ? __ldcg(Pin + (size_t)c * op.p + u) : 0.0;
+      v[q] = c < f.Gtot ? __ldcg(Pin + (size_t)c * f.Bp) : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) a = __dadd_rn(a, v[q]);
   }
   return warp_sum(a);
+}
+// node value of an owned row -> every rank's replica (parity `par`)
+__device__ __forceinline__ void publish_node(const TileOp& to, uint32_t p, uint32_t par, uint32_t u, double w) {
+  for (int r = 0; r < to.fab.world; ++r) __stcg(to.fab.nodebuf[r] + (size_t)par * p + u, w);
+}
+__device__ __forceinline__ const double* local_nodebuf(const TileOp& to, uint32_t p, uint32_t par) {
+  return to.fab.nodebuf[to.fab.rank] + (size_t)par * p;
+}
+
+__device__ __forceinline__ void st_relaxed_sys_v4(uint4* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Barrier + all-reduce over the CTAs of ALL ranks (world > 1): the same self-validating 16-byte slots as grid_sync, but every
+// CTA pushes its slot into every rank's replica over NVLink (lane r -> rank r) and polls only its local replica.  System-scope
+// fences order the peer-memory data written before the call (partials, node values) before the slot, and the local reads
+// after the poll.  The payloads are added in slot order: the result is identical in every CTA of every rank.
+template <bool REDUCE>
+__device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsigned int& epoch, CtaShared& sh) {
+  const Fabric& f = to.fab;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  epoch += 1;
+  if (REDUCE) {
+    v = warp_sum(v);
+    if (lane == 0) sh.warp_part[warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double t = 0.0;
+    if (REDUCE) {
+      t = lane < kWarps ? sh.warp_part[lane] : 0.0;
+      t = warp_sum(t);
+    }
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+    const uint32_t src = f.rank * gridDim.x + blockIdx.x;
+    fence_acq_rel_sys();
+    if (lane < f.world)
+      st_relaxed_sys_v4(f.slots[lane] + (size_t)(epoch & 1u) * f.Gtot + src,
+                        make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
+    const uint4* slots = f.slots[f.rank] + (size_t)(epoch & 1u) * f.Gtot;
+    double s = 0.0;
+    for (uint32_t base = 0; base < f.Gtot; base += 160) {
+      uint4 q4[5];
+      unsigned int spins = 0;
+      for (;;) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const uint32_t i = base + lane + 32 * q;
+          q4[q] = ld_relaxed_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1));
+        }
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const uint32_t i = base + lane + 32 * q;
+          ok = ok & ((i >= f.Gtot) | ((q4[q].y == epoch) & (q4[q].w == epoch)));
+        }
+        if (ok) break;
+        if (++spins > kSpinLimit) __trap();
+      }
+      if (REDUCE) {
+        // slot order inside a chunk of 160 is lane-strided; the chunk sums are combined by the xor tree below: fixed order
+        double c = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+          if (base + lane + 32 * q < f.Gtot)
+            c = __dadd_rn(c, __longlong_as_double((long long)(((unsigned long long)q4[q].z << 32) | q4[q].x)));
+        s = __dadd_rn(s, c);
+      }
+    }
+    __syncwarp();
+    fence_acq_rel_sys();
+    if (REDUCE) {
+      s = warp_sum(s);
+      if (lane == 0) sh.result = s;
+    }
+  }
+  __syncthreads();
+  return REDUCE ? sh.result : 0.0;
+}
+// the barrier of the tiled kernels: the single-GPU grid barrier, or the fabric-wide one
+template <bool REDUCE>
+__device__ __forceinline__ double tile_sync(double v, const TileOp& to, const GridSync& gs, unsigned int& epoch, CtaShared& sh) {
+  if (to.fab.world > 1) return fabric_sync<REDUCE>(v, to, epoch, sh);
+  return grid_sync<REDUCE>(v, gs, epoch, sh);
 }
 
 // Tile loop shared by every phase that produces a new vector.  The chunk is streamed in batches of BATCH arcs (a tile is
@@ -281,7 +392,6 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
   const TileCtx c = tile_ctx(op, to);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t m = op.m, p = op.p;
-  const size_t pstride = (size_t)gridDim.x * p;
 
   unsigned int epoch = a.st->epoch;
   int steps = 0, status = ST_RUNNING, rot = 0;
@@ -306,12 +416,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       const double bi = __ldg(a.b + m + u);
       __stcg(Wc + m + u, bi);
       __stcg(Wp + m + u, 0.0);
-      __stcg(to.nodebuf + p + u, bi);  // parity of "step -1"
+      publish_node(to, p, 1, u, bi);  // parity of "step -1"
       acc = fma(bi, bi, acc);
     }
     tile_sums_of(op, to, s, c, a.b);
-    publish_tile_partials(op, s, to.partials);
-    bnorm = sqrt(grid_sync<true>(acc, a.gs, epoch, sh));
+    publish_tile_partials(op, to, s, 0);
+    bnorm = sqrt(tile_sync<true>(acc, to, a.gs, epoch, sh));
     if (bnorm <= a.tol) status = ST_ZERO_B;
     sc = 1.0 / bnorm;
   }
@@ -320,10 +430,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       const double* Wp = pick(rot);
       const double* Wc = pick((rot + 1) % 3);
       double* Wn = pick((rot + 2) % 3);
-      const double* Xnode = to.nodebuf + (size_t)((j + 1) & 1) * p;  // node part of the current vector
-      double* Nout = to.nodebuf + (size_t)(j & 1) * p;
-      const double* Pin = to.partials + (size_t)(j & 1) * pstride;
-      double* Pout = to.partials + (size_t)((j + 1) & 1) * pstride;
+      const double* Xnode = local_nodebuf(to, p, (j + 1) & 1);  // node part of the current vector
       double* Vcol = WITH_V ? a.V + (size_t)j * a.ldv : nullptr;
       gs.trace_step = j;
       trace_mark(gs.trace, j, 0);
@@ -332,16 +439,20 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       for (uint32_t u = threadIdx.x; u < p; u += kBlock) sm_st(s.node, u, __dmul_rn(__ldcg(Xnode + u), sc));
       __syncthreads();
       trace_mark(gs.trace, j, 1);
+      if (WITH_V) {  // node part of the basis column: replicated on every rank, each CTA writes its share
+        uint32_t vlo, vhi;
+        cta_chunk(p, vlo, vhi);
+        for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) __stcs(Vcol + m + u, sm_ld(s.node, u));
+      }
       double acc = 0.0;
       for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
-        const double t = __dmul_rn(sc, tile_node_total(op, Pin, u, lane));
+        const double t = __dmul_rn(sc, tile_node_total(to, j & 1, u, lane));
         if (lane == 0) {
           const double v = sm_ld(s.node, u);
           const double vp = __dmul_rn(__ldcg(Wp + m + u), sp);
           const double wt = rec_sub(t, bp, vp);
           acc = fma(v, wt, acc);
           __stcg(Wn + m + u, wt);
-          if (WITH_V) __stcs(Vcol + m + u, v);
         }
       }
       trace_mark(gs.trace, j, 2);
@@ -374,7 +485,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       }
       trace_mark(gs.trace, j, 3);
       gs.trace_base = 4;
-      const double alpha = grid_sync<true>(acc, gs, epoch, sh);
+      const double alpha = tile_sync<true>(acc, to, gs, epoch, sh);
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
       acc = 0.0;
@@ -383,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
         const double v = __dmul_rn(__ldcg(Wc + m + u), sc);
         const double w = rec_sub(__ldcg(Wn + m + u), alpha, v);
         __stcg(Wn + m + u, w);
-        __stcg(Nout + u, w);
+        publish_node(to, p, j & 1, u, w);
         acc = fma(w, w, acc);
       }
       __syncthreads();  // accumulators are zero before the first fold
@@ -416,9 +527,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
           },
           &gs.trace, j);
       trace_mark(gs.trace, j, 8);
-      publish_tile_partials(op, s, Pout);
+      publish_tile_partials(op, to, s, (j + 1) & 1);
       gs.trace_base = 9;
-      const double beta = sqrt(grid_sync<true>(acc, gs, epoch, sh));
+      const double beta = sqrt(tile_sync<true>(acc, to, gs, epoch, sh));
 
       if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.alphas[j] = alpha;
@@ -460,7 +571,8 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
   const TileCtx c = tile_ctx(op, to);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t m = op.m, p = op.p;
-  const size_t pstride = (size_t)gridDim.x * p;
+  uint32_t vlo, vhi;  // share of the (replicated) node part of x / V this CTA writes
+  cta_chunk(p, vlo, vhi);
   unsigned int epoch = a.st->epoch;
   double* const buf0 = a.buf[0];
   double* const buf1 = a.buf[1];
@@ -478,7 +590,10 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
       const double v = __dmul_rn(__ldg(a.b + m + u), inv);
       __stcg(Vc + m + u, v);
       __stcg(Vp + m + u, 0.0);
-      __stcg(to.nodebuf + p + u, v);
+      publish_node(to, p, 1, u, v);
+    }
+    for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
+      const double v = __dmul_rn(__ldg(a.b + m + u), inv);
       __stcg(a.x + m + u, __dmul_rn(v, y0));
       if (WITH_V) __stcs(a.V + m + u, v);
     }
@@ -492,17 +607,14 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
     // node sums are taken over the UN-normalised vector and scaled afterwards, exactly as pass 1 does with its lazily
     // scaled w (bit-identical node rows)
     tile_sums_of(op, to, s, c, a.b);
-    publish_tile_partials(op, s, to.partials);
-    grid_sync<false>(0.0, a.gs, epoch, sh);
+    publish_tile_partials(op, to, s, 0);
+    tile_sync<false>(0.0, to, a.gs, epoch, sh);
   }
   for (int j = 0; j + 1 < a.steps; ++j) {
     const double* Vp = pick(rot);
     const double* Vc = pick((rot + 1) % 3);
     double* Vn = pick((rot + 2) % 3);
-    const double* Xnode = to.nodebuf + (size_t)((j + 1) & 1) * p;
-    double* Nout = to.nodebuf + (size_t)(j & 1) * p;
-    const double* Pin = to.partials + (size_t)(j & 1) * pstride;
-    double* Pout = to.partials + (size_t)((j + 1) & 1) * pstride;
+    const double* Xnode = local_nodebuf(to, p, (j + 1) & 1);
     double* Vcol = WITH_V ? a.V + (size_t)(j + 1) * a.ldv : nullptr;
     const double alpha = __ldg(a.alphas + j);
     const double beta = __ldg(a.betas + j);
@@ -515,15 +627,23 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
       sm_st(s.acc, u, 0.0);
     }
     __syncthreads();
+    if (j > 0) {
+      // the staged node values are v_{j+1}, regenerated by the previous step: their share of x (and of the basis column)
+      // is added here, by every rank for its replica (each CTA its share of the nodes)
+      const double yprev = __ldg(a.y + j);
+      for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
+        const double vn = sm_ld(s.node, u);
+        __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(yprev, vn)));
+        if (WITH_V) __stcs(a.V + (size_t)j * a.ldv + m + u, vn);
+      }
+    }
     for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
-      const double t = __dmul_rn(sc_cur, tile_node_total(op, Pin, u, lane));
+      const double t = __dmul_rn(sc_cur, tile_node_total(to, j & 1, u, lane));
       if (lane == 0) {
         const double w = rec_sub(rec_sub(t, bp, __ldcg(Vp + m + u)), alpha, sm_ld(s.node, u));
         const double vn = __dmul_rn(w, sinv);
         __stcg(Vn + m + u, vn);
-        __stcg(Nout + u, vn);
-        __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(yj, vn)));
-        if (WITH_V) __stcs(Vcol + m + u, vn);
+        publish_node(to, p, j & 1, u, vn);
       }
     }
     __syncthreads();  // node rows are done with s.node reads of other warps; accumulators are zero
@@ -563,10 +683,19 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
             }
           }
         });
-    publish_tile_partials(op, s, Pout);
-    grid_sync<false>(0.0, a.gs, epoch, sh);
+    publish_tile_partials(op, to, s, (j + 1) & 1);
+    tile_sync<false>(0.0, to, a.gs, epoch, sh);
     rot = (rot + 1) % 3;
     sc_cur = sinv;
+  }
+  if (a.steps > 1) {  // node part of the last regenerated vector v_steps (published by the last step, parity (steps - 2) & 1)
+    const double* Xnode = local_nodebuf(to, p, (a.steps - 2) & 1);
+    const double ylast = __ldg(a.y + a.steps - 1);
+    for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
+      const double vn = __ldcg(Xnode + u);
+      __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(ylast, vn)));
+      if (WITH_V) __stcs(a.V + (size_t)(a.steps - 1) * a.ldv + m + u, vn);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) a.st->epoch = epoch;
 }

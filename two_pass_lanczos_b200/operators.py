@@ -113,6 +113,18 @@ class LinOp:
         _lib.check(_lib.load().tpl_op_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"pass_one_ms": a.value, "pass_two_ms": b.value, "gemv_ms": c.value}
 
+    def fabric_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's exchange block (sharded operators)."""
+        buf = (C.c_uint8 * 64)()
+        _lib.check(_lib.load().tpl_op_fabric_export(self._h, buf))
+        return bytes(buf)
+
+    def fabric_import(self, handles):
+        """Maps the exchange blocks of all ranks (their handles in rank order): the passes then run fused."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _lib.check(_lib.load().tpl_op_fabric_import(self._h, buf, len(handles)))
+
     def shard_info(self):
         r, w, a, p = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
         _lib.check(_lib.load().tpl_op_shard_info(self._h, C.byref(r), C.byref(w), C.byref(a), C.byref(p)))

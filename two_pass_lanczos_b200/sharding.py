@@ -56,9 +56,28 @@ def broadcast_unique_id(dist, rank: int, make=unique_id) -> bytes:
     return box[0]
 
 
-def sharded_linop(m: int, p: int, tail, head, d, rank: int, world: int, nccl_id: bytes, device: int = -1) -> LinOp:
+def connect_fabric(op: LinOp, dist) -> bool:
+    """Exchanges the CUDA IPC handles of the ranks' exchange blocks over an initialised torch.distributed group and maps
+    them: the passes of `op` then run as one persistent kernel per rank with the collectives fused in (peer-memory stores
+    over NVLink).  Returns False (and leaves the NCCL phase kernels in charge) when a rank has no exchange block."""
+    world = dist.get_world_size()
+    try:
+        mine = op.fabric_export()
+    except Exception:  # noqa: BLE001 - e.g. the tiled kernels do not fit this rank's block
+        mine = None
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    if any(h is None for h in handles):
+        return False
+    op.fabric_import(handles)
+    dist.barrier()  # nobody starts a fused pass before every rank has mapped its peers
+    return True
+
+
+def sharded_linop(m: int, p: int, tail, head, d, rank: int, world: int, nccl_id: bytes, device: int = -1, dist=None) -> LinOp:
     """LinOp over this rank's arc block of A = [[D, E^T], [E, 0]] (global tail / head / d arrays are passed; the
-    library slices them)."""
+    library slices them).  With `dist` (an initialised torch.distributed module) and world > 1 the ranks' exchange
+    blocks are connected (`connect_fabric`)."""
     tail = np.ascontiguousarray(tail, dtype=np.uint32)
     head = np.ascontiguousarray(head, dtype=np.uint32)
     d = np.ascontiguousarray(d, dtype=np.float64)
@@ -70,4 +89,5 @@ def sharded_linop(m: int, p: int, tail, head, d, rank: int, world: int, nccl_id:
                                                    C.byref(h)))
     op = LinOp(h)
     op.arc_lo, op.arc_hi, op.m_global, op.p = lo, hi, m, p
+    op.fused = bool(dist is not None and world > 1 and connect_fabric(op, dist))
     return op
