@@ -96,3 +96,55 @@ def test_world2_gloo_sharded_product_matches_oracle():
     assert arcs_exact                 # arc rows follow the reference's accumulation order exactly
     assert err < 1e-14
     assert replica_gap == 0.0         # node replicas are bit-identical after the all-reduce
+
+
+class _StubOp:
+    """Stands in for a sharded LinOp on a box without GPUs: records the handles `connect_fabric` hands over."""
+
+    def __init__(self, rank, has_block=True):
+        self.rank, self.has_block, self.imported = rank, has_block, None
+
+    def fabric_export(self):
+        if not self.has_block:
+            raise RuntimeError("no exchange block")
+        return bytes([self.rank]) * 64
+
+    def fabric_import(self, handles):
+        self.imported = list(handles)
+
+
+def _fabric_worker(rank, world, port, q, broken_rank):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        op = _StubOp(rank, has_block=rank != broken_rank)
+        ok = sharding.connect_fabric(op, dist)
+        q.put((rank, ok, op.imported))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("broken_rank", [-1, 1])
+def test_world2_gloo_fabric_rendezvous(broken_rank):
+    """Every rank receives all 64-byte handles in rank order; if one rank has no exchange block, nobody connects."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_fabric_worker, args=(r, world, port, q, broken_rank)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, ok, imported in got:
+        if broken_rank < 0:
+            assert ok and imported == [bytes([0]) * 64, bytes([1]) * 64]
+        else:
+            assert not ok and imported is None
