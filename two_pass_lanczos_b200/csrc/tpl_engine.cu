@@ -309,7 +309,7 @@ struct HostTiles {
 
 void build_tiles(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int G, uint32_t T, HostTiles& h) {
   const size_t A = (m + G - 1) / G;
-  const int B = tpl::kBlock;
+  const int B = tpl::kFoldThreads;  // the fold warps walk the lists
   h.T = T;
   h.ntile = (uint32_t)std::max<size_t>(1, (A + T - 1) / T);
   const size_t ntiles = (size_t)G * h.ntile;
@@ -783,9 +783,9 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   if (!rc && p >= 1 && p < (1u << 17)) {
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
-    const long budget = (long)max_optin - 2048 - (long)(2 * p + tpl::kMaxPieces) * 8;
-    const uint32_t step = tpl::kUnroll * tpl::kBlock;
-    uint32_t T = budget > 0 ? (uint32_t)std::min<long>(8192, budget / 8 / step * step) : 0;  // <= ~kPre entries per thread
+    const long budget = (long)max_optin - 2048 - (long)(2 * p + 2 * tpl::kMaxPieces) * 8;
+    const uint32_t step = tpl::kUnrollB * tpl::kStreamThreads;  // a tile is a whole number of the largest stream batch
+    uint32_t T = budget > 0 ? (uint32_t)std::min<long>(8192 / step * step, budget / 16 / step * step) : 0;  // two tile buffers
     const size_t A = (m + op->G - 1) / op->G;
     if (T >= step) {
       T = (uint32_t)std::min<size_t>(T, std::max<size_t>(step, (A + step - 1) / step * step));

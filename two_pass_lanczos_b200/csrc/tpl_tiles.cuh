@@ -28,7 +28,11 @@ constexpr uint32_t kPieceMax = 256;    // longest piece (longer runs are split a
 constexpr uint32_t kMaxPieces = 512;   // per tile (shared-memory slots after the T arc values); T + kMaxPieces <= 16384
 constexpr int kUnroll = 4;             // arcs per thread per batch of the streaming loops
 constexpr int kUnroll2 = 2;            // pass 2: six loads per arc, two batches of registers in flight
-constexpr int kPre = 16;               // list entries per thread fetched into registers BEFORE the tile is streamed
+constexpr int kUnrollB = 4;            // pass 1 phase B: two loads per arc
+constexpr int kPre = 16;               // list entries per fold thread requested together
+constexpr int kStreamWarps = 8;        // warps 0..7 stream a tile from HBM while warps 8..15 fold the previous one into the node sums
+constexpr int kFoldWarps = kWarps - kStreamWarps;
+constexpr int kStreamThreads = kStreamWarps * 32, kFoldThreads = kFoldWarps * 32;
 
 // The exchange buffers of every rank of an arc-partitioned multi-GPU operator as seen from THIS rank (peer memory mapped
 // through CUDA IPC over NVLink); world == 1: the local buffers only.  The persistent kernels below write partial node sums,
@@ -76,58 +80,33 @@ __device__ __forceinline__ void sm_st(SmArr arr, uint32_t i, double v) {
 struct TileSmem {
   SmArr node;  // [p]  scaled node segment of the current vector (phases that form arc rows)
   SmArr acc;   // [p]  partial node sums of this CTA            (phases that produce a new vector)
-  SmArr wt;    // [T + kMaxPieces] arc values of the current tile + piece sums
+  SmArr wt;    // [2][T + kMaxPieces] arc values of a tile + its piece sums, double-buffered (stream / fold)
+  uint32_t wt_stride;  // bytes between the two buffers
 };
 // pass 1 never needs node and acc at the same time (they alias); pass 2 needs both.
 __host__ __device__ inline size_t tile_smem_bytes(uint32_t p, uint32_t T, bool pass2) {
-  return ((pass2 ? 2 : 1) * (size_t)p + T + kMaxPieces) * sizeof(double);
+  return ((pass2 ? 2 : 1) * (size_t)p + 2 * ((size_t)T + kMaxPieces)) * sizeof(double);
 }
-__device__ __forceinline__ TileSmem carve_tiles(double* base, uint32_t p, bool pass2) {
+__device__ __forceinline__ TileSmem carve_tiles(double* base, uint32_t p, uint32_t T, bool pass2) {
   const uint32_t b = (uint32_t)__cvta_generic_to_shared(base);
   TileSmem s;
   s.node.a = b;
   s.acc.a = pass2 ? b + p * 8u : b;
   s.wt.a = s.acc.a + p * 8u;
+  s.wt_stride = (T + kMaxPieces) * 8u;
   return s;
 }
 
-// Everything a thread needs from HBM to fold a tile is requested before the tile's arcs are streamed, so that the
-// latency of these small dependent loads (tile header -> list words) hides behind the stream: the header of tile t+1 is
-// fetched while tile t is processed, the first kPre list words and the warp's first piece while tile t itself streams.
 struct TileHdr {
-  uint32_t e0, L;   // first entry word of the tile, entries per thread
+  uint32_t e0, L;   // first entry word of the tile, entries per fold thread
   uint32_t q0, q1;  // the tile's pieces
 };
-struct TilePre {
-  uint32_t ent[kPre];
-  uint32_t pc, pc2;  // the warp's first two pieces
-};
-// The prefetching loads are volatile asm: the compiler must issue them HERE (it otherwise sinks them to their first use
-// after the stream, which exposes a full HBM latency per tile -- 23 % of all stall samples in the first ncu capture).
-__device__ __forceinline__ uint32_t ld_nc_early(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ TileHdr tile_hdr(const TileOp& to, uint32_t tile_id) {
   TileHdr h;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(h.e0), "=r"(h.L), "=r"(h.q0), "=r"(h.q1)
                : "l"(to.thdr + tile_id));
   return h;
-}
-__device__ __forceinline__ void tile_pre(const TileOp& to, const TileHdr& h, TilePre& pre) {
-  const uint32_t* mine = to.lent + h.e0 + threadIdx.x;
-#pragma unroll
-  for (int q = 0; q < kPre; ++q) {
-    pre.ent[q] = kEntPad;
-    if ((uint32_t)q < h.L) pre.ent[q] = ld_nc_early(mine + (size_t)q * kBlock);  // uniform predicate
-  }
-  const uint32_t q = h.q0 + (threadIdx.x >> 5);
-  pre.pc = 0u;
-  pre.pc2 = 0u;
-  if (q < h.q1) pre.pc = ld_nc_early(to.piece + q);
-  if (q + kWarps < h.q1) pre.pc2 = ld_nc_early(to.piece + q + kWarps);
 }
 
 // One list entry: acc[node] += (+-) wt[index], a plain read-modify-write (a thread's entries are folded in list order, so
@@ -140,15 +119,22 @@ __device__ __forceinline__ void fold_entry(uint32_t ent, SmArr wt, SmArr acc) {
   sm_st(acc, node, __dadd_rn(sm_ld(acc, node), __longlong_as_double(x)));
 }
 
-// Adds the node sums of the tile held in s.wt[0 .. n_arcs) into s.acc.  Caller has synchronised after filling s.wt and
-// must synchronise before refilling it.
-__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, const TileHdr& h, const TilePre& pre) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// named barriers of the stream / fold hand-off (barrier 0 is __syncthreads): full[b] = tile buffer b holds a streamed tile
+// (the stream warps arrive, the fold warps wait), empty[b] = the fold warps are done with buffer b (they arrive, the stream
+// warps wait before refilling it), kBarFold = the fold warps among themselves.  bar.arrive / bar.sync order the shared-memory
+// accesses of the arriving threads before those of the waiting threads (PTX producer / consumer pattern).
+constexpr int kBarFull = 1, kBarEmpty = 3, kBarFold = 5;
+__device__ __forceinline__ void bar_sync_n(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Fold warps: adds the node sums of the tile held in buffer `wt` into s.acc.
+__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, SmArr wt, const TileHdr& h) {
+  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
   if (h.q1 > h.q0) {
-    for (uint32_t q = h.q0 + warp; q < h.q1; q += kWarps) {
-      const uint32_t pc = q == h.q0 + warp ? pre.pc : (q == h.q0 + warp + kWarps ? pre.pc2 : __ldg(to.piece + q));
+    for (uint32_t q = h.q0 + fwarp; q < h.q1; q += kFoldWarps) {
+      const uint32_t pc = __ldg(to.piece + q);
       const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
-      const SmArr w{s.wt.a + first * 8u};
+      const SmArr w{wt.a + first * 8u};
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent lane-strided chains, combined in a fixed order
       for (uint32_t e = lane; e < len; e += 128) {
         const double x0 = sm_ld(w, e);
@@ -161,19 +147,18 @@ __device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem&
         a3 = __dadd_rn(a3, x3);
       }
       const double a = warp_sum(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)));
-      if (lane == 0) sm_st(s.wt, to.T + (q - h.q0), a);
+      if (lane == 0) sm_st(wt, to.T + (q - h.q0), a);
     }
-    __syncthreads();
+    bar_sync_n(kBarFold, kFoldThreads);
   }
+  const uint32_t* mine = to.lent + h.e0 + ftid;
+  for (uint32_t q0 = 0; q0 < h.L; q0 += kPre) {  // kPre list words requested together, then folded in order
+    uint32_t ent[kPre];
 #pragma unroll
-  for (int q = 0; q < kPre; ++q) {
-    if ((uint32_t)q >= h.L) break;  // uniform: every thread of the tile carries L words (the last ones may be padding)
-    if (pre.ent[q] != kEntPad) fold_entry(pre.ent[q], s.wt, s.acc);
-  }
-  const uint32_t* mine = to.lent + h.e0 + threadIdx.x;
-  for (uint32_t q = kPre; q < h.L; ++q) {  // long slices (hub nodes): the rest straight from the list
-    const uint32_t ent = __ldg(mine + (size_t)q * kBlock);
-    if (ent != kEntPad) fold_entry(ent, s.wt, s.acc);
+    for (int q = 0; q < kPre; ++q) ent[q] = q0 + q < h.L ? __ldg(mine + (size_t)(q0 + q) * kFoldThreads) : kEntPad;
+#pragma unroll
+    for (int q = 0; q < kPre; ++q)
+      if (ent[q] != kEntPad) fold_entry(ent[q], wt, s.acc);
   }
 }
 
@@ -308,51 +293,67 @@ __device__ __forceinline__ double tile_sync(double v, const TileOp& to, const Gr
   return grid_sync<REDUCE>(v, gs, epoch, sh);
 }
 
-// Tile loop shared by every phase that produces a new vector.  The chunk is streamed in batches of BATCH arcs (a tile is
-// a whole number of batches): `issue(i0, regs)` starts the global loads of batch [i0, i0 + BATCH), `consume(i0, t0, regs)`
-// computes the new arc values, stores them and writes them to s.wt[i - t0].  The loads of the NEXT batch -- also across a
-// tile boundary -- are issued before the current batch is consumed and before a finished tile is folded into s.acc, so
-// the HBM stream keeps flowing while the CTA synchronises and walks its lists.  The caller has zeroed s.acc.
-template <int BATCH, class REGS, class ISSUE, class CONSUME>
+// Tile loop shared by every phase that produces a new vector, warp-specialised: the STREAM warps (0..7) move the chunk
+// through registers in batches of BATCH arcs -- `issue(i0, regs)` starts the global loads of batch [i0, i0 + BATCH),
+// `consume(i0, t0, regs, wt)` computes the new arc values, stores them and writes them to the tile buffer wt[i - t0] -- while
+// the FOLD warps (8..15) add the node sums of the PREVIOUS tile into s.acc from the other tile buffer.  The HBM stream and
+// the (shared-memory bound) list walk therefore overlap; before, they alternated and the walk was 57 % of the phase.
+// Inside issue / consume a stream thread addresses arcs i0 + q * kStreamThreads + threadIdx.x.  The caller has zeroed s.acc
+// and synchronised; on return every fold is complete (CTA-wide barrier).
+// DEEP: two batches of loads in flight ahead of the one being consumed (three register sets) instead of one.
+template <int BATCH, class REGS, bool DEEP, class ISSUE, class CONSUME>
 __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, const TileCtx& c, ISSUE issue, CONSUME consume,
                                           const Trace* tr = nullptr, int tr_step = -1) {
   const uint32_t tile0 = blockIdx.x * to.ntile;
-  if (c.alo >= c.ahi) return;
-  long long c_stream = 0, c_sync1 = 0, c_fold = 0, c_sync2 = 0, t_a = 0, t_b = 0;
+  uint32_t ntiles = 0;
+  if (c.alo < c.ahi) ntiles = min(to.ntile, (c.ahi - c.alo + to.T - 1) / to.T);
   const bool timed = tr != nullptr && tr->buf != nullptr;
-  TileHdr hdr = tile_hdr(to, tile0);
-  REGS cur;
-  issue(c.alo, cur);
-  for (uint32_t t = 0; t < to.ntile; ++t) {
-    const uint32_t t0 = c.alo + t * to.T;
-    if (t0 >= c.ahi) break;
-    const uint32_t t1 = min(c.ahi, t0 + to.T);
-    TilePre pre;
-    tile_pre(to, hdr, pre);
-    TileHdr next = hdr;
-    if (t + 1 < to.ntile && t1 < c.ahi) next = tile_hdr(to, tile0 + t + 1);
-    if (timed) t_a = clock64();
-    for (uint32_t i0 = t0; i0 < t1; i0 += BATCH) {
-      REGS nxt;
-      if (i0 + BATCH < c.ahi) issue(i0 + BATCH, nxt);
-      consume(i0, t0, cur);
-      cur = nxt;
+  if (threadIdx.x < kStreamThreads) {
+    long long c_stream = 0, c_wait = 0, t_a = 0, t_b = 0;
+    REGS cur, nx1;
+    if (ntiles) issue(c.alo, cur);
+    if (DEEP && ntiles && c.alo + BATCH < c.ahi) issue(c.alo + BATCH, nx1);
+    for (uint32_t t = 0; t < ntiles; ++t) {
+      const uint32_t t0 = c.alo + t * to.T, t1 = min(c.ahi, t0 + to.T);
+      const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
+      if (timed) t_a = clock64();
+      if (t >= 2) bar_sync_n(kBarEmpty + (t & 1u), kBlock);  // the fold of tile t - 2 has left this buffer
+      if (timed) { t_b = clock64(); c_wait += t_b - t_a; }
+      for (uint32_t i0 = t0; i0 < t1; i0 += BATCH) {
+        REGS nxt;
+        if (DEEP) {
+          if (i0 + 2 * BATCH < c.ahi) issue(i0 + 2 * BATCH, nxt);
+          consume(i0, t0, cur, wt);
+          cur = nx1;
+          nx1 = nxt;
+        } else {
+          if (i0 + BATCH < c.ahi) issue(i0 + BATCH, nxt);
+          consume(i0, t0, cur, wt);
+          cur = nxt;
+        }
+      }
+      bar_arrive_n(kBarFull + (t & 1u), kBlock);
+      if (timed) c_stream += clock64() - t_b;
     }
-    if (timed) { t_b = clock64(); c_stream += t_b - t_a; }
-    __syncthreads();
-    if (timed) { t_a = clock64(); c_sync1 += t_a - t_b; }
-    tile_node_sums(to, s, hdr, pre);
-    if (timed) { t_b = clock64(); c_fold += t_b - t_a; }
-    __syncthreads();
-    if (timed) { t_a = clock64(); c_sync2 += t_a - t_b; }
-    hdr = next;
+    // drain: every arrival of the fold warps is matched by a wait, so that the barriers are clean for the next call
+    for (uint32_t t = ntiles > 2 ? ntiles - 2 : 0; t < ntiles; ++t) bar_sync_n(kBarEmpty + (t & 1u), kBlock);
+    if (timed) {
+      trace_value(*tr, tr_step, 16, c_stream);
+      trace_value(*tr, tr_step, 17, c_wait);
+    }
+  } else {
+    TileHdr hdr = tile_hdr(to, tile0);
+    for (uint32_t t = 0; t < ntiles; ++t) {
+      TileHdr next = hdr;
+      if (t + 1 < ntiles) next = tile_hdr(to, tile0 + t + 1);
+      const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
+      bar_sync_n(kBarFull + (t & 1u), kBlock);
+      tile_node_sums(to, s, wt, hdr);
+      bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
+      hdr = next;
+    }
   }
-  if (timed) {
-    trace_value(*tr, tr_step, 16, c_stream);
-    trace_value(*tr, tr_step, 17, c_sync1);
-    trace_value(*tr, tr_step, 18, c_fold);
-    trace_value(*tr, tr_step, 19, c_sync2);
-  }
+  __syncthreads();
 }
 
 // node partial sums of an arbitrary arc vector X (init: b) over the CTA's chunk
@@ -363,20 +364,20 @@ __device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp
   struct R {
     double x[kUnroll];
   };
-  tile_loop<kUnroll * kBlock, R>(
+  tile_loop<kUnroll * kStreamThreads, R, false>(
       to, s, c,
       [&](uint32_t i0, R& r) {
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
-          const uint32_t i = i0 + q * kBlock + threadIdx.x;
+          const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
           r.x[q] = i < c.ahi ? __ldg(X + i) : 0.0;
         }
       },
-      [&](uint32_t i0, uint32_t t0, const R& r) {
+      [&](uint32_t i0, uint32_t t0, const R& r, SmArr wt) {
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
-          const uint32_t i = i0 + q * kBlock + threadIdx.x;
-          if (i < c.ahi) sm_st(s.wt, i - t0, r.x[q]);
+          const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
+          if (i < c.ahi) sm_st(wt, i - t0, r.x[q]);
         }
       });
 }
@@ -388,7 +389,7 @@ template <bool WITH_V>
 __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceOp op, const TileOp to, const Pass1Args a) {
   extern __shared__ double smem[];
   __shared__ CtaShared sh;
-  const TileSmem s = carve_tiles(smem, op.p, false);
+  const TileSmem s = carve_tiles(smem, op.p, to.T, false);
   const TileCtx c = tile_ctx(op, to);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t m = op.m, p = op.p;
@@ -499,28 +500,28 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       }
       __syncthreads();  // accumulators are zero before the first fold
       struct RB {
-        double wn[kUnroll], wc[kUnroll];
+        double wn[kUnrollB], wc[kUnrollB];
       };
-      tile_loop<kUnroll * kBlock, RB>(
+      tile_loop<kUnrollB * kStreamThreads, RB, false>(
           to, s, c,
           [&](uint32_t i0, RB& r) {
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-              const uint32_t i = i0 + q * kBlock + threadIdx.x;
+            for (int q = 0; q < kUnrollB; ++q) {
+              const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
               if (i < c.ahi) {
                 r.wn[q] = __ldcg(Wn + i);
                 r.wc[q] = __ldcg(Wc + i);
               }
             }
           },
-          [&](uint32_t i0, uint32_t t0, const RB& r) {
+          [&](uint32_t i0, uint32_t t0, const RB& r, SmArr wt) {
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-              const uint32_t i = i0 + q * kBlock + threadIdx.x;
+            for (int q = 0; q < kUnrollB; ++q) {
+              const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
               if (i < c.ahi) {
                 const double w = rec_sub(r.wn[q], alpha, __dmul_rn(r.wc[q], sc));
                 __stcg(Wn + i, w);
-                sm_st(s.wt, i - t0, w);
+                sm_st(wt, i - t0, w);
                 acc = fma(w, w, acc);
               }
             }
@@ -567,7 +568,7 @@ template <bool WITH_V>
 __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceOp op, const TileOp to, const Pass2Args a) {
   extern __shared__ double smem[];
   __shared__ CtaShared sh;
-  const TileSmem s = carve_tiles(smem, op.p, true);
+  const TileSmem s = carve_tiles(smem, op.p, to.T, true);
   const TileCtx c = tile_ctx(op, to);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t m = op.m, p = op.p;
@@ -651,12 +652,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
       double vc[kUnroll2], vp[kUnroll2], dd[kUnroll2], xx[kUnroll2];
       uint32_t tl[kUnroll2], hd[kUnroll2];
     };
-    tile_loop<kUnroll2 * kBlock, R2>(
+    tile_loop<kUnroll2 * kStreamThreads, R2, false>(
         to, s, c,
         [&](uint32_t i0, R2& r) {
 #pragma unroll
           for (int q = 0; q < kUnroll2; ++q) {
-            const uint32_t i = i0 + q * kBlock + threadIdx.x;
+            const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
             if (i < c.ahi) {
               r.vc[q] = __ldcg(Vc + i);
               r.vp[q] = __ldcg(Vp + i);
@@ -667,10 +668,10 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
             }
           }
         },
-        [&](uint32_t i0, uint32_t t0, const R2& r) {
+        [&](uint32_t i0, uint32_t t0, const R2& r, SmArr wt) {
 #pragma unroll
           for (int q = 0; q < kUnroll2; ++q) {
-            const uint32_t i = i0 + q * kBlock + threadIdx.x;
+            const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
             if (i < c.ahi) {
               const double v = r.vc[q];
               const double w = rec_sub(
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
               __stcg(Vn + i, vn);
               __stcg(a.x + i, __dadd_rn(r.xx[q], __dmul_rn(yj, vn)));
               if (WITH_V) __stcs(Vcol + i, vn);
-              sm_st(s.wt, i - t0, w);
+              sm_st(wt, i - t0, w);
             }
           }
         });
