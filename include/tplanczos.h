@@ -96,6 +96,10 @@ typedef struct tpl_op tpl_op;
  * (what `&a.as_ref()` is at src/bin/tradeoff.rs:268).  device < 0: current device. */
 int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, const double* val,
                     int device, tpl_op** out);
+/* Dense symmetric operator (the `Mat<f64>` used as `&impl LinOp<f64>` by src/bin/dense_tradeoff.rs:154-162): n x n,
+ * column-major with leading dimension lda >= n, copied to the device.  The matrix must be symmetric (as Lanczos
+ * requires; the kernels read column i as row i).  SURVEY 8f, N4. */
+int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op** out);
 /* Network-incidence form of A = [[D, E^T], [E, 0]]: reads arc tail/head instead of stored +-1.
  * d_len <= m honours the loader's short-D quirk (rows >= d_len have no diagonal entry). */
 int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d,
@@ -105,7 +109,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
 int tpl_op_from_kkt_system(const tpl_kkt* kkt, int format, int device, tpl_op** out);
 void tpl_op_free(tpl_op* op);
 size_t tpl_op_nrows(const tpl_op* op); /* LinOp::nrows == ncols */
-int tpl_op_format(const tpl_op* op);   /* 1 = CSR, 2 = incidence */
+int tpl_op_format(const tpl_op* op);   /* 1 = CSR, 2 = incidence, 3 = dense */
 int tpl_op_device(const tpl_op* op);
 /* LinOp::apply: y = A x (used by the reference's property tests, mod.rs:510). */
 int tpl_op_apply(tpl_op* op, const double* x, double* y);

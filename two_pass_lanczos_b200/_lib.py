@@ -35,6 +35,7 @@ SIGNATURES = {
     "tpl_kkt_incidence": (C.c_int, [C.c_void_p, C.POINTER(c_u32p), C.POINTER(c_u32p), C.POINTER(c_dp), c_szp,
                                     C.POINTER(C.c_int)]),
     "tpl_op_from_csc": (C.c_int, [C.c_size_t, c_u64p, c_u64p, c_dp, C.c_int, C.POINTER(C.c_void_p)]),
+    "tpl_op_from_dense": (C.c_int, [C.c_size_t, c_dp, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "tpl_op_from_kkt": (C.c_int, [C.c_size_t, C.c_size_t, c_u32p, c_u32p, c_dp, C.c_size_t, C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "tpl_op_from_kkt_system": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -15,6 +15,7 @@
 
 #include "tpl_internal.h"
 #include "tpl_cells_host.h"
+#include "tpl_dense.cuh"
 #include "tpl_kernels.cuh"
 #include "tpl_sharded.cuh"
 #include "tpl_tiles.cuh"
@@ -139,11 +140,12 @@ struct tpl_op {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  int format = 0;  // 1 = CSR, 2 = incidence
+  int format = 0;  // 1 = CSR, 2 = incidence, 3 = dense symmetric
   uint32_t n = 0;
   int G = 0;  // CTAs of the persistent grid (= SM count)
   tpl::IncidenceOp inc{};
   tpl::CsrOp csr{};
+  tpl::DenseOp dense{};
   std::vector<std::pair<void*, size_t>> allocs;
   size_t device_bytes = 0;
   uint64_t matrix_bytes = 0;
@@ -550,6 +552,13 @@ int finish_setup(tpl_op* op) {
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t2, tpl::pass2_tiled_kernel<true>, tpl::kBlock, op->smem_tile2));
       if (t1 < 1 || t2 < 1) op->tiled_ok = false;
     }
+  } else if (op->format == 3) {
+    if (int rc = set_smem(tpl::pass1_dense_kernel<false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass1_dense_kernel<true>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_dense_kernel<false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_dense_kernel<true>, smem)) return rc;
+    if (int rc = set_smem(tpl::apply_dense_kernel, smem)) return rc;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_dense_kernel<true>, tpl::kBlock, smem));
   } else {
     if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, false>, smem)) return rc;
     if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, true>, smem)) return rc;
@@ -640,6 +649,40 @@ int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, co
   if (!rc) rc = upload_long_rows(op, h, op->csr.lr);
   op->matrix_bytes = 12ull * nnz + 4ull * (n + 1);
   op->smem_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
+  if (!rc) rc = finish_setup(op);
+  if (rc) {
+    std::string keep = tpl::g_err;
+    tpl_op_free(op);
+    tpl::g_err = keep;
+    return rc;
+  }
+  *out = op;
+  return TPL_OK;
+}
+
+int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op** out) {
+  tpl::clear_error();
+  if (!out || (n && !a)) return fail(TPL_ERR_PANIC, "null argument");
+  if (n == 0 || n >= 0x7fffffffull || lda < n)
+    return fail(TPL_ERR_DIMENSION_MISMATCH, "Dimension mismatch: operator has %zu columns but vector has %zu rows.", n, lda);
+  tpl_op* op = new tpl_op;
+  int rc = open_device(op, device);
+  if (rc) {
+    delete op;
+    return rc;
+  }
+  op->format = 3;
+  op->n = (uint32_t)n;
+  double* ad = nullptr;
+  rc = dev_alloc(op, &ad, n * n);
+  if (!rc && cudaMemcpy2D(ad, n * sizeof(double), a, lda * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = fail(TPL_ERR_CUDA, "CUDA error: copying the dense operator to the device failed");
+  op->dense.n = (uint32_t)n;
+  op->dense.lda = n;
+  op->dense.a = ad;
+  op->dense.stage = n * sizeof(double) <= kSmemBudget ? 1u : 0u;
+  op->smem_bytes = op->dense.stage ? n * sizeof(double) : 0;
+  op->matrix_bytes = 8ull * n * n;
   if (!rc) rc = finish_setup(op);
   if (rc) {
     std::string keep = tpl::g_err;
@@ -990,6 +1033,7 @@ bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op
 }  // namespace
 static const char* shape_name(const tpl_op* op) {
   if (op->comm) return op->fab_connected && op->mode == 0 ? "sharded-fused" : "sharded";
+  if (op->format == 3) return "dense";
   if (op->format != 2) return "csr";
   if (op->mode == 1) return "gather";
   if (use_cells(op)) return "cells";
@@ -1019,6 +1063,8 @@ int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   if (whole_pass && use_tiled(op))
     return with_v ? launch_tiled(op, tpl::pass1_tiled_kernel<true>, a, op->smem_tile1)
                   : launch_tiled(op, tpl::pass1_tiled_kernel<false>, a, op->smem_tile1);
+  if (op->format == 3)
+    return with_v ? launch_coop(op, tpl::pass1_dense_kernel<true>, op->dense, a) : launch_coop(op, tpl::pass1_dense_kernel<false>, op->dense, a);
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, false>, op->inc, a);
@@ -1036,6 +1082,8 @@ int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   if (use_tiled(op))
     return with_v ? launch_tiled(op, tpl::pass2_tiled_kernel<true>, a, op->smem_tile2)
                   : launch_tiled(op, tpl::pass2_tiled_kernel<false>, a, op->smem_tile2);
+  if (op->format == 3)
+    return with_v ? launch_coop(op, tpl::pass2_dense_kernel<true>, op->dense, a) : launch_coop(op, tpl::pass2_dense_kernel<false>, op->dense, a);
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, false>, op->inc, a);
@@ -1350,7 +1398,9 @@ int tpl_op_apply(tpl_op* op, const double* x, double* y) {
   const double* x_dev = nullptr;
   if (int rc = stage_b(op, x, &x_dev)) return rc;
   double* y_dev = is_device_ptr(y) ? y : op->x_d;
-  if (op->format == 2)
+  if (op->format == 3)
+    tpl::apply_dense_kernel<<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->dense, x_dev, y_dev);
+  else if (op->format == 2)
     tpl::apply_kernel<tpl::IncidenceOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->inc, x_dev, y_dev);
   else
     tpl::apply_kernel<tpl::CsrOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->csr, x_dev, y_dev);

@@ -24,7 +24,7 @@ def _vec_ptr(v):
 class LinOp:
     """Owns a `tpl_op*`.  `nrows()`/`ncols()`/`apply()` mirror faer's LinOp trait."""
 
-    FORMAT = {1: "csr", 2: "incidence"}
+    FORMAT = {1: "csr", 2: "incidence", 3: "dense"}
 
     def __init__(self, handle: C.c_void_p):
         self._h = handle
@@ -50,9 +50,14 @@ class LinOp:
 
     @classmethod
     def from_dense(cls, a, device: int = -1) -> "LinOp":
-        import scipy.sparse as sp
-
-        return cls.from_scipy(sp.csc_matrix(np.asarray(a, dtype=np.float64)), device)
+        """Dense symmetric operator (faer `Mat<f64>` as LinOp, src/bin/dense_tradeoff.rs:154-162): streamed by the dense
+        kernels, 8 n^2 bytes per product."""
+        a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+        if a.ndim != 2 or a.shape[0] != a.shape[1]:
+            raise ValueError("a square matrix is required")
+        h = C.c_void_p()
+        _lib.check(_lib.load().tpl_op_from_dense(a.shape[0], a.ctypes.data_as(c_dp), a.shape[0], device, C.byref(h)))
+        return cls(h)
 
     @classmethod
     def from_kkt(cls, m, p, tail, head, d, device: int = -1) -> "LinOp":
