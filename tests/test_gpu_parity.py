@@ -220,3 +220,40 @@ def test_device_resident_vectors():
     assert x_dev.is_cuda and np.array_equal(x_dev.cpu().numpy(), x_host)
     y = gop.apply(torch.from_numpy(b).cuda())
     assert np.array_equal(y.cpu().numpy(), gop.apply(b))
+
+
+@pytest.mark.parametrize("fmt", ["incidence", "incidence-chunks", "incidence-tiled", "incidence-gather"])
+def test_irregular_random_graph(fmt):
+    """Arcs in no particular order, self-loops, parallel arcs, isolated nodes and a short D (the loader's quirk): every
+    execution shape of the incidence operator against the oracle on the same triplets."""
+    rng = np.random.default_rng(17)
+    p, m = 403, 9000
+    tail = rng.integers(0, p - 30, m).astype(np.uint32)    # the last 30 nodes never appear as tails
+    head = rng.integers(12, p - 12, m).astype(np.uint32)   # ... 12 nodes are isolated altogether
+    tail[::19] = head[::19]                                # self-loops (merged E entry = explicit 0)
+    tail[1::37], head[1::37] = tail[0], head[0]            # parallel arcs
+    d = np.zeros(m)
+    d[: m - 500] = rng.uniform(1.0, 10.0, m - 500)         # D shorter than m: zero beyond (data_loader.rs:172-195)
+    j = np.arange(m, dtype=np.uint64)
+    t, h = tail.astype(np.uint64), head.astype(np.uint64)
+    ones = np.ones(m)
+    oop = orc.SparseColMat.try_new_from_triplets(
+        m + p, m + p, np.concatenate([j, m + t, m + h, j, j]), np.concatenate([j, j, j, m + t, m + h]),
+        np.concatenate([d, ones, -ones, ones, -ones]))
+    gop = tpl.LinOp.from_kkt(m, p, tail, head, d[: m - 500])
+    gop.set_mode({"incidence-chunks": 4, "incidence-tiled": 2, "incidence-gather": 3}.get(fmt, 0))
+    x = rng.standard_normal(m + p)
+    assert helpers.rel(gop.apply(x), oop.apply(x)) < 1e-14
+    b = helpers.seeded_b(m + p)
+    k = 50
+    v_ref, d_ref = orc.lanczos_standard(oop, b, k)
+    po = alg.lanczos_pass_one(gop, b, k)
+    J = helpers.ortho_horizon(v_ref, 1e-8)
+    assert J >= 20 and po.steps_taken == d_ref.steps_taken
+    assert np.max(np.abs(po.alphas[:J] - d_ref.alphas[:J])) <= COEF_RTOL * np.abs(d_ref.alphas).max()
+    assert np.max(np.abs(po.betas[:J - 1] - d_ref.betas[:J - 1])) <= COEF_RTOL * np.abs(d_ref.betas).max()
+    out = alg.lanczos_standard(gop, b, k)
+    p2 = alg.lanczos_pass_two_with_basis(gop, b, po, 0.1 * (np.arange(k) + 1))
+    assert np.array_equal(p2.v_k, out.v_k)
+    x2 = tpl.lanczos_two_pass(gop, b / np.linalg.norm(b), 30, "exp")
+    assert helpers.rel(x2, orc.lanczos_two_pass(oop, b / np.linalg.norm(b), 30, npo.exp_tk_solver)) < X_RTOL
