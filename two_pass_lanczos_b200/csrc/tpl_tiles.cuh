@@ -218,13 +218,20 @@ __device__ __forceinline__ uint4 ld_relaxed_sys_v4(const uint4* p) {
   asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 ld_acquire_sys_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.acquire.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
 // Barrier + all-reduce over the CTAs of ALL ranks (world > 1): the same self-validating 16-byte slots as grid_sync, but every
 // CTA pushes its slot into every rank's replica over NVLink (lane r -> rank r) and polls only its local replica.  System-scope
 // fences order the peer-memory data written before the call (partials, node values) before the slot, and the local reads
 // after the poll.  The payloads are added in slot order: the result is identical in every CTA of every rank.
-template <bool REDUCE>
+// FENCED = false: pure barrier + all-reduce, for the alpha reduction of pass 1 -- no peer memory is written in the phase
+// before it and none is read in the phase after it, so the two system-scope fences (an NVLink round trip each) are skipped.
+template <bool REDUCE, bool FENCED>
 __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsigned int& epoch, CtaShared& sh) {
   const Fabric& f = to.fab;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,7 +249,7 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
     }
     const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
     const uint32_t src = f.rank * gridDim.x + blockIdx.x;
-    fence_acq_rel_sys();
+    if (FENCED) fence_acq_rel_sys();
     if (lane < f.world)
       st_relaxed_sys_v4(f.slots[lane] + (size_t)(epoch & 1u) * f.Gtot + src,
                         make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
@@ -255,7 +262,9 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
           const uint32_t i = base + lane + 32 * q;
-          q4[q] = ld_relaxed_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1));
+          // FENCED: acquire loads pair with the peers' fence + store (a trailing fence would also wait for the acknowledgement
+          // of our own slot stores, a whole NVLink round trip)
+          q4[q] = FENCED ? ld_acquire_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1)) : ld_relaxed_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1));
         }
         bool ok = true;
 #pragma unroll
@@ -277,7 +286,6 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
       }
     }
     __syncwarp();
-    fence_acq_rel_sys();
     if (REDUCE) {
       s = warp_sum(s);
       if (lane == 0) sh.result = s;
@@ -287,9 +295,9 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
   return REDUCE ? sh.result : 0.0;
 }
 // the barrier of the tiled kernels: the single-GPU grid barrier, or the fabric-wide one
-template <bool REDUCE>
+template <bool REDUCE, bool FENCED = true>
 __device__ __forceinline__ double tile_sync(double v, const TileOp& to, const GridSync& gs, unsigned int& epoch, CtaShared& sh) {
-  if (to.fab.world > 1) return fabric_sync<REDUCE>(v, to, epoch, sh);
+  if (to.fab.world > 1) return fabric_sync<REDUCE, FENCED>(v, to, epoch, sh);
   return grid_sync<REDUCE>(v, gs, epoch, sh);
 }
 
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       }
       trace_mark(gs.trace, j, 3);
       gs.trace_base = 4;
-      const double alpha = tile_sync<true>(acc, to, gs, epoch, sh);
+      const double alpha = tile_sync<true, false>(acc, to, gs, epoch, sh);
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
       acc = 0.0;
