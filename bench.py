@@ -84,7 +84,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -229,12 +229,13 @@ def run_b200(args, rank, world, local_rank):
     def solve_host():
         return tpl.lanczos_two_pass(op, b_host, k, "inv")
 
+    # nvidia-smi needs ~0.1 s before its first sample: it is started before the warm-up so that it is already sampling
+    # (every 50 ms) when the timed regions begin; the clocks reported are the median over warm-up + timed regions
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         solve_dev()
         solve_host()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     # ---- value: device-resident inputs, CUDA events on the launching stream, L2 flushed between solves
     launches0 = op.kernel_launches()
     barrier()

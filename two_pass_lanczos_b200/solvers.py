@@ -47,6 +47,13 @@ def _solve(entry: str, operator: LinOp, b, k: int, f_tk_solver):
     if is_torch and keep.is_cuda:
         x = keep.new_empty(n)
         xptr = C.c_void_p(x.data_ptr())
+    elif is_torch and keep.is_pinned():
+        # pinned host tensor in -> pinned host tensor out (torch caches pinned blocks): the result comes back in one DMA
+        # instead of the driver's staged copy into pageable memory
+        import torch
+
+        x = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        xptr = C.c_void_p(x.data_ptr())
     else:
         x = np.empty(n)
         xptr = C.c_void_p(x.ctypes.data)
