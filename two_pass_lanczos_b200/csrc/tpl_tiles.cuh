@@ -233,6 +233,7 @@ __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_re
 // before it and none is read in the phase after it, so the two system-scope fences (an NVLink round trip each) are skipped.
 template <bool REDUCE, bool FENCED>
 __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsigned int& epoch, CtaShared& sh) {
+  __shared__ double chunk_sum[kWarps];
   const Fabric& f = to.fab;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   epoch += 1;
@@ -253,46 +254,50 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
     if (lane < f.world)
       st_relaxed_sys_v4(f.slots[lane] + (size_t)(epoch & 1u) * f.Gtot + src,
                         make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
-    const uint4* slots = f.slots[f.rank] + (size_t)(epoch & 1u) * f.Gtot;
-    double s = 0.0;
-    for (uint32_t base = 0; base < f.Gtot; base += 160) {
-      uint4 q4[5];
-      unsigned int spins = 0;
-      for (;;) {
+  }
+  // The slots are polled in chunks of 160 (five per lane); chunk w by warp w, all chunks at the same time (8 ranks: 1184
+  // slots, one L2 round trip instead of eight).  Slot order inside a chunk is lane-strided, the lanes are combined by the
+  // xor tree and the chunk sums are added in chunk order: a fixed order, identical in every CTA of every rank.
+  const uint32_t nchunks = (f.Gtot + 159) / 160;
+  const uint4* slots = f.slots[f.rank] + (size_t)(epoch & 1u) * f.Gtot;
+  for (uint32_t ch = warp; ch < nchunks; ch += kWarps) {
+    const uint32_t base = ch * 160;
+    uint4 q4[5];
+    unsigned int spins = 0;
+    for (;;) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const uint32_t i = base + lane + 32 * q;
-          // FENCED: acquire loads pair with the peers' fence + store (a trailing fence would also wait for the acknowledgement
-          // of our own slot stores, a whole NVLink round trip)
-          q4[q] = FENCED ? ld_acquire_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1)) : ld_relaxed_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1));
-        }
-        bool ok = true;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const uint32_t i = base + lane + 32 * q;
-          ok = ok & ((i >= f.Gtot) | ((q4[q].y == epoch) & (q4[q].w == epoch)));
-        }
-        if (ok) break;
-        if (++spins > kSpinLimit) __trap();
+      for (int q = 0; q < 5; ++q) {
+        const uint32_t i = base + lane + 32 * q;
+        // FENCED: acquire loads pair with the peers' fence + store (a trailing fence would also wait for the acknowledgement
+        // of our own slot stores, a whole NVLink round trip)
+        q4[q] = FENCED ? ld_acquire_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1)) : ld_relaxed_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1));
       }
-      if (REDUCE) {
-        // slot order inside a chunk of 160 is lane-strided; the chunk sums are combined by the xor tree below: fixed order
-        double c = 0.0;
+      bool ok = true;
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-          if (base + lane + 32 * q < f.Gtot)
-            c = __dadd_rn(c, __longlong_as_double((long long)(((unsigned long long)q4[q].z << 32) | q4[q].x)));
-        s = __dadd_rn(s, c);
+      for (int q = 0; q < 5; ++q) {
+        const uint32_t i = base + lane + 32 * q;
+        ok = ok & ((i >= f.Gtot) | ((q4[q].y == epoch) & (q4[q].w == epoch)));
       }
+      if (ok) break;
+      if (++spins > kSpinLimit) __trap();
     }
     __syncwarp();
     if (REDUCE) {
-      s = warp_sum(s);
-      if (lane == 0) sh.result = s;
+      double c = 0.0;
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (base + lane + 32 * q < f.Gtot)
+          c = __dadd_rn(c, __longlong_as_double((long long)(((unsigned long long)q4[q].z << 32) | q4[q].x)));
+      c = warp_sum(c);
+      if (lane == 0) chunk_sum[ch % kWarps] = c;  // (more than kWarps chunks never happens: Gtot <= 8 * 148)
     }
   }
   __syncthreads();
-  return REDUCE ? sh.result : 0.0;
+  double s = 0.0;
+  if (REDUCE)
+    for (uint32_t ch = 0; ch < nchunks; ++ch) s = __dadd_rn(s, chunk_sum[ch]);
+  __syncthreads();  // chunk_sum may be rewritten by the next call
+  return s;
 }
 // the barrier of the tiled kernels: the single-GPU grid barrier, or the fabric-wide one
 template <bool REDUCE, bool FENCED = true>
