@@ -1,5 +1,6 @@
 """Timing of the cell kernels at one size, with the per-phase / per-warp trace (diagnostics).
-usage: cells_exp.py [arcs] [k] ; TPL_CELL_FLAGS selects experiment switches."""
+usage: cells_exp.py [arcs] [k] [--trace] [--grid] [--skew]
+(the trace itself costs ~2 000 cycles per step, most of them on warp 0, whose thread 0 writes the marks)"""
 import os
 import sys
 
@@ -21,7 +22,7 @@ for rep in range(4):
     tm = op.last_timing()
     best = min(best, (tm["pass_one_ms"], tm["pass_two_ms"]))
 res = np.linalg.norm(op.apply(x) - b) / np.linalg.norm(b)
-print(f"flags={os.environ.get('TPL_CELL_FLAGS', '0')} m={arcs} k={K}: pass1 {best[0]:.3f} ms pass2 {best[1]:.3f} ms "
+print(f"{op.kernel_shape()} m={arcs} k={K}: pass1 {best[0]:.3f} ms pass2 {best[1]:.3f} ms "
       f"total {best[0] + best[1]:.3f} ms residual {res:.3e}", flush=True)
 if "--trace" not in sys.argv:
     sys.exit(0)

@@ -38,6 +38,27 @@ def test_headline_two_pass_residual_and_variants(headline):
     assert np.array_equal(tpl.lanczos_two_pass(gop, 2.0 * b, k, "inv"), 2.0 * x2)
 
 
+def test_kernel_shapes_by_size(headline):
+    """The headline instance runs on the cell kernels; 650k arcs (cells too large) on the chunk-resident or the tiled ones,
+    whichever fits; 2M arcs on the tiled streaming ones; every mode switch reports what it selects."""
+    inst, gop, b = headline
+    assert gop.kernel_shape() == "cells"
+    for mode, shape in ((4, "chunks"), (2, "tiled"), (3, "gather"), (1, "gather"), (0, "cells")):
+        gop.set_mode(mode)
+        assert gop.kernel_shape() == shape
+    for m, shapes in ((650_000, ("chunks", "tiled")), (2_000_000, ("tiled",))):
+        big = datagen.gen_kkt(m, 3, 2, "wc")
+        op = tpl.LinOp.from_kkt(big.m, big.p, big.tail, big.head, big.d)
+        assert op.kernel_shape() in shapes, op.kernel_shape()
+        bb = op.apply(np.full(big.n, 1.0 / np.sqrt(big.n)))
+        d1 = alg.lanczos_pass_one(op, bb, 30)
+        op.set_mode(3)  # the gather kernels as an independent implementation
+        d2 = alg.lanczos_pass_one(op, bb, 30)
+        assert np.max(np.abs(d1.alphas - d2.alphas)) <= 1e-10 * np.abs(d2.alphas).max()
+        assert np.max(np.abs(d1.betas - d2.betas)) <= 1e-10 * np.abs(d2.betas).max()
+        op.close()
+
+
 def test_headline_against_oracle_prefix(headline):
     """alpha/beta vs the CPU oracle on the full-size instance for the first 40 steps (seconds on one core)."""
     inst, gop, b = headline

@@ -5,7 +5,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
-#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -52,8 +51,7 @@ inline std::vector<uint32_t> balanced_blocks(const std::vector<uint64_t>& weight
   // Blocks end on line boundaries whenever there are enough lines: a line cut by a block boundary would collect the
   // contributions of two rows (or columns) of cells, and its owner -- which every all-reduce waits for -- would be the last
   // to have its node sums complete (measured: 36 instead of 24 contributions cost its owner ~2x the wait).
-  static const bool align = !(std::getenv("TPL_CELL_ALIGN") && std::getenv("TPL_CELL_ALIGN")[0] == '0');
-  if (align && p >= (size_t)parts * kLine * 8)  // at least 8 lines per block: rounding then costs < ~10 % of balance
+  if (p >= (size_t)parts * kLine * 8)  // at least 8 lines per block: rounding then costs < ~10 % of balance
     for (uint32_t i = 1; i < parts; ++i) bnd[i] = std::min<uint32_t>((uint32_t)p, (bnd[i] + kLine / 2) / kLine * kLine);
   for (uint32_t i = 1; i <= parts; ++i) bnd[i] = std::max(bnd[i], bnd[i - 1]);
   return bnd;

@@ -821,7 +821,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       }
     }
   }
-  // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of kUnroll * kBlock arcs, at most
+  // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of the stream batch, at most
   // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
   if (!rc && p >= 1 && p < (1u << 17)) {
     int max_optin = 0;

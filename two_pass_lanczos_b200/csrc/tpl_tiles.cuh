@@ -31,6 +31,7 @@ constexpr int kUnroll2 = 2;            // pass 2: six loads per arc, two batches
 constexpr int kUnrollB = 4;            // pass 1 phase B: two loads per arc
 constexpr int kPre = 16;               // list entries per fold thread requested together
 constexpr int kStreamWarps = 8;        // warps 0..7 stream a tile from HBM while warps 8..15 fold the previous one into the node sums
+                                       // (10 / 6 is better at 5M arcs, worse at 50M; 12 / 4 is worse everywhere)
 constexpr int kFoldWarps = kWarps - kStreamWarps;
 constexpr int kStreamThreads = kStreamWarps * 32, kFoldThreads = kFoldWarps * 32;
 
@@ -55,7 +56,7 @@ struct TileOp {
   Fabric fab;
   // per tile: {first entry word, entries per thread L, first piece, end piece}
   const uint4* thdr;      // [G * ntile]
-  // entries, per tile L x kBlock words, thread-interleaved (word q of thread i at q * kBlock + i => coalesced):
+  // entries, per tile L x kFoldThreads words, thread-interleaved (word q of fold thread i at q * kFoldThreads + i => coalesced):
   //   node << 15 | minus << 14 | index into the tile (arcs, then pieces);  0xffffffff = padding.
   // A tile's entries are sorted by node and cut into kBlock slices of (nearly) equal length at node boundaries, so a
   // node is folded by exactly one thread per tile and all threads carry the same load.
@@ -313,8 +314,7 @@ __device__ __forceinline__ double tile_sync(double v, const TileOp& to, const Gr
 // the (shared-memory bound) list walk therefore overlap; before, they alternated and the walk was 57 % of the phase.
 // Inside issue / consume a stream thread addresses arcs i0 + q * kStreamThreads + threadIdx.x.  The caller has zeroed s.acc
 // and synchronised; on return every fold is complete (CTA-wide barrier).
-// DEEP: two batches of loads in flight ahead of the one being consumed (three register sets) instead of one.
-template <int BATCH, class REGS, bool DEEP, class ISSUE, class CONSUME>
+template <int BATCH, class REGS, class ISSUE, class CONSUME>
 __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, const TileCtx& c, ISSUE issue, CONSUME consume,
                                           const Trace* tr = nullptr, int tr_step = -1) {
   const uint32_t tile0 = blockIdx.x * to.ntile;
@@ -323,9 +323,8 @@ __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, c
   const bool timed = tr != nullptr && tr->buf != nullptr;
   if (threadIdx.x < kStreamThreads) {
     long long c_stream = 0, c_wait = 0, t_a = 0, t_b = 0;
-    REGS cur, nx1;
+    REGS cur;
     if (ntiles) issue(c.alo, cur);
-    if (DEEP && ntiles && c.alo + BATCH < c.ahi) issue(c.alo + BATCH, nx1);
     for (uint32_t t = 0; t < ntiles; ++t) {
       const uint32_t t0 = c.alo + t * to.T, t1 = min(c.ahi, t0 + to.T);
       const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
@@ -334,16 +333,9 @@ __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, c
       if (timed) { t_b = clock64(); c_wait += t_b - t_a; }
       for (uint32_t i0 = t0; i0 < t1; i0 += BATCH) {
         REGS nxt;
-        if (DEEP) {
-          if (i0 + 2 * BATCH < c.ahi) issue(i0 + 2 * BATCH, nxt);
-          consume(i0, t0, cur, wt);
-          cur = nx1;
-          nx1 = nxt;
-        } else {
-          if (i0 + BATCH < c.ahi) issue(i0 + BATCH, nxt);
-          consume(i0, t0, cur, wt);
-          cur = nxt;
-        }
+        if (i0 + BATCH < c.ahi) issue(i0 + BATCH, nxt);  // (two batches ahead was tried: the third register set spills)
+        consume(i0, t0, cur, wt);
+        cur = nxt;
       }
       bar_arrive_n(kBarFull + (t & 1u), kBlock);
       if (timed) c_stream += clock64() - t_b;
@@ -377,7 +369,7 @@ __device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp
   struct R {
     double x[kUnroll];
   };
-  tile_loop<kUnroll * kStreamThreads, R, false>(
+  tile_loop<kUnroll * kStreamThreads, R>(
       to, s, c,
       [&](uint32_t i0, R& r) {
 #pragma unroll
@@ -515,7 +507,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       struct RB {
         double wn[kUnrollB], wc[kUnrollB];
       };
-      tile_loop<kUnrollB * kStreamThreads, RB, false>(
+      tile_loop<kUnrollB * kStreamThreads, RB>(
           to, s, c,
           [&](uint32_t i0, RB& r) {
 #pragma unroll
@@ -665,7 +657,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
       double vc[kUnroll2], vp[kUnroll2], dd[kUnroll2], xx[kUnroll2];
       uint32_t tl[kUnroll2], hd[kUnroll2];
     };
-    tile_loop<kUnroll2 * kStreamThreads, R2, false>(
+    tile_loop<kUnroll2 * kStreamThreads, R2>(
         to, s, c,
         [&](uint32_t i0, R2& r) {
 #pragma unroll
