@@ -85,6 +85,16 @@ int tpl_kkt_csc(const tpl_kkt* kkt, size_t* n, size_t* nnz, const uint64_t** col
 int tpl_kkt_incidence(const tpl_kkt* kkt, const uint32_t** tail, const uint32_t** head,
                       const double** d, size_t* d_len, int* regular);
 
+/* Binary instance container (no reference counterpart -- the reference only reads the text pair,
+ * data_loader.rs:81-137 line by line).  64-byte header {"TPLKKT1\n", version, nodes, arcs, costs, checksum}, then
+ * tail[arcs] and head[arcs] (u32, 0-based, each padded to 8 bytes) and the quadratic costs the .qfc really gave (f64).
+ * A loaded container is the same KKTSystem the text pair gives (its CSC is built on first use); saving needs an
+ * instance whose incidence view is exact (`regular`). */
+int tpl_write_kkt_binary(const char* path, size_t nodes, size_t arcs, const uint32_t* tail, const uint32_t* head,
+                         const double* costs, size_t n_costs);
+int tpl_kkt_save_binary(const tpl_kkt* kkt, const char* path);
+int tpl_load_kkt_binary(const char* path, tpl_kkt** out);
+
 /* ------------------------------------------------------------------------------------
  * Operators  --  the device-resident stand-in for `&impl faer::matrix_free::LinOp<f64>`
  * (src/solvers.rs:56, src/algorithms/mod.rs:167).  Construction uploads the matrix to HBM and builds

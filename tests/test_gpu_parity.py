@@ -208,6 +208,22 @@ def test_irregular_instances_fall_back_to_csr(tmp_path):
     assert np.allclose(d1.alphas, d2.alphas, rtol=1e-12, atol=1e-13)
 
 
+@pytest.mark.parametrize("fmt", ["incidence", "csr"])
+def test_binary_container_gives_the_same_operator(tmp_path, fmt):
+    """text pair and TPLKKT1 container of one instance: same operator, bit-identical solve; the CSR
+    form uses the CSC built straight from the arc list"""
+    dmx = golden_instances()[0]
+    text = data_loader.load_kkt_system(dmx, dmx[:-3] + "wc.qfc", fmt=fmt)
+    path = str(tmp_path / "inst.tplkkt")
+    text.host.save_binary(path)
+    cont = data_loader.load_kkt_system_binary(path, fmt=fmt)
+    assert cont.a.format == text.a.format == fmt
+    assert (cont.num_nodes, cont.num_arcs) == (text.num_nodes, text.num_arcs)
+    b = helpers.seeded_b(text.a.nrows())
+    assert np.array_equal(cont.a.apply(b), text.a.apply(b))
+    assert np.array_equal(tpl.lanczos_two_pass(cont.a, b, 40, "exp"), tpl.lanczos_two_pass(text.a, b, 40, "exp"))
+
+
 def test_device_resident_vectors():
     """b and x may live in HBM (torch CUDA tensors): same bits as the host-pointer path."""
     import torch

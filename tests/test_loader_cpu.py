@@ -179,3 +179,109 @@ def test_generator_shape():
     assert a.d.min() >= 400.0 and a.d.max() <= 1.1e6
     w = datagen.gen_kkt(50_000, 3, 11, "wc")
     assert 1.0 <= w.d.min() and w.d.max() <= 10.0
+
+
+# ------------------------------------------------------------------ binary container
+def _same_system(a, b):
+    assert (a.num_nodes, a.num_arcs, a.num_costs) == (b.num_nodes, b.num_arcs, b.num_costs)
+    for x, y in zip(a.incidence(), b.incidence()):
+        assert np.array_equal(x, y)
+    na, ca, ra, va = a.csc()
+    nb, cb, rb, vb = b.csc()
+    assert na == nb and np.array_equal(ca, cb) and np.array_equal(ra, rb)
+    assert np.array_equal(va, vb) and np.array_equal(np.signbit(va), np.signbit(vb))
+
+
+@pytest.mark.parametrize("dmx", golden_instances()[:2], ids=os.path.basename)
+@pytest.mark.parametrize("ext", ["qfc", "lines.qfc"])
+def test_binary_container_round_trip_on_reference_tool_output(tmp_path, dmx, ext):
+    """text pair -> container -> KKTSystem: incidence view and the CSC of KKTSystem.a (built straight from the arc
+    list, no triplet sort) are entry for entry what the text path gives."""
+    host = data_loader.load_kkt_host(dmx, dmx[:-3] + ext)
+    path = str(tmp_path / "inst.tplkkt")
+    host.save_binary(path)
+    m, nd = host.num_arcs, host.num_costs
+    assert os.path.getsize(path) == 64 + 2 * ((4 * m + 7) // 8 * 8) + 8 * nd
+    _same_system(data_loader.load_kkt_host_binary(path), host)
+
+
+def test_binary_container_quirks_survive(tmp_path):
+    """self-loop (merged explicit zero), parallel arcs, short D, inf: the container keeps all of them"""
+    dmx = _write(tmp_path, "q.dmx", "p min 4 5\na 1 2\na 2 2\na 3 4\na 3 4\na 4 1\n")
+    qfc = _write(tmp_path, "q.qfc", "5\n1\n1\n1\n1\n1\n1.5\n-0.0\ninf\n")
+    host = data_loader.load_kkt_host(dmx, qfc)
+    assert host.num_costs == 3
+    path = str(tmp_path / "q.tplkkt")
+    host.save_binary(path)
+    back = data_loader.load_kkt_host_binary(path)
+    _same_system(back, host)
+    # straight from arrays (what a generator would call), odd arc count -> padded index blocks
+    tail, head, d, d_len, _ = host.incidence()
+    path2 = str(tmp_path / "q2.tplkkt")
+    data_loader.write_kkt_binary(path2, 4, tail, head, d[:d_len])
+    assert open(path, "rb").read() == open(path2, "rb").read()
+    # empty instance
+    path3 = str(tmp_path / "e.tplkkt")
+    data_loader.write_kkt_binary(path3, 0, [], [])
+    e = data_loader.load_kkt_host_binary(path3)
+    assert (e.num_nodes, e.num_arcs, e.csc()[0]) == (0, 0, 0)
+    # an instance whose incidence view is not exact cannot be stored
+    dmx3 = _write(tmp_path, "f.dmx", "p min 3 4\na 1 2\na 2 3\n")
+    host3 = data_loader.load_kkt_host(dmx3, _write(tmp_path, "f.qfc", "4\n0\n0\n0\n0\n1\n2\n3\n4\n"))
+    with pytest.raises(DataLoaderError) as err:
+        host3.save_binary(str(tmp_path / "f.tplkkt"))
+    assert err.value.kind == "SparseMatrixConstructionError"
+
+
+def test_binary_container_generated_instance_matches_text_path(tmp_path):
+    inst = datagen.gen_kkt(20_000, 3, 5, "wc")
+    dmx, qfc = datagen.write_instance(str(tmp_path), inst, layout="lines")
+    host = data_loader.load_kkt_host(dmx, qfc)
+    path = str(tmp_path / "g.tplkkt")
+    data_loader.write_kkt_binary(path, inst.p, inst.tail, inst.head, inst.d)
+    _same_system(data_loader.load_kkt_host_binary(path), host)
+
+
+def test_binary_container_error_branches(tmp_path):
+    good = str(tmp_path / "g.tplkkt")
+    data_loader.write_kkt_binary(good, 3, [0, 1, 2], [1, 2, 0], [1.0, 2.0])
+    raw = open(good, "rb").read()
+
+    def load(data):
+        p = str(tmp_path / "bad.tplkkt")
+        open(p, "wb").write(data)
+        with pytest.raises(DataLoaderError) as e:
+            data_loader.load_kkt_host_binary(p)
+        return e.value.kind
+
+    assert load(b"") == "UnexpectedEof"
+    assert load(b"X" + raw[1:]) == "ProblemLineMissing"       # magic
+    assert load(raw[:-1]) == "UnexpectedEof"                   # truncated payload
+    assert load(raw + b"\0") == "ArcCountMismatch"             # trailing bytes
+    flipped = bytearray(raw)
+    flipped[64] ^= 1                                           # tail[0]: 0 -> 1, checksum no longer matches
+    assert load(bytes(flipped)) == "Io"
+    with pytest.raises(DataLoaderError) as e:
+        data_loader.load_kkt_host_binary(str(tmp_path / "missing.tplkkt"))
+    assert e.value.kind == "Io"
+    with pytest.raises(DataLoaderError) as e:  # node id out of range is refused at write time, like the triplet check
+        data_loader.write_kkt_binary(str(tmp_path / "o.tplkkt"), 3, [0, 3], [1, 2])
+    assert e.value.kind == "SparseMatrixConstructionError"
+    with pytest.raises(DataLoaderError) as e:
+        data_loader.write_kkt_binary(str(tmp_path / "o.tplkkt"), 3, [0], [1], [1.0, 2.0])
+    assert e.value.kind == "ArcCountMismatch"
+
+
+def test_cost_spellings_round_like_the_reference(tmp_path):
+    """<f64 as FromStr> corner spellings: saturating overflow / underflow, subnormals, long mantissas, exponent forms"""
+    vals = ["1e400", "-1e400", "1e-400", "4.9e-324", "2.2250738585072011e-308", "0.1", "123456789012345678901234567890",
+            "1E5", "-.5e-3", "+7.", "9007199254740993", "0.3000000000000000444089209850062616169452667236328125", "NaN", "-inf"]
+    m = len(vals)
+    dmx = _write(tmp_path, "v.dmx", "p min 2 %d\n" % m + "a 1 2\n" * m)
+    qfc = _write(tmp_path, "v.qfc", "%d\n" % m + "0\n" * m + "\n".join(vals) + "\n")
+    host = data_loader.load_kkt_host(dmx, qfc)
+    ref = orc.load_kkt_system(dmx, qfc)
+    d = host.incidence()[2]
+    want = np.array([float(v) for v in vals])
+    assert np.array_equal(d, want, equal_nan=True) and np.array_equal(np.signbit(d), np.signbit(want))
+    assert np.array_equal(host.csc()[3], ref.a.csc()[2], equal_nan=True)

@@ -26,6 +26,9 @@ SIGNATURES = {
     "tpl_last_error_message": (C.c_char_p, []),
     "tpl_version": (C.c_char_p, []),
     "tpl_load_kkt": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "tpl_write_kkt_binary": (C.c_int, [C.c_char_p, C.c_size_t, C.c_size_t, c_u32p, c_u32p, c_dp, C.c_size_t]),
+    "tpl_kkt_save_binary": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "tpl_load_kkt_binary": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "tpl_kkt_free": (None, [C.c_void_p]),
     "tpl_kkt_num_nodes": (C.c_size_t, [C.c_void_p]),
     "tpl_kkt_num_arcs": (C.c_size_t, [C.c_void_p]),

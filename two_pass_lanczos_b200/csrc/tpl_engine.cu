@@ -871,6 +871,7 @@ int tpl_op_from_kkt_system(const tpl_kkt* kkt, int format, int device, tpl_op** 
   if (format == 2 || (format == 0 && kkt->regular))
     return tpl_op_from_kkt(kkt->num_arcs, kkt->num_nodes, kkt->tail.data(), kkt->head.data(), kkt->d.data(),
                            kkt->costs.size(), device, out);
+  tpl::kkt_ensure_csc(kkt);
   return tpl_op_from_csc(kkt->num_arcs + kkt->num_nodes, kkt->colptr.data(), kkt->rowidx.data(), kkt->val.data(),
                          device, out);
 }

@@ -37,4 +37,9 @@ struct tpl_kkt {
   std::vector<uint32_t> tail, head;
   std::vector<double> d;  // zero-padded to num_arcs
   bool regular = false;
+  bool lazy_csc = false;  // container-loaded: the CSC views above are built on first use (kkt_ensure_csc)
 };
+
+namespace tpl {
+void kkt_ensure_csc(const tpl_kkt* kkt);
+}

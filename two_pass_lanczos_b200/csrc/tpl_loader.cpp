@@ -12,12 +12,20 @@
 //     (SURVEY C2).  Reproduced on purpose: this is a drop-in.
 //   * A = [[D, E^T], [E, 0]], n = nodes + arcs, arcs first (data_loader.rs:222-248).
 // The whole file is read once and scanned in place (the reference goes line by line through a
-// BufReader); a 500k-arc pair loads in tens of milliseconds.
+// BufReader).
+//
+// the binary instance container (`tpl_write_kkt_binary` / `tpl_load_kkt_binary`).  A text pair of a
+// 50M-arc instance is ~1.5 GB and parse-bound; the container holds the incidence view as raw little-endian arrays
+// (12 bytes per arc + 8 per cost) behind a 64-byte header with a checksum and loads at file-read speed.  The CSC of
+// KKTSystem.a is then built on first use, directly from the arc list in O(nnz) (no triplet sort), entry for entry what
+// the triplet path produces (tests/test_loader_cpu.py compares the two).
 #include <algorithm>
 #include <cerrno>
+#include <charconv>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "tpl_internal.h"
@@ -32,10 +40,15 @@ bool read_file(const char* path, std::string& out, std::string& why) {
     why = strerror(errno);
     return false;
   }
-  char buf[1 << 16];
-  size_t got;
   out.clear();
-  while ((got = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, got);
+  if (fseek(f, 0, SEEK_END) == 0) {  // regular file: one read into a buffer of the right size
+    const long size = ftell(f);
+    if (size > 0) out.reserve(size_t(size));
+    rewind(f);
+  }
+  std::vector<char> buf(1 << 20);
+  size_t got;
+  while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) out.append(buf.data(), got);
   bool ok = !ferror(f);
   if (!ok) why = strerror(errno);
   fclose(f);
@@ -121,8 +134,13 @@ bool rust_f64(const char* b, const char* e, double& out) {
     if (!ed) return false;
   }
   if (s != e) return false;
-  std::string tmp(b, e);
-  out = strtod(tmp.c_str(), nullptr);  // correctly rounded, like core::num::dec2flt
+  // correctly rounded, like core::num::dec2flt; the syntax was validated above (from_chars takes no leading '+')
+  const char* first = (*b == '+') ? b + 1 : b;
+  const std::from_chars_result r = std::from_chars(first, e, out, std::chars_format::general);
+  if (r.ec == std::errc::result_out_of_range) {  // dec2flt saturates: overflow -> inf, underflow -> 0
+    std::string tmp(b, e);
+    out = strtod(tmp.c_str(), nullptr);
+  }
   return true;
 }
 
@@ -200,13 +218,13 @@ int parse_dmx(const char* path, tpl_kkt& k, std::vector<uint64_t>& tails, std::v
       uint64_t uv[2];
       for (int q = 0; q < 2; ++q) {
         uint64_t v;
-        std::string s(tok[1 + q].first, tok[1 + q].second);
         if (!rust_usize(tok[1 + q].first, tok[1 + q].second, v))
-          return fail(TPL_ERR_PARSE_INT, "Parse error: Failed to parse integer from '%s'", s.c_str());
+          return fail(TPL_ERR_PARSE_INT, "Parse error: Failed to parse integer from '%s'",
+                      std::string(tok[1 + q].first, tok[1 + q].second).c_str());
         if (v == 0)
           return fail(TPL_ERR_INVALID_NODE_INDEX,
                       "Format error: Invalid node index '%s'. DIMACS format requires 1-based positive integers.",
-                      s.c_str());
+                      std::string(tok[1 + q].first, tok[1 + q].second).c_str());
         uv[q] = v - 1;
       }
       tails.push_back(uv[0]);
@@ -216,15 +234,6 @@ int parse_dmx(const char* path, tpl_kkt& k, std::vector<uint64_t>& tails, std::v
   if (!found)
     return fail(TPL_ERR_PROBLEM_LINE_MISSING,
                 "Format error: The 'p min' problem line was not found or was malformed.");
-  std::vector<Trip> t;
-  t.reserve(2 * tails.size());
-  for (size_t j = 0; j < tails.size(); ++j) {
-    t.push_back({tails[j], j, 1.0});
-    t.push_back({heads[j], j, -1.0});
-  }
-  if (!build_csc(k.num_nodes, k.num_arcs, t, k.e_colptr, k.e_rowidx, k.e_val))
-    return fail(TPL_ERR_SPARSE_CONSTRUCTION,
-                "Internal error: Failed to construct the sparse matrix from triplets.");
   return TPL_OK;
 }
 
@@ -256,7 +265,114 @@ int parse_qfc(const char* path, size_t expected_arcs, std::vector<double>& costs
   return TPL_OK;
 }
 
+
+// ---------------------------------------------------------------- binary container
+constexpr char kMagic[8] = {'T', 'P', 'L', 'K', 'K', 'T', '1', '\n'};
+struct BinHeader {  // 64 bytes, little endian
+  char magic[8];
+  uint32_t version;  // 1
+  uint32_t flags;    // reserved, 0
+  uint64_t nodes, arcs, n_costs;
+  uint64_t checksum;  // word_hash over the payload as written
+  uint64_t reserved[2];
+};
+static_assert(sizeof(BinHeader) == 64, "header layout");
+
+// 4-lane multiply-xorshift hash over 8-byte words (a 1.2 GB payload hashes in a fraction of its read time)
+uint64_t word_hash(const unsigned char* p, size_t bytes, uint64_t seed) {
+  uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull,
+                   seed ^ 0x27D4EB2F165667C5ull};
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32) {
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+    for (int q = 0; q < 4; ++q) {
+      h[q] = (h[q] ^ w[q]) * 0xFF51AFD7ED558CCDull;
+      h[q] ^= h[q] >> 29;
+    }
+  }
+  uint64_t t = bytes;
+  for (; i < bytes; ++i) t = (t ^ p[i]) * 0x100000001B3ull;
+  for (int q = 0; q < 4; ++q) {
+    t = (t ^ h[q]) * 0xC4CEB9FE1A85EC53ull;
+    t ^= t >> 32;
+  }
+  return t;
+}
+
+size_t pad8(size_t bytes) { return (bytes + 7) & ~size_t(7); }
+
+// E and A = [[D,E^T],[E,0]] straight from the arc list, entry for entry what build_csc makes of the loader's triplets:
+// column j < m holds D_jj (when the .qfc gave it), then the tail / head rows in ascending order (a self-loop's +1 and -1
+// merge into one explicit 0); column m+i holds the arcs at node i in ascending arc order.
+void csc_from_incidence(tpl_kkt& k) {
+  const size_t m = k.num_arcs, p = k.num_nodes, n = m + p, nd = k.costs.size();
+  k.e_colptr.assign(m + 1, 0);
+  k.e_rowidx.clear();
+  k.e_val.clear();
+  k.e_rowidx.reserve(2 * m);
+  k.e_val.reserve(2 * m);
+  std::vector<uint64_t> deg(p + 1, 0);
+  for (size_t j = 0; j < m; ++j) {
+    const uint64_t t = k.tail[j], h = k.head[j];
+    if (t == h) {
+      k.e_rowidx.push_back(t);
+      k.e_val.push_back(1.0 + -1.0);
+      ++deg[t + 1];
+    } else {
+      const bool tf = t < h;
+      k.e_rowidx.push_back(tf ? t : h);
+      k.e_val.push_back(tf ? 1.0 : -1.0);
+      k.e_rowidx.push_back(tf ? h : t);
+      k.e_val.push_back(tf ? -1.0 : 1.0);
+      ++deg[t + 1];
+      ++deg[h + 1];
+    }
+    k.e_colptr[j + 1] = k.e_rowidx.size();
+  }
+  const size_t nnz = nd + 2 * k.e_rowidx.size();
+  k.colptr.assign(n + 1, 0);
+  k.rowidx.assign(nnz, 0);
+  k.val.assign(nnz, 0.0);
+  size_t q = 0;
+  for (size_t j = 0; j < m; ++j) {
+    if (j < nd) {
+      k.rowidx[q] = j;
+      k.val[q++] = k.costs[j];
+    }
+    for (uint64_t e = k.e_colptr[j]; e < k.e_colptr[j + 1]; ++e) {
+      k.rowidx[q] = k.e_rowidx[e] + m;
+      k.val[q++] = k.e_val[e];
+    }
+    k.colptr[j + 1] = q;
+  }
+  for (size_t i = 0; i < p; ++i) {
+    deg[i + 1] += deg[i];
+    k.colptr[m + i + 1] = q + deg[i + 1];
+  }
+  std::vector<uint64_t> fill(deg.begin(), deg.end() - 1);
+  for (size_t j = 0; j < m; ++j)
+    for (uint64_t e = k.e_colptr[j]; e < k.e_colptr[j + 1]; ++e) {
+      const size_t at = q + fill[k.e_rowidx[e]]++;
+      k.rowidx[at] = j;
+      k.val[at] = k.e_val[e];
+    }
+}
+
+std::mutex g_csc_mutex;
+
 }  // namespace
+
+namespace tpl {
+// the CSC views of a container-loaded system are built on first use
+void kkt_ensure_csc(const tpl_kkt* kkt) {
+  std::lock_guard<std::mutex> lock(g_csc_mutex);
+  if (!kkt->lazy_csc) return;
+  tpl_kkt& k = *const_cast<tpl_kkt*>(kkt);
+  csc_from_incidence(k);
+  k.lazy_csc = false;
+}
+}  // namespace tpl
 
 extern "C" {
 
@@ -266,24 +382,17 @@ int tpl_load_kkt(const char* dmx_path, const char* qfc_path, tpl_kkt** out) {
   tpl_kkt* k = new tpl_kkt;
   std::vector<uint64_t> tails, heads;
   int rc = parse_dmx(dmx_path, *k, tails, heads);
+  const size_t m = k->num_arcs, p = k->num_nodes, n = m + p;
+  if (!rc) {  // E is assembled inside parse_dmx in the reference (data_loader.rs:139-155): its bounds error comes first
+    bool in_range = tails.size() <= m;  // the j-th `a` line is column j of E
+    for (size_t j = 0; j < tails.size() && in_range; ++j) in_range = tails[j] < p && heads[j] < p;
+    if (!in_range)
+      rc = fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  }
   if (!rc) rc = parse_qfc(qfc_path, k->num_arcs, k->costs);
   if (rc) {
     delete k;
     return rc;
-  }
-  const size_t m = k->num_arcs, p = k->num_nodes, n = m + p;
-  std::vector<Trip> t;
-  t.reserve(k->costs.size() + 2 * k->e_val.size());
-  for (size_t i = 0; i < k->costs.size(); ++i) t.push_back({i, i, k->costs[i]});
-  for (size_t c = 0; c < m; ++c)
-    for (uint64_t q = k->e_colptr[c]; q < k->e_colptr[c + 1]; ++q) {
-      t.push_back({k->e_rowidx[q] + m, c, k->e_val[q]});
-      t.push_back({c, k->e_rowidx[q] + m, k->e_val[q]});
-    }
-  if (!build_csc(n, n, t, k->colptr, k->rowidx, k->val)) {
-    delete k;
-    return fail(TPL_ERR_SPARSE_CONSTRUCTION,
-                "Internal error: Failed to construct the sparse matrix from triplets.");
   }
   // incidence view: exact iff every arc column of E came from exactly one `a` line (self-loops are fine:
   // their merged explicit 0 contributes nothing and the incidence kernels skip them)
@@ -292,10 +401,142 @@ int tpl_load_kkt(const char* dmx_path, const char* qfc_path, tpl_kkt** out) {
   k->head.assign(m, 0);
   k->d.assign(m, 0.0);
   for (size_t i = 0; i < k->costs.size(); ++i) k->d[i] = k->costs[i];
-  for (size_t j = 0; j < std::min(m, tails.size()); ++j) {
+  for (size_t j = 0; j < tails.size(); ++j) {
     k->tail[j] = uint32_t(tails[j]);
     k->head[j] = uint32_t(heads[j]);
   }
+  if (k->regular) {
+    k->lazy_csc = true;  // plain arc list: the CSC views come straight from it, on first use (csc_from_incidence)
+  } else {
+    // fewer `a` lines than announced (only a debug_assert in the reference, data_loader.rs:145-148): the general
+    // triplet route of SparseColMat::try_new_from_triplets
+    std::vector<Trip> t;
+    t.reserve(2 * tails.size());
+    for (size_t j = 0; j < tails.size(); ++j) {
+      t.push_back({tails[j], j, 1.0});
+      t.push_back({heads[j], j, -1.0});
+    }
+    bool ok = build_csc(p, m, t, k->e_colptr, k->e_rowidx, k->e_val);
+    t.clear();
+    t.reserve(k->costs.size() + 2 * k->e_val.size());
+    for (size_t i = 0; i < k->costs.size(); ++i) t.push_back({i, i, k->costs[i]});
+    for (size_t c = 0; ok && c < m; ++c)
+      for (uint64_t q = k->e_colptr[c]; q < k->e_colptr[c + 1]; ++q) {
+        t.push_back({k->e_rowidx[q] + m, c, k->e_val[q]});
+        t.push_back({c, k->e_rowidx[q] + m, k->e_val[q]});
+      }
+    ok = ok && build_csc(n, n, t, k->colptr, k->rowidx, k->val);
+    if (!ok) {
+      delete k;
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION,
+                  "Internal error: Failed to construct the sparse matrix from triplets.");
+    }
+  }
+  *out = k;
+  return TPL_OK;
+}
+
+
+int tpl_write_kkt_binary(const char* path, size_t nodes, size_t arcs, const uint32_t* tail, const uint32_t* head,
+                         const double* costs, size_t n_costs) {
+  tpl::clear_error();
+  if (!path || (arcs && (!tail || !head)) || (n_costs && !costs)) return fail(TPL_ERR_PANIC, "null argument");
+  if (n_costs > arcs) return fail(TPL_ERR_ARC_COUNT_MISMATCH, "Dimension mismatch: %zu costs for %zu arcs.", n_costs, arcs);
+  if (arcs > 0x7fffffffu || nodes > 0x7fffffffu)
+    return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: the container holds at most 2^31-1 arcs and nodes.");
+  for (size_t j = 0; j < arcs; ++j)
+    if (tail[j] >= nodes || head[j] >= nodes)
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  const size_t idx_bytes = pad8(4 * arcs);
+  BinHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, kMagic, 8);
+  h.version = 1;
+  h.nodes = nodes;
+  h.arcs = arcs;
+  h.n_costs = n_costs;
+  std::vector<unsigned char> idx(2 * idx_bytes, 0);
+  if (arcs) {
+    memcpy(idx.data(), tail, 4 * arcs);
+    memcpy(idx.data() + idx_bytes, head, 4 * arcs);
+  }
+  uint64_t c = word_hash(idx.data(), idx.size(), nodes * 0x10001ull + arcs);
+  c = word_hash(reinterpret_cast<const unsigned char*>(costs), 8 * n_costs, c);
+  h.checksum = c;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(TPL_ERR_IO, "I/O error: %s", strerror(errno));
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (idx.empty() || fwrite(idx.data(), 1, idx.size(), f) == idx.size()) &&
+            (!n_costs || fwrite(costs, 8, n_costs, f) == n_costs);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return fail(TPL_ERR_IO, "I/O error: short write to '%s'", path);
+  return TPL_OK;
+}
+
+int tpl_kkt_save_binary(const tpl_kkt* kkt, const char* path) {
+  tpl::clear_error();
+  if (!kkt || !path) return fail(TPL_ERR_PANIC, "null argument");
+  if (!kkt->regular)
+    return fail(TPL_ERR_SPARSE_CONSTRUCTION,
+                "Internal error: the instance is not a plain arc list; the container stores the incidence view only.");
+  return tpl_write_kkt_binary(path, kkt->num_nodes, kkt->num_arcs, kkt->tail.data(), kkt->head.data(),
+                              kkt->costs.data(), kkt->costs.size());
+}
+
+int tpl_load_kkt_binary(const char* path, tpl_kkt** out) {
+  tpl::clear_error();
+  if (!path || !out) return fail(TPL_ERR_PANIC, "null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(TPL_ERR_IO, "I/O error: %s", strerror(errno));
+  BinHeader h;
+  if (fread(&h, sizeof h, 1, f) != 1) {
+    fclose(f);
+    return fail(TPL_ERR_UNEXPECTED_EOF, "Format error: Unexpected end of file while reading data.");
+  }
+  if (memcmp(h.magic, kMagic, 8) != 0 || h.version != 1) {
+    fclose(f);
+    return fail(TPL_ERR_PROBLEM_LINE_MISSING, "Format error: not a TPLKKT1 container (bad magic or version).");
+  }
+  if (h.arcs > 0x7fffffffu || h.nodes > 0x7fffffffu || h.n_costs > h.arcs) {
+    fclose(f);
+    return fail(TPL_ERR_ARC_COUNT_MISMATCH, "Dimension mismatch: container header holds %llu arcs, %llu nodes, %llu costs.",
+                (unsigned long long)h.arcs, (unsigned long long)h.nodes, (unsigned long long)h.n_costs);
+  }
+  const size_t m = h.arcs, idx_bytes = pad8(4 * m);
+  tpl_kkt* k = new tpl_kkt;
+  k->num_nodes = h.nodes;
+  k->num_arcs = m;
+  std::vector<unsigned char> idx(2 * idx_bytes);
+  k->costs.resize(h.n_costs);
+  bool ok = (idx.empty() || fread(idx.data(), 1, idx.size(), f) == idx.size()) &&
+            (!h.n_costs || fread(k->costs.data(), 8, h.n_costs, f) == h.n_costs);
+  const bool trailing = ok && fgetc(f) != EOF;
+  fclose(f);
+  if (!ok || trailing) {
+    delete k;
+    return ok ? fail(TPL_ERR_ARC_COUNT_MISMATCH, "Dimension mismatch: container is longer than its header says.")
+              : fail(TPL_ERR_UNEXPECTED_EOF, "Format error: Unexpected end of file while reading data.");
+  }
+  uint64_t c = word_hash(idx.data(), idx.size(), h.nodes * 0x10001ull + h.arcs);
+  c = word_hash(reinterpret_cast<const unsigned char*>(k->costs.data()), 8 * k->costs.size(), c);
+  if (c != h.checksum) {
+    delete k;
+    return fail(TPL_ERR_IO, "I/O error: container checksum mismatch (corrupt file)");
+  }
+  k->tail.resize(m);
+  k->head.resize(m);
+  if (m) {
+    memcpy(k->tail.data(), idx.data(), 4 * m);
+    memcpy(k->head.data(), idx.data() + idx_bytes, 4 * m);
+  }
+  for (size_t j = 0; j < m; ++j)
+    if (k->tail[j] >= h.nodes || k->head[j] >= h.nodes) {
+      delete k;
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+    }
+  k->d.assign(m, 0.0);
+  std::copy(k->costs.begin(), k->costs.end(), k->d.begin());
+  k->regular = true;
+  k->lazy_csc = true;
   *out = k;
   return TPL_OK;
 }
@@ -304,10 +545,14 @@ void tpl_kkt_free(tpl_kkt* kkt) { delete kkt; }
 size_t tpl_kkt_num_nodes(const tpl_kkt* kkt) { return kkt->num_nodes; }
 size_t tpl_kkt_num_arcs(const tpl_kkt* kkt) { return kkt->num_arcs; }
 size_t tpl_kkt_num_costs(const tpl_kkt* kkt) { return kkt->costs.size(); }
-size_t tpl_kkt_nnz(const tpl_kkt* kkt) { return kkt->val.size(); }
+size_t tpl_kkt_nnz(const tpl_kkt* kkt) {
+  tpl::kkt_ensure_csc(kkt);
+  return kkt->val.size();
+}
 
 int tpl_kkt_csc(const tpl_kkt* kkt, size_t* n, size_t* nnz, const uint64_t** colptr, const uint64_t** rowidx,
                 const double** val) {
+  tpl::kkt_ensure_csc(kkt);
   if (n) *n = kkt->num_nodes + kkt->num_arcs;
   if (nnz) *nnz = kkt->val.size();
   if (colptr) *colptr = kkt->colptr.data();
