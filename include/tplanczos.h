@@ -143,6 +143,12 @@ int tpl_op_set_mode(tpl_op* op, int mode);
 /* Name of the kernel family a whole-pass solve through this handle runs: "cells", "chunks", "tiled", "gather", "csr" or
  * "sharded" (static string). */
 const char* tpl_op_kernel_shape(const tpl_op* op);
+/* Host-only: builds the tile entry lists of the tiled streaming kernels for `ctas` CTAs and tiles of `tile_arcs` arcs on
+ * `threads` host threads (0 = automatic) and checks them (every non-loop arc once on its head and once on its tail node
+ * per tile, a node's entries of a tile in one thread's slice).  stats = {check code (0 = consistent), tiles per CTA, list
+ * entries incl. padding, pieces, padding entries, longest per-thread list, hash of the lists, fold threads}. */
+int tpl_tiles_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, uint32_t tile_arcs, int threads,
+                   uint64_t stats[8]);
 /* Diagnostics (host only, no device needed): builds the 2-D cell partition the resident kernels would use on a grid
  * of `ctas` CTAs with `smem_limit` bytes of shared memory each and checks its tables on the host.
  * stats = {fits, tail blocks, head blocks, arc slots per cell, node lines, most entry rows, most node-sum groups,

@@ -19,6 +19,7 @@
 #include "tpl_kernels.cuh"
 #include "tpl_sharded.cuh"
 #include "tpl_tiles.cuh"
+#include "tpl_tiles_host.h"
 
 // ============================================================================ errors
 namespace tpl {
@@ -300,123 +301,6 @@ int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
   if (!h.ent_val.empty())
     if (int rc = dev_upload(op, &d.ent_val, h.ent_val)) return rc;
   return TPL_OK;
-}
-
-// ---------------------------------------------------------------- tiled node-sum lists (tpl_tiles.cuh)
-struct HostTiles {
-  uint32_t T = 0, ntile = 0;
-  std::vector<uint4> thdr;
-  std::vector<uint32_t> lent, piece;
-};
-
-void build_tiles(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int G, uint32_t T, HostTiles& h) {
-  const size_t A = (m + G - 1) / G;
-  const int B = tpl::kFoldThreads;  // the fold warps walk the lists
-  h.T = T;
-  h.ntile = (uint32_t)std::max<size_t>(1, (A + T - 1) / T);
-  const size_t ntiles = (size_t)G * h.ntile;
-  h.thdr.assign(ntiles, make_uint4(0, 0, 0, 0));
-  h.lent.clear();
-  h.lent.reserve(m + m / 4);
-  h.piece.clear();
-  std::vector<uint32_t> cnt(p + 1), e_node, e_code, sorted_node, sorted_code, order, cut(B + 1);
-  for (int c = 0; c < G; ++c) {
-    const size_t lo = std::min(m, A * (size_t)c), hi = std::min(m, lo + A);
-    for (uint32_t t = 0; t < h.ntile; ++t) {
-      const size_t tile_id = (size_t)c * h.ntile + t;
-      const size_t t0 = std::min(hi, lo + (size_t)t * T), t1 = std::min(hi, t0 + T);
-      const uint32_t q0 = (uint32_t)h.piece.size();
-      e_node.clear();
-      e_code.clear();
-      uint32_t npieces = 0;
-      for (size_t i = t0; i < t1;) {  // tail side: maximal runs of equal tail (self-loops contribute nothing)
-        if (tail[i] == head[i]) {
-          ++i;
-          continue;
-        }
-        size_t j = i;
-        while (j < t1 && tail[j] == tail[i] && tail[j] != head[j]) ++j;
-        const size_t len = j - i;
-        const size_t need = (len + tpl::kPieceMax - 1) / tpl::kPieceMax;
-        if (len >= tpl::kPieceMin && npieces + need <= tpl::kMaxPieces) {
-          for (size_t q = i; q < j; q += tpl::kPieceMax) {
-            const uint32_t l = (uint32_t)std::min<size_t>(tpl::kPieceMax, j - q);
-            h.piece.push_back((uint32_t)(q - t0) | ((l - 1) << 16));
-            e_node.push_back(tail[i]);
-            e_code.push_back(T + npieces);
-            ++npieces;
-          }
-        } else {
-          for (size_t q = i; q < j; ++q) {
-            e_node.push_back(tail[i]);
-            e_code.push_back((uint32_t)(q - t0));
-          }
-        }
-        i = j;
-      }
-      for (size_t i = t0; i < t1; ++i)  // head side
-        if (tail[i] != head[i]) {
-          e_node.push_back(head[i]);
-          e_code.push_back((uint32_t)(i - t0) | 0x4000u);
-        }
-      // stable counting sort by node: per node the tail entries come first (ascending index), then the head entries
-      const size_t ne = e_node.size();
-      std::fill(cnt.begin(), cnt.end(), 0u);
-      for (size_t e = 0; e < ne; ++e) ++cnt[e_node[e] + 1];
-      for (size_t u = 0; u < p; ++u) cnt[u + 1] += cnt[u];
-      sorted_node.resize(ne);
-      sorted_code.resize(ne);
-      order.assign(cnt.begin(), cnt.end() - 1);
-      for (size_t e = 0; e < ne; ++e) {
-        const uint32_t dst = order[e_node[e]]++;
-        sorted_node[dst] = e_node[e];
-        sorted_code[dst] = e_code[e];
-      }
-      // cut into B slices of nearly equal length at node boundaries (a node never straddles two threads)
-      cut[0] = 0;
-      for (int i = 1; i <= B; ++i) {
-        size_t want = std::max<size_t>(cut[i - 1], (ne * (size_t)i + B - 1) / B);
-        while (want < ne && want > 0 && sorted_node[want] == sorted_node[want - 1]) ++want;
-        cut[i] = (uint32_t)std::min(want, ne);
-      }
-      cut[B] = (uint32_t)ne;
-      uint32_t L = 0;
-      for (int i = 0; i < B; ++i) L = std::max(L, cut[i + 1] - cut[i]);
-      const size_t base = h.lent.size();
-      h.lent.resize(base + (size_t)L * B, tpl::kEntPad);
-      // The order in which a thread folds its entries is free (any fixed order is deterministic).  It is chosen so that the
-      // 16 threads of a half-warp, which execute fold step q together, read their tile values and their accumulators from
-      // different shared-memory banks whenever they can: a random order costs ~3 wavefronts per 8-byte access.
-      for (int i0 = 0; i0 < B; i0 += 16) {
-        std::vector<std::vector<uint32_t>> rem(16);
-        for (int l = 0; l < 16 && i0 + l < B; ++l)
-          for (uint32_t e = cut[i0 + l]; e < cut[i0 + l + 1]; ++e) rem[l].push_back(e);
-        for (uint32_t q = 0; q < L; ++q) {
-          uint32_t used_w[16] = {0}, used_a[16] = {0};
-          for (int l = 0; l < 16 && i0 + l < B; ++l) {
-            if (rem[l].empty()) continue;
-            size_t pick = 0;
-            uint32_t best = 0xffffffffu;
-            for (size_t x = 0; x < rem[l].size(); ++x) {
-              const uint32_t e = rem[l][x];
-              const uint32_t cost = used_w[(sorted_code[e] & 0x3fffu) & 15u] + used_a[sorted_node[e] & 15u];
-              if (cost < best) {
-                best = cost;
-                pick = x;
-                if (!cost) break;
-              }
-            }
-            const uint32_t e = rem[l][pick];
-            rem[l].erase(rem[l].begin() + (long)pick);
-            ++used_w[(sorted_code[e] & 0x3fffu) & 15u];
-            ++used_a[sorted_node[e] & 15u];
-            h.lent[base + (size_t)q * B + i0 + l] = (sorted_node[e] << 15) | sorted_code[e];
-          }
-        }
-      }
-      h.thdr[tile_id] = make_uint4((uint32_t)base, L, q0, (uint32_t)h.piece.size());
-    }
-  }
 }
 
 template <class K>
@@ -832,9 +716,9 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
     const size_t A = (m + op->G - 1) / op->G;
     if (T >= step) {
       T = (uint32_t)std::min<size_t>(T, std::max<size_t>(step, (A + step - 1) / step * step));
-      HostTiles ht;
-      build_tiles(m, p, tail, head, op->G, T, ht);
-      if (ht.lent.size() < 0xffffffffull) {
+      tpl::HostTiles ht;
+      tpl::build_tiles(m, p, tail, head, op->G, T, ht);
+      if (ht.T) {
         op->tile.T = ht.T;
         op->tile.ntile = ht.ntile;
         rc = dev_upload(op, &op->tile.thdr, ht.thdr);
@@ -922,6 +806,43 @@ int tpl_op_trace_read(tpl_op* op, uint64_t* out, size_t capacity, size_t* ctas, 
   CUDA_TRY(cudaStreamSynchronize(op->stream));
   CUDA_TRY(cudaMemcpy(out, op->trace_d, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemset(op->trace_d, 0, words * sizeof(unsigned long long)));
+  return TPL_OK;
+}
+
+int tpl_tiles_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, uint32_t tile_arcs, int threads,
+                   uint64_t stats[8]) {
+  tpl::clear_error();
+  if (!tail || !head || !stats) return fail(TPL_ERR_PANIC, "null argument");
+  if (ctas < 1 || tile_arcs < 1 || tile_arcs + tpl::kMaxPieces > 16384 || p >= (1u << 17))
+    return fail(TPL_ERR_PANIC, "tile plan: ctas >= 1, 1 <= tile_arcs <= %u and nodes < 2^17 are required", 16384 - tpl::kMaxPieces);
+  for (size_t j = 0; j < m; ++j)
+    if (tail[j] >= p || head[j] >= p)
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  tpl::HostTiles ht;
+  tpl::build_tiles(m, p, tail, head, ctas, tile_arcs, ht, threads);
+  std::fill(stats, stats + 8, 0ull);
+  if (!ht.T) return fail(TPL_ERR_PANIC, "tile plan: more than 2^32 list entries");
+  stats[0] = (uint64_t)tpl::check_tiles(m, p, tail, head, ctas, ht);
+  stats[1] = ht.ntile;
+  stats[2] = ht.lent.size();
+  stats[3] = ht.piece.size();
+  uint64_t pads = 0, lmax = 0, hsh = 1469598103934665603ull;
+  for (uint32_t e : ht.lent) {
+    pads += e == tpl::kEntPad;
+    hsh = (hsh ^ e) * 1099511628211ull;
+  }
+  for (uint32_t e : ht.piece) hsh = (hsh ^ e) * 1099511628211ull;
+  for (const uint4& x : ht.thdr) {
+    lmax = std::max<uint64_t>(lmax, x.y);
+    hsh = (hsh ^ x.x) * 1099511628211ull;
+    hsh = (hsh ^ x.y) * 1099511628211ull;
+    hsh = (hsh ^ x.z) * 1099511628211ull;
+    hsh = (hsh ^ x.w) * 1099511628211ull;
+  }
+  stats[4] = pads;
+  stats[5] = lmax;
+  stats[6] = hsh;
+  stats[7] = tpl::kFoldThreads;
   return TPL_OK;
 }
 
