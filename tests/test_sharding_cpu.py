@@ -101,8 +101,8 @@ def test_world2_gloo_sharded_product_matches_oracle():
 class _StubOp:
     """Stands in for a sharded LinOp on a box without GPUs: records the handles `connect_fabric` hands over."""
 
-    def __init__(self, rank, has_block=True):
-        self.rank, self.has_block, self.imported = rank, has_block, None
+    def __init__(self, rank, has_block=True, can_map=True):
+        self.rank, self.has_block, self.can_map, self.imported, self.mode = rank, has_block, can_map, None, 0
 
     def fabric_export(self):
         if not self.has_block:
@@ -110,19 +110,24 @@ class _StubOp:
         return bytes([self.rank]) * 64
 
     def fabric_import(self, handles):
+        if not self.can_map:
+            raise RuntimeError("CUDA error: peer mapping failed")
         self.imported = list(handles)
 
+    def set_mode(self, mode):
+        self.mode = mode
 
-def _fabric_worker(rank, world, port, q, broken_rank):
+
+def _fabric_worker(rank, world, port, q, broken_rank, unmappable_rank=-1):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        op = _StubOp(rank, has_block=rank != broken_rank)
+        op = _StubOp(rank, has_block=rank != broken_rank, can_map=rank != unmappable_rank)
         ok = sharding.connect_fabric(op, dist)
-        q.put((rank, ok, op.imported))
+        q.put((rank, ok, op.imported, op.mode))
     finally:
         dist.destroy_process_group()
 
@@ -143,8 +148,25 @@ def test_world2_gloo_fabric_rendezvous(broken_rank):
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
-    for rank, ok, imported in got:
+    for rank, ok, imported, mode in got:
         if broken_rank < 0:
-            assert ok and imported == [bytes([0]) * 64, bytes([1]) * 64]
+            assert ok and imported == [bytes([0]) * 64, bytes([1]) * 64] and mode == 0
         else:
             assert not ok and imported is None
+
+
+def test_world2_gloo_fabric_falls_back_collectively_when_one_rank_cannot_map():
+    """rank 1 cannot map its peer's block: both ranks leave the fused path (mode 1 = NCCL phase kernels), nobody hangs"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fabric_worker, args=(r, 2, port, q, -1, 1)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert [(ok, mode) for _, ok, _, mode in got] == [(False, 1), (False, 1)]

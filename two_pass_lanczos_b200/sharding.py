@@ -1,9 +1,11 @@
 """Arc-partitioned multi-GPU mode: host-side plumbing around `tpl_op_from_kkt_sharded`.
 
 Rank r of `world` owns the contiguous arc block `arc_range(m, r, world)` and a replica of the p node entries of every
-vector; a rank-local vector is `[arc slice | node part]`.  Collectives on the data path (one all-reduce of the p node
-sums + the alpha partial and one scalar all-reduce per Lanczos step) run inside the library over NCCL; this module only
-does the rendezvous (`torch.distributed`, any backend) and the slicing / gathering of vectors.
+vector; a rank-local vector is `[arc slice | node part]`.  The collectives on the data path (node-sum reduce-scatter,
+node-value all-gather, alpha / beta all-reduce per Lanczos step) run inside the library: fused into one persistent kernel
+per rank over peer memory once `connect_fabric` has mapped the ranks' exchange blocks, otherwise as NCCL calls between
+phase kernels.  This module only does the rendezvous (`torch.distributed`, any backend) and the slicing / gathering of
+vectors.
 """
 from __future__ import annotations
 
@@ -59,7 +61,9 @@ def broadcast_unique_id(dist, rank: int, make=unique_id) -> bytes:
 def connect_fabric(op: LinOp, dist) -> bool:
     """Exchanges the CUDA IPC handles of the ranks' exchange blocks over an initialised torch.distributed group and maps
     them: the passes of `op` then run as one persistent kernel per rank with the collectives fused in (peer-memory stores
-    over NVLink).  Returns False (and leaves the NCCL phase kernels in charge) when a rank has no exchange block."""
+    over NVLink).  Returns False (and leaves the NCCL phase kernels in charge on EVERY rank) when a rank has no exchange
+    block or cannot map a peer's (no peer access / CUDA IPC between the processes): the decision is collective, a rank never
+    runs fused against one that does not."""
     world = dist.get_world_size()
     try:
         mine = op.fabric_export()
@@ -69,8 +73,16 @@ def connect_fabric(op: LinOp, dist) -> bool:
     dist.all_gather_object(handles, mine)
     if any(h is None for h in handles):
         return False
-    op.fabric_import(handles)
-    dist.barrier()  # nobody starts a fused pass before every rank has mapped its peers
+    try:
+        op.fabric_import(handles)
+        mapped = True
+    except Exception:  # noqa: BLE001
+        mapped = False
+    flags = [None] * world
+    dist.all_gather_object(flags, mapped)  # also the barrier: nobody starts a fused pass before every rank has mapped its peers
+    if not all(flags):
+        op.set_mode(1)  # NCCL phase kernels on every rank, also on those whose own import succeeded
+        return False
     return True
 
 
