@@ -44,7 +44,10 @@ def main():
         print("arcs,nodes,n,k,gpus,variant,time_s,pass1_ms,pass2_ms,algorithmic_gb,gbs,frac_of_measured_hbm_peak,residual",
               flush=True)
     for m in args.arcs:
+        import time
+
         inst = datagen.gen_kkt(m, args.rho, 1, "aa")
+        t_build = time.time()
         if world > 1:
             ident = sharding.broadcast_unique_id(dist, rank)
             op = sharding.sharded_linop(inst.m, inst.p, inst.tail, inst.head, inst.d, rank, world, ident, device=local,
@@ -52,6 +55,8 @@ def main():
         else:
             op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d, device=local)
         op.set_stream(torch.cuda.current_stream().cuda_stream)
+        if rank == 0:
+            print(f"# {m} arcs: operator built in {time.time() - t_build:.2f} s ({op.kernel_shape()})", file=sys.stderr, flush=True)
         nloc = op.nrows()
         mloc = nloc - inst.p
         b = op.apply(torch.full((nloc,), 1.0 / np.sqrt(inst.n), dtype=torch.float64, device=dev))
