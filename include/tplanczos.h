@@ -217,6 +217,17 @@ int tpl_ftk_exp(const double* alphas, size_t na, const double* betas, size_t nb,
 int tpl_ftk_square(const double* alphas, size_t na, const double* betas, size_t nb, double* y,
                    size_t* y_len, void* user);
 
+/* SURVEY 8f N1 (no reference counterpart; the reference's benches re-solve for every k, src/bin/tradeoff.rs:262-290):
+ * residual norms ||b - A x_j||, j = 1..na, of the iterates x_j = ||b|| V_j T_j^{-1} e_1 from the coefficients of ONE
+ * pass 1 (progressive Givens QR of T, O(na), host).  betas[j-1] = beta_j must be given for every j that is wanted
+ * (res[j-1] = NaN beyond nb); exact in exact arithmetic, and in floating point up to the loss-of-orthogonality horizon. */
+int tpl_ftk_inv_residuals(const double* alphas, size_t na, const double* betas, size_t nb, double b_norm, double* res);
+/* A x = b with k chosen from those estimates: pass 1 runs k_max + 1 steps, k = the first j <= k_max whose estimate is
+ * <= rtol * ||b|| (else the j with the smallest one), y = T_k^{-1} e_1 ||b||, pass 2 regenerates only k vectors.
+ * *k_used and *res_est (estimate at k, absolute) are optional outputs. */
+int tpl_lanczos_two_pass_inv_adaptive(tpl_op* op, const double* b, size_t k_max, double rtol, double* x, size_t* k_used,
+                                      double* res_est);
+
 /* ------------------------------------------------------------------------------------
  * Multi-GPU (arc-partitioned KKT operator): rank r of `world` owns arcs
  * [arc_begin, arc_end) and a replica of the p node rows.  The communicator is NCCL; the caller

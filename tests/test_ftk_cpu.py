@@ -87,3 +87,58 @@ def test_empty():
     for name in ("tpl_ftk_inv", "tpl_ftk_exp", "tpl_ftk_square"):
         rc, y = call(name, [], [])
         assert rc == 0 and len(y) == 0  # `return Ok(Mat::zeros(0, 1))` in every reference closure
+
+
+# ------------------------------------------------------------------ residual estimates
+def _direct_residuals(al, be_full, b_norm):
+    """||b|| beta_j |e_j^T T_j^{-1} e_1| by dense solves"""
+    out = np.empty(len(al))
+    for j in range(1, len(al) + 1):
+        t = np.diag(al[:j]) + np.diag(be_full[: j - 1], 1) + np.diag(be_full[: j - 1], -1)
+        e1 = np.zeros(j)
+        e1[0] = 1.0
+        out[j - 1] = b_norm * be_full[j - 1] * abs(np.linalg.solve(t, e1)[-1])
+    return out
+
+
+@pytest.mark.parametrize("k,shift", [(1, 4.0), (2, 4.0), (40, 4.0), (200, 4.0), (60, 0.0), (120, 0.3)])
+def test_inv_residual_estimates_match_dense_solves(k, shift):
+    """definite (shift 4) and indefinite (shift 0 / 0.3: some T_j nearly singular) tridiagonals"""
+    from two_pass_lanczos_b200 import solvers
+
+    al, be = lanczos_like_tridiag(k + 1, 100 + k)
+    al, be = al[:k] + shift, be[:k]  # k betas: beta_k couples to v_{k+1}
+    est = solvers.inv_residual_estimates(al, be, b_norm=3.0)
+    ref = _direct_residuals(al, be, 3.0)
+    assert est.shape == (k,) and np.all(np.isfinite(est))
+    assert np.max(np.abs(est - ref) / ref) < 1e-8  # dense solves lose digits where T_j is nearly singular
+
+
+def test_inv_residual_estimates_follow_a_real_lanczos_run():
+    """on a well-conditioned diagonal operator the estimates equal the true residuals of the oracle's iterates"""
+    from oracle import oracle as orc
+    from two_pass_lanczos_b200 import solvers
+
+    n, k = 400, 30
+    eigs = np.linspace(1.0, 20.0, n)
+    a = orc.SparseColMat.try_new_from_triplets(n, n, np.arange(n), np.arange(n), eigs)
+    b = np.cos(np.arange(n)) + 2.0
+    dec = orc.lanczos_pass_one(a, b, k + 1)
+    est = solvers.inv_residual_estimates(dec.alphas[:k], dec.betas[:k], dec.b_norm)
+    for j in (1, 5, 17, 30):
+        xj = orc.lanczos_two_pass(a, b, j, npo.inv_tk_solver)
+        true = np.linalg.norm(b - eigs * xj)
+        assert abs(est[j - 1] - true) <= 1e-9 * np.linalg.norm(b) + 1e-6 * true, (j, est[j - 1], true)
+    assert est[-1] < 1e-3 * est[0]  # and they decay
+
+
+def test_inv_residual_estimates_edge_cases():
+    from two_pass_lanczos_b200 import solvers
+
+    assert solvers.inv_residual_estimates([], [], 1.0).shape == (0,)
+    est = solvers.inv_residual_estimates([2.0, 3.0, 4.0], [1.0, 1.0], 1.0)  # reference-style: steps - 1 betas
+    assert np.isfinite(est[0]) and np.isfinite(est[1]) and np.isnan(est[2])
+    est = solvers.inv_residual_estimates([0.0, 1.0], [1.0, 1.0], 1.0)  # T_1 = [0] is singular: no first iterate
+    assert np.isinf(est[0]) and np.isfinite(est[1])
+    est = solvers.inv_residual_estimates([2.0, 3.0], [0.0, 1.0], 5.0)  # exact breakdown after one step: x_1 is exact
+    assert est[0] == 0.0

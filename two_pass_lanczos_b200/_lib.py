@@ -67,6 +67,8 @@ SIGNATURES = {
     "tpl_lanczos_two_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, FTK_FN, C.c_void_p, C.c_void_p]),
     "tpl_ftk_inv": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, c_dp, c_szp, C.c_void_p]),
     "tpl_ftk_exp": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, c_dp, c_szp, C.c_void_p]),
+    "tpl_ftk_inv_residuals": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, C.c_double, c_dp]),
+    "tpl_lanczos_two_pass_inv_adaptive": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p, c_szp, c_dp]),
     "tpl_ftk_square": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, c_dp, c_szp, C.c_void_p]),
     "tpl_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "tpl_op_from_kkt_sharded": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, c_u32p, c_u32p, c_dp,

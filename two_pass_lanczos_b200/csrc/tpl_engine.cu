@@ -1451,6 +1451,51 @@ int tpl_lanczos_two_pass(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f
   return finish_x(op, x_dev, x);
 }
 
+// k chosen from the residual estimates of one pass 1
+int tpl_lanczos_two_pass_inv_adaptive(tpl_op* op, const double* b, size_t k_max, double rtol, double* x, size_t* k_used,
+                                      double* res_est) {
+  tpl::clear_error();
+  if (!op || !b || !x) return fail(TPL_ERR_PANIC, "null argument");
+  if (!(rtol >= 0.0)) return tpl::fail_input("rtol must be a non-negative number");
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  Decomp d;
+  if (k_max == 0) return fail(TPL_ERR_PANIC, "capacity overflow (k == 0; the reference panics in Vec::with_capacity(k - 1))");
+  // one step more than asked for: the decomposition holds beta_1 .. beta_{steps-1}, and the estimate of iterate j needs beta_j
+  if (int rc = run_pass_one(op, b_dev, k_max + 1, nullptr, 0, nullptr, nullptr, d)) return rc;
+  double* x_dev = is_device_ptr(x) ? x : op->x_d;
+  if (k_used) *k_used = 0;
+  if (res_est) *res_est = d.b_norm;
+  if (d.steps == 0) {
+    CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * op->n, op->stream));
+    return finish_x(op, x_dev, x);
+  }
+  const size_t cand = std::min(d.steps, k_max);  // iterates 1 .. cand are candidates
+  std::vector<double> betas(d.betas), res(cand);
+  if (betas.size() < cand) betas.push_back(0.0);  // pass 1 broke down at step `steps`: beta_steps <= 1000 eps, x_steps is exact
+  if (int rc = tpl_ftk_inv_residuals(d.alphas.data(), cand, betas.data(), betas.size(), d.b_norm, res.data())) return rc;
+  size_t k = 0;
+  for (size_t j = 0; j < cand; ++j) {
+    if (!(res[j] == res[j])) continue;  // NaN
+    if (res[j] <= rtol * d.b_norm) {
+      k = j + 1;
+      break;
+    }
+    if (k == 0 || res[j] < res[k - 1]) k = j + 1;
+  }
+  if (k == 0) return tpl::fail_solver("no Lanczos iterate exists (T_j singular for every j)");
+  std::vector<double> y(k);
+  size_t y_len = 0;
+  if (int rc = tpl_ftk_inv(d.alphas.data(), k, d.betas.data(), k - 1, y.data(), &y_len, nullptr)) return rc;
+  for (double& yi : y) yi = yi * d.b_norm;
+  if (int rc = run_pass_two(op, b_dev, d.alphas.data(), d.betas.data(), k, d.b_norm, y.data(), y.size(), x_dev, nullptr, 0))
+    return rc;
+  if (k_used) *k_used = k;
+  if (res_est) *res_est = res[k - 1];
+  return finish_x(op, x_dev, x);
+}
+
 // ---------------------------------------------------------------------------- multi-GPU
 int tpl_comm_unique_id(uint8_t id_out[128]) {
   tpl::clear_error();

@@ -128,6 +128,37 @@ int tpl_ftk_inv(const double* alphas, size_t na, const double* betas, size_t nb,
   return 0;
 }
 
+// residual norms of ALL Lanczos iterates from one pass-1 decomposition, without touching a vector.
+// x_j = ||b|| V_j T_j^{-1} e_1 has the residual b - A x_j = -||b|| beta_j (e_j^T T_j^{-1} e_1) v_{j+1}.  Its norm is read off a
+// progressive Givens QR of the (j+1) x j tridiagonal (Paige-Saunders): with rotations G_i = [[c_i, s_i], [-s_i, c_i]]
+// annihilating beta_i, ||r_j|| = ||b|| |s_1 ... s_j| / |c_j|  (c_j = 0: T_j is singular, the iterate does not exist -> inf).
+// Stable for indefinite T (KKT systems), unlike the pivot-free LU recurrence.
+int tpl_ftk_inv_residuals(const double* alphas, size_t na, const double* betas, size_t nb, double b_norm, double* res) {
+  if ((na && !alphas) || (nb && !betas) || (na && !res)) return tpl::fail(TPL_ERR_PANIC, "null argument");
+  double c_prev = 1.0, s_prev = 0.0, c_prev2 = 1.0;  // G_{j-1}, and the cosine of G_{j-2}
+  double phi = b_norm;                               // ||b|| |s_1 ... s_{j-1}|
+  for (size_t j = 0; j < na; ++j) {
+    if (j >= nb) {  // beta_j unknown: nothing can be said from here on
+      for (size_t i = j; i < na; ++i) res[i] = NAN;
+      break;
+    }
+    const double sup = j ? c_prev2 * betas[j - 1] : 0.0;        // row j-1 of column j after G_{j-2}
+    const double gamma = c_prev * alphas[j] - s_prev * sup;     // row j after G_{j-1}
+    const double rho = std::hypot(gamma, betas[j]);
+    if (rho == 0.0) {  // breakdown with a singular T_j: invariant subspace, no iterate
+      for (size_t i = j; i < na; ++i) res[i] = NAN;
+      break;
+    }
+    const double c = gamma / rho, s = betas[j] / rho;
+    res[j] = c == 0.0 ? INFINITY : phi * std::fabs(s) / std::fabs(c);
+    phi *= std::fabs(s);
+    c_prev2 = c_prev;
+    c_prev = c;
+    s_prev = s;
+  }
+  return 0;
+}
+
 int tpl_ftk_exp(const double* alphas, size_t na, const double* betas, size_t nb, double* y, size_t* y_len,
                 void*) {
   if (na == 0) {

@@ -76,3 +76,34 @@ def lanczos(operator: LinOp, b, k: int, f_tk_solver):
 def lanczos_two_pass(operator: LinOp, b, k: int, f_tk_solver):
     """Two-pass f(A)b (src/solvers.rs:133-175): O(n) memory, basis regenerated in pass 2."""
     return _solve("tpl_lanczos_two_pass", operator, b, k, f_tk_solver)
+
+
+def inv_residual_estimates(alphas, betas, b_norm: float = 1.0):
+    """||b - A x_j||, j = 1..len(alphas), of the iterates x_j = ||b|| V_j T_j^{-1} e_1, from the coefficients of one pass 1
+    (`tpl_ftk_inv_residuals`).  `betas[j-1]` = beta_j; entries whose beta is not given come back NaN (a
+    reference-style decomposition holds steps - 1 betas, so its last estimate is NaN)."""
+    al = np.ascontiguousarray(alphas, dtype=np.float64)
+    be = np.ascontiguousarray(betas, dtype=np.float64)
+    res = np.empty(len(al))
+    dp = _lib.c_dp
+    _lib.check(_lib.load().tpl_ftk_inv_residuals((al if len(al) else np.zeros(1)).ctypes.data_as(dp), len(al),
+                                                 (be if len(be) else np.zeros(1)).ctypes.data_as(dp), len(be), b_norm,
+                                                 (res if len(res) else np.zeros(1)).ctypes.data_as(dp)))
+    return res
+
+
+def lanczos_two_pass_inv_adaptive(operator: LinOp, b, k_max: int, rtol: float):
+    """A x = b with the number of steps chosen from the residual estimates of ONE pass 1: returns
+    (x, k_used, residual_estimate).  k_used is the first j <= k_max whose estimate is <= rtol ||b|| (else the best j);
+    pass 2 regenerates only k_used basis vectors."""
+    bp, keep, is_torch = _vec_ptr(b)
+    n = operator.nrows()
+    if is_torch and keep.is_cuda:
+        x = keep.new_empty(n)
+        xptr = C.c_void_p(x.data_ptr())
+    else:
+        x = np.empty(n)
+        xptr = C.c_void_p(x.ctypes.data)
+    k_used, est = C.c_size_t(), C.c_double()
+    _lib.check(_lib.load().tpl_lanczos_two_pass_inv_adaptive(operator._h, bp, k_max, rtol, xptr, C.byref(k_used), C.byref(est)))
+    return x, k_used.value, est.value
