@@ -28,7 +28,7 @@ constexpr uint32_t kPieceMax = 256;    // longest piece (longer runs are split a
 constexpr uint32_t kMaxPieces = 512;   // per tile (shared-memory slots after the T arc values); T + kMaxPieces <= 16384
 constexpr int kUnroll = 4;             // arcs per thread per batch of the streaming loops
 constexpr int kUnroll2 = 2;            // pass 2: six loads per arc, two batches of registers in flight
-constexpr int kUnrollB = 4;            // pass 1 phase B: two loads per arc
+constexpr int kUnrollB = 8;            // pass 1 phase B: two loads per arc
 constexpr int kPre = 16;               // list entries per fold thread requested together
 constexpr int kStreamWarps = 8;        // warps 0..7 stream a tile from HBM while warps 8..15 fold the previous one into the node sums
                                        // (10 / 6 is better at 5M arcs, worse at 50M; 12 / 4 is worse everywhere)
@@ -128,8 +128,79 @@ constexpr int kBarFull = 1, kBarEmpty = 3, kBarFold = 5;
 __device__ __forceinline__ void bar_sync_n(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive_n(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// Fold warps: adds the node sums of the tile held in buffer `wt` into s.acc.
-__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, SmArr wt, const TileHdr& h) {
+// List and piece words of the fold are static data: a fold thread requests them one batch AHEAD of their use -- the next
+// kPre entries (of this tile, or the first ones of the next tile) before it folds the current batch, the next tile's piece
+// words while it folds this tile -- so that no global-load latency sits between two hand-offs of the stream / fold pipeline
+// (before: ~3 dependent piece loads + L / kPre list round trips per tile, about a third of the fold's time at 50M arcs).
+struct FoldRegs {
+  uint32_t ent[kPre];  // the batch to fold next
+  uint32_t pc[2];      // piece words of this warp: lane l holds pieces fwarp + kFoldWarps * (l + 32 * i)
+};
+static_assert(kMaxPieces <= 2 * 32 * kFoldWarps, "two piece words per lane cover a tile");
+__device__ __forceinline__ void fold_request(const TileOp& to, const TileHdr& h, uint32_t q0, uint32_t (&ent)[kPre]) {
+  const uint32_t* mine = to.lent + h.e0 + (threadIdx.x - kStreamThreads);
+#pragma unroll
+  for (int q = 0; q < kPre; ++q) ent[q] = q0 + q < h.L ? __ldg(mine + (size_t)(q0 + q) * kFoldThreads) : kEntPad;
+}
+__device__ __forceinline__ void piece_request(const TileOp& to, const TileHdr& h, uint32_t (&pc)[2]) {
+  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t q = h.q0 + fwarp + kFoldWarps * (lane + 32 * i);
+    pc[i] = q < h.q1 ? __ldg(to.piece + q) : 0u;
+  }
+}
+
+// Fold warps: adds the node sums of the tile held in buffer `wt` into s.acc.  `fr` holds the tile's first list batch and
+// its piece words on entry, those of tile `next` (if there is one) on return.
+__device__ __forceinline__ void tile_node_sums(const TileOp& to, const TileSmem& s, SmArr wt, const TileHdr& h, const TileHdr& next,
+                                               bool has_next, FoldRegs& fr) {
+  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
+  if (h.q1 > h.q0) {
+    uint32_t i = 0;
+    for (uint32_t q = h.q0 + fwarp; q < h.q1; q += kFoldWarps, ++i) {
+      const uint32_t pc = __shfl_sync(0xffffffffu, i < 32 ? fr.pc[0] : fr.pc[1], i & 31);
+      const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
+      const SmArr w{wt.a + first * 8u};
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent lane-strided chains, combined in a fixed order
+      for (uint32_t e = lane; e < len; e += 128) {
+        const double x0 = sm_ld(w, e);
+        const double x1 = e + 32 < len ? sm_ld(w, e + 32) : 0.0;
+        const double x2 = e + 64 < len ? sm_ld(w, e + 64) : 0.0;
+        const double x3 = e + 96 < len ? sm_ld(w, e + 96) : 0.0;
+        a0 = __dadd_rn(a0, x0);
+        a1 = __dadd_rn(a1, x1);
+        a2 = __dadd_rn(a2, x2);
+        a3 = __dadd_rn(a3, x3);
+      }
+      const double a = warp_sum(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)));
+      if (lane == 0) sm_st(wt, to.T + (q - h.q0), a);
+    }
+    bar_sync_n(kBarFold, kFoldThreads);
+  }
+  if (has_next) piece_request(to, next, fr.pc);
+  uint32_t q0 = 0;
+  do {  // (runs once for an empty list: the first batch of the next tile still has to be requested)
+    uint32_t nxt[kPre];
+    if (q0 + kPre < h.L) {
+      fold_request(to, h, q0 + kPre, nxt);
+    } else if (has_next) {
+      fold_request(to, next, 0, nxt);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) nxt[q] = kEntPad;
+    }
+#pragma unroll
+    for (int q = 0; q < kPre; ++q)
+      if (fr.ent[q] != kEntPad) fold_entry(fr.ent[q], wt, s.acc);
+#pragma unroll
+    for (int q = 0; q < kPre; ++q) fr.ent[q] = nxt[q];
+    q0 += kPre;
+  } while (q0 < h.L);
+}
+
+// Fold warps, plain form (pass 2): words requested when they are needed.
+__device__ __forceinline__ void tile_node_sums_plain(const TileOp& to, const TileSmem& s, SmArr wt, const TileHdr& h) {
   const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
   if (h.q1 > h.q0) {
     for (uint32_t q = h.q0 + fwarp; q < h.q1; q += kFoldWarps) {
@@ -322,6 +393,70 @@ __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, c
   if (c.alo < c.ahi) ntiles = min(to.ntile, (c.ahi - c.alo + to.T - 1) / to.T);
   const bool timed = tr != nullptr && tr->buf != nullptr;
   if (threadIdx.x < kStreamThreads) {
+    long long c_stream = 0, c_wait = 0, t_a = 0;
+    // Flat loop over the batches of the chunk with two register sets used alternately (no copies): batch bi + 1 is requested
+    // before batch bi is consumed, across tile boundaries.
+    const uint32_t nb = c.alo < c.ahi ? (c.ahi - c.alo + BATCH - 1) / BATCH : 0, bpt = to.T / BATCH;
+    uint32_t t = 0, in_tile = 0;  // tile of the current batch, its position inside the tile
+    auto step = [&](uint32_t bi, REGS& mine, REGS& other) __attribute__((always_inline)) {
+      const uint32_t i0 = c.alo + bi * BATCH;
+      if (in_tile == 0 && t >= 2) {  // the fold of tile t - 2 has left this buffer
+        if (timed) t_a = clock64();
+        bar_sync_n(kBarEmpty + (t & 1u), kBlock);
+        if (timed) c_wait += clock64() - t_a;
+      }
+      if (bi + 1 < nb) issue(i0 + BATCH, other);
+      consume(i0, c.alo + t * to.T, mine, SmArr{s.wt.a + (t & 1u) * s.wt_stride});
+      if (++in_tile == bpt || bi + 1 == nb) {
+        bar_arrive_n(kBarFull + (t & 1u), kBlock);
+        ++t;
+        in_tile = 0;
+      }
+    };
+    if (timed) c_stream = -clock64();
+    REGS ra, rb;
+    if (nb) issue(c.alo, ra);
+    for (uint32_t bi = 0; bi < nb; bi += 2) {
+      step(bi, ra, rb);
+      if (bi + 1 < nb) step(bi + 1, rb, ra);
+    }
+    // drain: every arrival of the fold warps is matched by a wait, so that the barriers are clean for the next call
+    for (uint32_t u = ntiles > 2 ? ntiles - 2 : 0; u < ntiles; ++u) bar_sync_n(kBarEmpty + (u & 1u), kBlock);
+    if (timed) {
+      trace_value(*tr, tr_step, 16, c_stream + clock64());
+      trace_value(*tr, tr_step, 17, c_wait);
+    }
+  } else {
+    TileHdr hdr = tile_hdr(to, tile0);
+    FoldRegs fr;
+    if (ntiles) {  // the first tile's list batch and piece words are on their way while the stream warps fill the buffer
+      fold_request(to, hdr, 0, fr.ent);
+      piece_request(to, hdr, fr.pc);
+    }
+    for (uint32_t t = 0; t < ntiles; ++t) {
+      TileHdr next = hdr;
+      if (t + 1 < ntiles) next = tile_hdr(to, tile0 + t + 1);
+      const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
+      bar_sync_n(kBarFull + (t & 1u), kBlock);
+      tile_node_sums(to, s, wt, hdr, next, t + 1 < ntiles, fr);
+      bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
+      hdr = next;
+    }
+  }
+  __syncthreads();
+}
+
+// The first form of the tile loop, kept for PASS 2: one register set copied per batch, conditional loads, fold words requested
+// when needed.  Measured on B200 (k = 500): with the loop above pass 2 is 7-10 % slower at 20M / 50M arcs (its six input
+// streams already keep the memory system busy; requests issued ahead by the fold warps delay them), pass 1 9-12 % faster.
+template <int BATCH, class REGS, class ISSUE, class CONSUME>
+__device__ __forceinline__ void tile_loop_plain(const TileOp& to, const TileSmem& s, const TileCtx& c, ISSUE issue, CONSUME consume,
+                                          const Trace* tr = nullptr, int tr_step = -1) {
+  const uint32_t tile0 = blockIdx.x * to.ntile;
+  uint32_t ntiles = 0;
+  if (c.alo < c.ahi) ntiles = min(to.ntile, (c.ahi - c.alo + to.T - 1) / to.T);
+  const bool timed = tr != nullptr && tr->buf != nullptr;
+  if (threadIdx.x < kStreamThreads) {
     long long c_stream = 0, c_wait = 0, t_a = 0, t_b = 0;
     REGS cur;
     if (ntiles) issue(c.alo, cur);
@@ -353,7 +488,7 @@ __device__ __forceinline__ void tile_loop(const TileOp& to, const TileSmem& s, c
       if (t + 1 < ntiles) next = tile_hdr(to, tile0 + t + 1);
       const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
       bar_sync_n(kBarFull + (t & 1u), kBlock);
-      tile_node_sums(to, s, wt, hdr);
+      tile_node_sums_plain(to, s, wt, hdr);
       bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
       hdr = next;
     }
@@ -371,14 +506,14 @@ __device__ __forceinline__ void tile_sums_of(const IncidenceOp& op, const TileOp
   };
   tile_loop<kUnroll * kStreamThreads, R>(
       to, s, c,
-      [&](uint32_t i0, R& r) {
+      [&](uint32_t i0, R& r) __attribute__((always_inline)) {
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
           const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
-          r.x[q] = i < c.ahi ? __ldg(X + i) : 0.0;
+          r.x[q] = __ldg(X + min(i, c.ahi - 1));
         }
       },
-      [&](uint32_t i0, uint32_t t0, const R& r, SmArr wt) {
+      [&](uint32_t i0, uint32_t t0, const R& r, SmArr wt) __attribute__((always_inline)) {
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
           const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
@@ -467,14 +602,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
         uint32_t tl[kUnroll], hd[kUnroll];
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
-          const uint32_t i = base + q * kBlock + threadIdx.x;
-          if (i < c.ahi) {
-            wc[q] = __ldcg(Wc + i);
-            wp[q] = __ldcg(Wp + i);
-            dd[q] = __ldg(op.d + i);
-            tl[q] = __ldg(op.tail + i);
-            hd[q] = __ldg(op.head + i);
-          }
+          const uint32_t i = min(base + q * kBlock + threadIdx.x, c.ahi - 1);  // (unconditional: see phase B)
+          wc[q] = __ldcg(Wc + i);
+          wp[q] = __ldcg(Wp + i);
+          dd[q] = __ldg(op.d + i);
+          tl[q] = __ldg(op.tail + i);
+          hd[q] = __ldg(op.head + i);
         }
 #pragma unroll
         for (int q = 0; q < kUnroll; ++q) {
@@ -509,17 +642,17 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_tiled_kernel(const IncidenceO
       };
       tile_loop<kUnrollB * kStreamThreads, RB>(
           to, s, c,
-          [&](uint32_t i0, RB& r) {
+          [&](uint32_t i0, RB& r) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < kUnrollB; ++q) {
-              const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
-              if (i < c.ahi) {
-                r.wn[q] = __ldcg(Wn + i);
-                r.wc[q] = __ldcg(Wc + i);
-              }
+              // (unconditional: a conditionally written register stays live around the whole loop; the batch past the end of
+              // the chunk re-reads its last arc and is discarded by consume)
+              const uint32_t i = min(i0 + q * kStreamThreads + threadIdx.x, c.ahi - 1);
+              r.wn[q] = __ldcg(Wn + i);
+              r.wc[q] = __ldcg(Wc + i);
             }
           },
-          [&](uint32_t i0, uint32_t t0, const RB& r, SmArr wt) {
+          [&](uint32_t i0, uint32_t t0, const RB& r, SmArr wt) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < kUnrollB; ++q) {
               const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
@@ -657,9 +790,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
       double vc[kUnroll2], vp[kUnroll2], dd[kUnroll2], xx[kUnroll2];
       uint32_t tl[kUnroll2], hd[kUnroll2];
     };
-    tile_loop<kUnroll2 * kStreamThreads, R2>(
+    tile_loop_plain<kUnroll2 * kStreamThreads, R2>(
         to, s, c,
-        [&](uint32_t i0, R2& r) {
+        [&](uint32_t i0, R2& r) __attribute__((always_inline)) {
 #pragma unroll
           for (int q = 0; q < kUnroll2; ++q) {
             const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
@@ -673,7 +806,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_tiled_kernel(const IncidenceO
             }
           }
         },
-        [&](uint32_t i0, uint32_t t0, const R2& r, SmArr wt) {
+        [&](uint32_t i0, uint32_t t0, const R2& r, SmArr wt) __attribute__((always_inline)) {
 #pragma unroll
           for (int q = 0; q < kUnroll2; ++q) {
             const uint32_t i = i0 + q * kStreamThreads + threadIdx.x;
