@@ -132,6 +132,20 @@ def algorithmic_bytes(n, bmat, k):
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def cpu_model():
+    """CPU model and core count of the box (stated next to every CPU number)."""
+    name = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    name = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return f"{name} ({os.cpu_count()} logical cores, 1 used)"
+
+
 def cpu_two_pass_seconds(inst, k, repeats=1):
     """Times the CPU oracle (oracle/lanczos_oracle.cpp: CSC scatter matvec, 8-byte indices, unfused sweeps, one
     thread -- the reference runs faer with Par::Seq) on the same instance and right-hand side."""
@@ -178,7 +192,7 @@ def run_reference(args, rank, world):
         "config": {"workload": f"netgen-shaped KKT {args.arcs} arcs rho={args.rho} n={inst.n}, lanczos_two_pass "
                                f"f=inv k={args.k}", "note": "reference = CPU oracle port (Rust/faer reference "
                                "cannot be built here: no cargo/rustc, faer un-vendored); single thread like Par::Seq"},
-        "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": "port", "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "published_reference_ms_other_hw": REF_PUBLISHED_S * 1e3,
@@ -390,7 +404,7 @@ def run_b200(args, rank, world, local_rank):
             line["large_instance"] = large
         if not args.no_cpu_baseline and world == 1:
             t_cpu = cpu_two_pass_seconds(inst, k)
-            line["cpu_baseline"] = {"value": t_cpu * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+            line["cpu_baseline"] = {"value": t_cpu * 1e3, "unit": "ms", "cores": 1, "kind": "port", "cpu": cpu_model(),
                                     "sample": f"full workload (k={k}), one cold run, single thread (Par::Seq)"}
         print(json.dumps(line), flush=True)
     if world > 1:
