@@ -264,6 +264,12 @@ def test_binary_container_error_branches(tmp_path):
     with pytest.raises(DataLoaderError) as e:
         data_loader.load_kkt_host_binary(str(tmp_path / "missing.tplkkt"))
     assert e.value.kind == "Io"
+    # a header announcing 2^31 - 1 arcs on a 100-byte file is refused before anything is allocated
+    import struct
+
+    huge = raw[:16] + struct.pack("<QQQ", 3, 2**31 - 1, 0) + raw[40:]
+    assert load(huge) == "UnexpectedEof"
+    assert load(raw[:16] + struct.pack("<QQQ", 3, 2**31, 0) + raw[40:]) == "ArcCountMismatch"  # beyond the 32-bit index range
     with pytest.raises(DataLoaderError) as e:  # node id out of range is refused at write time, like the triplet check
         data_loader.write_kkt_binary(str(tmp_path / "o.tplkkt"), 3, [0, 3], [1, 2])
     assert e.value.kind == "SparseMatrixConstructionError"

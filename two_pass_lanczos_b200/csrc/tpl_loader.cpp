@@ -502,6 +502,22 @@ int tpl_load_kkt_binary(const char* path, tpl_kkt** out) {
                 (unsigned long long)h.arcs, (unsigned long long)h.nodes, (unsigned long long)h.n_costs);
   }
   const size_t m = h.arcs, idx_bytes = pad8(4 * m);
+  {  // the file must be exactly as long as the header says, checked before anything of that size is allocated
+    const long at = ftell(f);
+    long size = -1;
+    if (at >= 0 && fseek(f, 0, SEEK_END) == 0) size = ftell(f);
+    const unsigned long long want = sizeof(BinHeader) + 2ull * idx_bytes + 8ull * h.n_costs;
+    if (at < 0 || size < 0 || fseek(f, at, SEEK_SET) != 0) {
+      fclose(f);
+      return fail(TPL_ERR_IO, "I/O error: cannot determine the size of '%s'", path);
+    }
+    if ((unsigned long long)size != want) {
+      fclose(f);
+      return (unsigned long long)size < want
+                 ? fail(TPL_ERR_UNEXPECTED_EOF, "Format error: Unexpected end of file while reading data.")
+                 : fail(TPL_ERR_ARC_COUNT_MISMATCH, "Dimension mismatch: container is longer than its header says.");
+    }
+  }
   tpl_kkt* k = new tpl_kkt;
   k->num_nodes = h.nodes;
   k->num_arcs = m;
