@@ -17,6 +17,17 @@ def seeded_b(n: int, seed: int = 42) -> np.ndarray:
     return np.random.default_rng(seed).random(n)
 
 
+def reference_b(n: int, seed: int = 42) -> np.ndarray:
+    """b of the reference's tests restated: `StdRng::seed_from_u64(42)` uniforms (two_pass_lanczos_b200/stdrng.py; ChaCha12
+    core pinned on published keystreams, seed expansion / float conversion unpinned)."""
+    from two_pass_lanczos_b200 import stdrng
+
+    return stdrng.std_rng_uniform(seed, n)
+
+
+B_GENERATORS = {"numpy": seeded_b, "stdrng": reference_b}
+
+
 def rhs_from_const(apply, n: int) -> np.ndarray:
     """b = A * (1/sqrt(n)) 1   (src/bin/tradeoff.rs:234-236)"""
     return apply(np.full(n, 1.0 / np.sqrt(n)))

@@ -61,14 +61,14 @@ def test_doctest():  # src/lib.rs:35-84
 @pytest.mark.parametrize("fname,f,tol", [("inv", lambda z: 1.0 / z, APPROX_TOLERANCE),
                                          ("exp", np.exp, APPROX_TOLERANCE),
                                          ("square", lambda z: z * z, EXACT_TOLERANCE)])
-@pytest.mark.parametrize("closure", ["python", "native"])
-def test_correctness_rs(solver, fname, f, tol, closure):  # tests/correctness.rs:165-325
+@pytest.mark.parametrize("closure,bgen", [("python", "numpy"), ("native", "numpy"), ("native", "stdrng")])
+def test_correctness_rs(solver, fname, f, tol, closure, bgen):  # tests/correctness.rs:165-325
     n, k = 100, 30
     eigs = np.arange(1, n + 1.0)
     import scipy.sparse as sp
 
     a = tpl.LinOp.from_scipy(sp.diags(eigs))
-    b = helpers.seeded_b(n)
+    b = helpers.B_GENERATORS[bgen](n)
     x_true = f(eigs) * b
     ftk = helpers.FTK[fname] if closure == "python" else fname
     x = getattr(tpl, solver)(a, b, k, ftk)

@@ -74,11 +74,12 @@ def test_doctest_one_pass_vs_two_pass():  # src/lib.rs:35-84
 @pytest.mark.parametrize("fname,f,tol", [("inv", lambda z: 1.0 / z, APPROX_TOLERANCE),
                                          ("exp", np.exp, APPROX_TOLERANCE),
                                          ("square", lambda z: z * z, EXACT_TOLERANCE)])
-def test_diagonal_ground_truth(solver, fname, f, tol):  # tests/correctness.rs:165-325
+@pytest.mark.parametrize("bgen", ["numpy", "stdrng"])
+def test_diagonal_ground_truth(solver, fname, f, tol, bgen):  # tests/correctness.rs:165-325
     n, k = 100, 30
     eigs = np.arange(1, n + 1.0)
     a = orc.SparseColMat.try_new_from_triplets(n, n, np.arange(n), np.arange(n), eigs)
-    b = helpers.seeded_b(n)
+    b = helpers.B_GENERATORS[bgen](n)
     x_true = f(eigs) * b
     x = solver(a, b, k, helpers.FTK[fname])
     assert helpers.rel(x, x_true) < tol
