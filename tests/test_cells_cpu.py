@@ -72,3 +72,29 @@ def test_too_large_for_shared_memory_is_reported():
     assert st["fits"] == 0
     inst = datagen.gen_kkt(800_000, 3, 1, "wc")
     assert plan(inst.m, inst.p, inst.tail, inst.head)["fits"] == 0
+
+
+def test_random_multigraphs_property():
+    """hypothesis: whenever the planner says an instance fits, its tables are consistent (code 0) -- any multigraph with
+    self-loops, parallel arcs, isolated nodes and unsorted tails, any grid size"""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=80, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(st.integers(1, 400), st.integers(1, 6000), st.sampled_from([1, 4, 16, 36, 100, 148]), st.integers(0, 2**31),
+           st.sampled_from(["uniform", "sorted", "hub"]))
+    def run(p, m, ctas, seed, shape):
+        rng = np.random.default_rng(seed)
+        tail = rng.integers(0, p, m)
+        head = rng.integers(0, p, m)
+        if shape == "sorted":
+            tail = np.sort(tail)
+        elif shape == "hub":
+            tail[: m // 2] = tail[0]
+            head[m // 2:] = head[-1]
+        st_ = plan(m, p, tail, head, ctas=ctas)
+        if st_["fits"]:
+            assert st_["code"] == 0, (p, m, ctas, seed, shape, st_)
+            assert st_["smem"] <= SMEM and st_["GR"] * st_["GC"] <= ctas
+
+    run()

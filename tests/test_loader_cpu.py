@@ -291,3 +291,27 @@ def test_cost_spellings_round_like_the_reference(tmp_path):
     want = np.array([float(v) for v in vals])
     assert np.array_equal(d, want, equal_nan=True) and np.array_equal(np.signbit(d), np.signbit(want))
     assert np.array_equal(host.csc()[3], ref.a.csc()[2], equal_nan=True)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_direct_csc_construction_matches_the_oracles_triplet_route(tmp_path, seed):
+    """random multigraph with self-loops, parallel arcs, isolated nodes and a short D: the CSC the product builds straight
+    from the arc list equals the oracle's `try_new_from_triplets` restatement entry for entry"""
+    rng = np.random.default_rng(seed)
+    p, m = 60, 2500
+    tail = rng.integers(1, p + 1, m)
+    head = rng.integers(1, p + 1, m)
+    head[::97] = tail[::97]  # self-loops
+    n_costs = m - 7 * seed
+    dmx = _write(tmp_path, "r.dmx", f"p min {p} {m}\n" + "".join(f"a {u} {v}\n" for u, v in zip(tail, head)))
+    costs = rng.uniform(-5, 5, n_costs)
+    qfc = _write(tmp_path, "r.qfc", f"{m}\n" + "0\n" * m + "".join(repr(float(c)) + "\n" for c in costs))
+    host = data_loader.load_kkt_host(dmx, qfc)
+    ref = orc.load_kkt_system(dmx, qfc)
+    n, colptr, rowidx, val = host.csc()
+    rc, rr, rv = ref.a.csc()
+    assert n == m + p and host.num_costs == n_costs
+    assert np.array_equal(colptr, rc) and np.array_equal(rowidx, rr) and np.array_equal(val, rv)
+    path = str(tmp_path / "r.tplkkt")
+    host.save_binary(path)
+    _same_system(data_loader.load_kkt_host_binary(path), host)

@@ -70,3 +70,27 @@ def test_tile_plan_edge_cases_and_errors():
         plan(2, 2, [0, 2], [1, 1])                                       # node id out of range
     with pytest.raises(LanczosError):
         plan(2, 2, [0, 1], [1, 0], tile=16384)                           # tile + piece slots exceed the 14-bit index
+
+
+def test_tile_lists_on_random_multigraphs_property():
+    """hypothesis: any multigraph (self-loops, parallel arcs, isolated nodes, unsorted tails), any grid, any tile size"""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(st.integers(1, 300), st.integers(0, 4000), st.integers(1, 40), st.sampled_from([64, 256, 1024, 4096]),
+           st.integers(0, 2**31), st.sampled_from(["uniform", "sorted", "hub"]))
+    def run(p, m, ctas, tile, seed, shape):
+        rng = np.random.default_rng(seed)
+        tail = rng.integers(0, p, m)
+        head = rng.integers(0, p, m)
+        if shape == "sorted":
+            tail = np.sort(tail)
+        elif shape == "hub" and m:
+            tail[: m // 2] = tail[0]  # one long same-tail run -> pieces, cut at tile and piece boundaries
+        st_ = plan(m, p, tail, head, ctas=ctas, tile=tile, threads=1 + seed % 3)
+        assert st_["code"] == 0, (p, m, ctas, tile, seed, shape, st_)
+        loops = int(np.sum(tail == head))
+        assert st_["entries"] - st_["pads"] <= 2 * (m - loops)
+
+    run()
