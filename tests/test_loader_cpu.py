@@ -315,3 +315,30 @@ def test_direct_csc_construction_matches_the_oracles_triplet_route(tmp_path, see
     path = str(tmp_path / "r.tplkkt")
     host.save_binary(path)
     _same_system(data_loader.load_kkt_host_binary(path), host)
+
+
+SPELLINGS = ["1", "2.5", "-3", "1e2", ".5", "+7.", "0", "1.e5", "1e+5", "1e-5", "-.5", "00012", "-0", "1E-400", "1e400", "-1e400",
+             "4.9e-324", "123456789012345678901234567890.5", "inf", "x", " 1", "1 ", "", "nan", ".e5", "1e", "--1", "1-2", "-", ".",
+             "e5", "1.5.2", "1e5e5", "1e-", "+-1", "-+1", "1_0", "0x10", "1f", "infinity", "-INF", "NaN", "nan(1)", "1e5.0", "+.5",
+             "+", "+e5", "1e+", "٣", "1,5", "1e٣"]
+
+
+@pytest.mark.parametrize("spelling", SPELLINGS)
+def test_cost_grammar_matches_the_oracle(tmp_path, spelling):
+    """every cost spelling takes the same branch in the product loader (fast decimal path or the validating one) and in the
+    oracle's restatement of `<f64 as FromStr>`: the same value bit for bit, or ParseFloat with the same message"""
+    dmx = _write(tmp_path, "g.dmx", "p min 2 1\na 1 2\n")
+    qfc = _write(tmp_path, "g.qfc", "1\n0\n" + spelling + "\n")
+    try:
+        want = ("ok", orc.load_kkt_system(dmx, qfc).a.csc()[2])
+    except orc.OracleError as e:
+        want = ("err", e.code, str(e))
+    try:
+        got = ("ok", data_loader.load_kkt_host(dmx, qfc).csc()[3])
+    except DataLoaderError as e:
+        got = ("err", e.code, str(e))
+    assert got[0] == want[0], (spelling, got, want)
+    if got[0] == "ok":
+        assert np.array_equal(got[1], want[1], equal_nan=True) and np.array_equal(np.signbit(got[1]), np.signbit(want[1]))
+    else:
+        assert got[1:] == want[1:]

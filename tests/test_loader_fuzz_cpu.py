@@ -35,8 +35,11 @@ def nearly_good_pair(draw):
             body.append(draw(line))
     dmx = draw(st.sampled_from(["", "c generated\n"])) + f"p min {nodes} {arcs}\n" + "".join(x + "\n" for x in body)
     m_line = arcs if draw(st.integers(0, 7)) else arcs + 1
-    good_num = st.sampled_from(["1", "2.5", "-3", "1e2", ".5", "+7.", "0"])
-    num = good_num if draw(st.integers(0, 5)) else st.sampled_from(["inf", "x", " 1", "1 ", "", "nan"])
+    good_num = st.sampled_from(["1", "2.5", "-3", "1e2", ".5", "+7.", "0", "1.e5", "1e+5", "1e-5", "-.5", "00012", "-0", "1E-400",
+                                "1e400", "-1e400", "4.9e-324", "123456789012345678901234567890.5"])
+    num = good_num if draw(st.integers(0, 5)) else st.sampled_from(
+        ["inf", "x", " 1", "1 ", "", "nan", ".e5", "1e", "--1", "1-2", "-", ".", "e5", "1.5.2", "1e5e5", "1e-", "+-1", "-+1", "1_0",
+         "0x10", "1f", "infinity", "-INF", "NaN", "nan(1)", "1e5.0"])
     n_costs = draw(st.sampled_from([arcs, arcs, arcs, 0, max(arcs - 1, 0), arcs + 2]))
     qfc = f"{m_line}\n" + "".join("skipped\n" for _ in range(arcs)) + "".join(draw(num) + "\n" for _ in range(n_costs))
     return dmx, qfc

@@ -144,6 +144,19 @@ bool rust_f64(const char* b, const char* e, double& out) {
   return true;
 }
 
+// Fast path of a cost line: only the characters of a plain decimal ([0-9 . e E -]) and std::from_chars consumes the whole
+// line without a range error.  Under that alphabet from_chars and <f64 as FromStr> accept exactly the same strings (both
+// follow `-? (digits [. digits*] | . digits) ([eE] -? digits)?`), and both round correctly.
+inline bool fast_f64_line(const char* b, const char* e, double& out) {
+  if (b >= e) return false;
+  for (const char* s = b; s < e; ++s) {
+    const char ch = *s;
+    if (!((ch >= '0' && ch <= '9') || ch == '.' || ch == 'e' || ch == 'E' || ch == '-')) return false;
+  }
+  const std::from_chars_result r = std::from_chars(b, e, out, std::chars_format::general);
+  return r.ec == std::errc() && r.ptr == e;
+}
+
 struct Trip {
   uint64_t r, c;
   double v;
@@ -174,6 +187,37 @@ bool build_csc(size_t nrows, size_t ncols, std::vector<Trip>& t, std::vector<uin
   return true;
 }
 
+// Fast path for the overwhelmingly common line `a <tail> <head> [ignored tokens]`, pure ASCII, both indices plain positive
+// decimals that fit: appends the arc and returns true.  Returns false WITHOUT side effects for every other line (other
+// kinds, malformed or zero indices, overflow, non-ASCII bytes anywhere), which then takes the general path and gets the
+// reference's exact error.
+inline bool fast_arc_line(const char* b, const char* e, std::vector<uint64_t>& tails, std::vector<uint64_t>& heads) {
+  const char* s = b;
+  while (s < e && is_ws(*s)) ++s;
+  if (s + 1 >= e || *s != 'a' || !is_ws(s[1])) return false;
+  ++s;
+  uint64_t uv[2];
+  for (int q = 0; q < 2; ++q) {
+    while (s < e && is_ws(*s)) ++s;
+    if (s < e && *s == '+') ++s;
+    const char* t = s;
+    uint64_t v = 0;
+    while (t < e && *t >= '0' && *t <= '9') {
+      if (t - s >= 18) return false;  // (cannot overflow below 19 digits; longer ones go the general way)
+      v = v * 10 + uint64_t(*t - '0');
+      ++t;
+    }
+    if (t == s || v == 0 || (t < e && !is_ws(*t))) return false;
+    uv[q] = v - 1;
+    s = t;
+  }
+  for (const char* t = s; t < e; ++t)
+    if (static_cast<unsigned char>(*t) >= 0x80) return false;  // UTF-8 validity of the ignored rest is the general path's job
+  tails.push_back(uv[0]);
+  heads.push_back(uv[1]);
+  return true;
+}
+
 int parse_dmx(const char* path, tpl_kkt& k, std::vector<uint64_t>& tails, std::vector<uint64_t>& heads) {
   std::string text, why;
   if (!read_file(path, text, why)) return fail(TPL_ERR_IO, "I/O error: %s", why.c_str());
@@ -182,6 +226,7 @@ int parse_dmx(const char* path, tpl_kkt& k, std::vector<uint64_t>& tails, std::v
   bool found = false;
   std::vector<std::pair<const char*, const char*>> tok;
   while (cur.next(b, e)) {
+    if (fast_arc_line(b, e, tails, heads)) continue;  // the plain `a <tail> <head> ...` line; anything else: general path
     if (!utf8_ok(b, e)) return fail(TPL_ERR_IO, "I/O error: stream did not contain valid UTF-8");
     tok.clear();
     for (const char* s = b; s < e;) {
@@ -256,8 +301,12 @@ int parse_qfc(const char* path, size_t expected_arcs, std::vector<double>& costs
   costs.clear();
   for (size_t i = 0; i < expected_arcs; ++i) {  // .take(m) with no length check
     if (!cur.next(b, e)) break;
-    if (!utf8_ok(b, e)) return fail(TPL_ERR_IO, "I/O error: stream did not contain valid UTF-8");
     double c;
+    if (fast_f64_line(b, e, c)) {  // plain decimal spelling; everything else is validated the long way
+      costs.push_back(c);
+      continue;
+    }
+    if (!utf8_ok(b, e)) return fail(TPL_ERR_IO, "I/O error: stream did not contain valid UTF-8");
     if (!rust_f64(b, e, c))
       return fail(TPL_ERR_PARSE_FLOAT, "Parse error: Failed to parse float from '%s'", std::string(b, e).c_str());
     costs.push_back(c);
