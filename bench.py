@@ -124,6 +124,22 @@ def build_instance(args):
     return inst
 
 
+def config_dict(args, inst):
+    """`config` of the JSON line: identical in both arms (same workload, same N)."""
+    world = args.gpus
+    return {"workload": workload_string(args, inst),
+            "l2": "GPU arm: L2 flushed between solves (256 MiB write); CPU arm: 28 MB working set, cold first run discarded",
+            "parallelism": "1 GPU" if world == 1 else
+            f"{world} GPUs, arc-partitioned rows + replicated node segment; per Lanczos step a reduction of the p={inst.p} "
+            f"node sums and two scalar all-reduces (pass 2: the node sums only); the CPU arm runs on rank 0's host cores"}
+
+
+def workload_string(args, inst):
+    """ONE description of the workload, shared verbatim by both arms (the driver compares the two lines' `config.workload`)."""
+    return (f"netgen-shaped KKT {args.arcs} arcs rho={args.rho} n={inst.n} (seed {args.seed}, qfcgen 'aa' costs), "
+            f"lanczos_two_pass f=inv k={args.k}, b=A*(1/sqrt(n))")
+
+
 def algorithmic_bytes(n, bmat, k):
     """pass-1 step = B_mat + 48 n, pass-2 step = B_mat + 40 n, init = 40 n."""
     pass1 = k * (bmat + 48 * n) + 16 * n
@@ -146,9 +162,10 @@ def cpu_model():
     return f"{name} ({os.cpu_count()} logical cores, 1 used)"
 
 
-def cpu_two_pass_seconds(inst, k, repeats=1):
+def cpu_two_pass_seconds(inst, k, repeats=1, keep=None):
     """Times the CPU oracle (oracle/lanczos_oracle.cpp: CSC scatter matvec, 8-byte indices, unfused sweeps, one
-    thread -- the reference runs faer with Par::Seq) on the same instance and right-hand side."""
+    thread -- the reference runs faer with Par::Seq) on the same instance and right-hand side.  `keep` (a dict) receives the
+    oracle's x and b: the GPU arm compares its own x with it (`parity` in the JSON line), outside every timed region."""
     from oracle import np_oracle as npo
     from oracle import oracle as orc
 
@@ -160,9 +177,11 @@ def cpu_two_pass_seconds(inst, k, repeats=1):
     best = None
     for _ in range(repeats):
         t = time.perf_counter()
-        orc.lanczos_two_pass(oop, b, k, npo.inv_tk_solver)
+        x = orc.lanczos_two_pass(oop, b, k, npo.inv_tk_solver)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
+        if keep is not None:
+            keep["x"], keep["b"] = x, b
     return best
 
 
@@ -189,9 +208,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"netgen-shaped KKT {args.arcs} arcs rho={args.rho} n={inst.n}, lanczos_two_pass "
-                               f"f=inv k={args.k}", "note": "reference = CPU oracle port (Rust/faer reference "
-                               "cannot be built here: no cargo/rustc, faer un-vendored); single thread like Par::Seq"},
+        "config": config_dict(args, inst),
+        "arm": {"format": "csc (faer SparseColMat, 8-byte indices)",
+                "note": "reference = CPU oracle port (Rust/faer reference cannot be built here: no cargo/rustc, faer "
+                        "un-vendored); single thread because the reference runs every faer call with Par::Seq"},
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": "port", "sample": sample, "cpu": cpu_model()},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -268,6 +288,8 @@ def run_b200(args, rank, world, local_rank):
     inst = build_instance(args)
     k = args.k
     stream = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    t_build = time.perf_counter()
     if world > 1:
         # arc-partitioned operator: rank r owns a contiguous arc block + a replica of the node entries; the
         # per-step all-reduces run inside the library over NCCL (same NVLink fabric torch.distributed uses)
@@ -280,6 +302,8 @@ def run_b200(args, rank, world, local_rank):
     else:
         op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d, device=local_rank)
         x_true = torch.full((inst.n,), 1.0 / np.sqrt(inst.n), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
     n = op.nrows()          # rank-local vector length (= inst.n on one GPU)
     m_loc = n - inst.p
     op.set_stream(stream.cuda_stream)
@@ -349,6 +373,23 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(sq)
     res = float(torch.sqrt((sq[0] + (r_loc[m_loc:] ** 2).sum()) / (sq[1] + (b_dev[m_loc:] ** 2).sum())))
     shape = op.kernel_shape()
+    # ---- parity: the whole x of the last device-resident solve on rank 0 (arc slices in rank order + the node replica)
+    if world > 1:
+        from two_pass_lanczos_b200 import sharding
+
+        lens = [sharding.arc_range(inst.m, r, world) for r in range(world)]
+        pad = max(hi - lo for lo, hi in lens) + inst.p
+        mine = torch.zeros(pad, dtype=torch.float64, device=dev)
+        mine[:n] = x_dev
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        x_full = np.concatenate([parts[r][: hi - lo].cpu().numpy() for r, (lo, hi) in enumerate(lens)]
+                                + [parts[0][lens[0][1] - lens[0][0]: lens[0][1] - lens[0][0] + inst.p].cpu().numpy()])
+        node_replicas_equal = all(
+            np.array_equal(parts[r][hi - lo: hi - lo + inst.p].cpu().numpy(), x_full[inst.m:]) for r, (lo, hi) in enumerate(lens))
+    else:
+        x_full = x_dev.cpu().numpy()
+        node_replicas_equal = True
     large = None
     if args.large_arcs > 0:
         try:
@@ -378,12 +419,10 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"netgen-shaped KKT {args.arcs} arcs rho={args.rho} n={inst.n} (seed {args.seed}, qfcgen "
-                                   f"'aa' costs), lanczos_two_pass f=inv k={k}, b=A*(1/sqrt(n))",
-                       "format": "incidence", "l2": "flushed between solves (256 MiB write)",
-                       "parallelism": "1 GPU" if world == 1 else
-                       f"{world} GPUs, arc-partitioned rows + replicated node segment ({shape}); per Lanczos step a reduction "
-                       f"of the p={inst.p} node sums and two scalar all-reduces (pass 2: the node sums only)"},
+            "config": config_dict(args, inst),
+            "arm": {"format": "incidence", "kernel_shape": shape, "operator_build_s": round(build_s, 4),
+                    "operator_build_note": "host tables + H2D of the operator, outside the timed region as in the reference's "
+                                           "protocol (src/bin/tradeoff.rs:265-288 times the solver call only)"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "ms", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n + 16 * k,
                     "per_step_ms": [round(t, 3) for t in e2e_ms]},
@@ -402,10 +441,26 @@ def run_b200(args, rank, world, local_rank):
         }
         if large is not None:
             line["large_instance"] = large
-        if not args.no_cpu_baseline and world == 1:
-            t_cpu = cpu_two_pass_seconds(inst, k)
-            line["cpu_baseline"] = {"value": t_cpu * 1e3, "unit": "ms", "cores": 1, "kind": "port", "cpu": cpu_model(),
-                                    "sample": f"full workload (k={k}), one cold run, single thread (Par::Seq)"}
+        if not args.no_cpu_baseline:
+            # the CPU oracle solves the same instance and b once (outside every timed region): its time is the cpu_baseline
+            # (reported at N = 1 only), its x is what `parity` compares the GPU result with -- at every N
+            kept = {}
+            t_cpu = cpu_two_pass_seconds(inst, k, keep=kept)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers
+
+            x_cpu = kept["x"]
+            line["parity"] = {
+                "x_rel_vs_cpu": helpers.rel(x_full, x_cpu),
+                "x_rel_vs_cpu_nullspace_projected": helpers.rel(helpers.project_out_null(x_full, inst.m, inst.p),
+                                                                 helpers.project_out_null(x_cpu, inst.m, inst.p)),
+                "tolerance": 1e-10, "node_replicas_bit_equal": bool(node_replicas_equal),
+                "what": f"||x_gpu - x_cpu|| / ||x_cpu||, x_gpu = the last device-timed solve assembled from {world} rank(s), "
+                        f"x_cpu = oracle/lanczos_oracle.cpp lanczos_two_pass on the same instance and b (k={k}, f=inv)"}
+            assert line["parity"]["x_rel_vs_cpu"] <= 1e-10, f"parity gate failed: {line['parity']}"
+            if world == 1:
+                line["cpu_baseline"] = {"value": t_cpu * 1e3, "unit": "ms", "cores": 1, "kind": "port", "cpu": cpu_model(),
+                                        "sample": f"full workload (k={k}), one cold run, single thread (Par::Seq)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

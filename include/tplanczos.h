@@ -18,7 +18,8 @@
  *     src/utils/data_loader.rs:18-42).
  *   - vectors b, x, y, V may live in host memory OR in device memory of the operator's GPU
  *     (detected with cudaPointerGetAttributes); alphas/betas/steps/b_norm are host outputs.
- *   - all arithmetic is f64.  A handle is not thread-safe; distinct handles are independent.
+ *   - all arithmetic is f64.  A handle is not thread-safe; distinct handles are independent (they share
+ *     nothing but the kernels' shared-memory opt-in, which the library only ever raises).
  *   - breakdown (beta <= 1000*eps) is NOT an error: it shortens steps_taken (mod.rs:206-211).
  *   - there is no CPU fallback: without a usable CUDA device every compute entry point returns
  *     TPL_ERR_CUDA.
@@ -119,11 +120,20 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
 int tpl_op_from_kkt_system(const tpl_kkt* kkt, int format, int device, tpl_op** out);
 void tpl_op_free(tpl_op* op);
 size_t tpl_op_nrows(const tpl_op* op); /* LinOp::nrows == ncols */
+/* The compute entry points take bare pointers: every vector (b, x, y of apply) must hold tpl_op_nrows(op) doubles.  A
+ * binding that knows the length of the buffer it is about to pass calls this first: TPL_ERR_DIMENSION_MISMATCH with the
+ * reference's message (src/error.rs:29-35, where faer panics on the mismatch) unless len == nrows. */
+int tpl_op_check_len(const tpl_op* op, size_t len);
 int tpl_op_format(const tpl_op* op);   /* 1 = CSR, 2 = incidence, 3 = dense */
 int tpl_op_device(const tpl_op* op);
 /* LinOp::apply: y = A x (used by the reference's property tests, mod.rs:510). */
 int tpl_op_apply(tpl_op* op, const double* x, double* y);
-/* Use an externally owned CUDA stream (a cudaStream_t passed as void*) instead of the handle's own. */
+/* Use an externally owned CUDA stream (a cudaStream_t passed as void*) instead of the handle's own.
+ * STREAM CONTRACT: every copy and kernel of a handle is issued on ITS stream (created non-blocking, i.e. not ordered
+ * against the legacy default stream).  A caller that passes DEVICE pointers produced or consumed on another stream must
+ * either hand that stream over with this call (what the Python mirror does for device tensors: it adopts the
+ * framework's current stream) or order the two streams itself (event / synchronize) before the call and after it.  Host pointers need
+ * nothing: the entry points return after the result has arrived. */
 int tpl_op_set_stream(tpl_op* op, void* cuda_stream);
 /* Device time (ms, CUDA events on the operator's stream) of the last pass-one / pass-two / standard /
  * gemv launched through this handle, and the number of kernels this library launched so far. */

@@ -13,12 +13,17 @@
 // matvec, of dot products and of norm_l2) is a documented choice:
 //   * sparse matvec  : CSC scatter, columns ascending, y[i] += a*x[j] (mul and add rounded
 //                      separately; build with -ffp-contract=off)
-//   * dot / norm_l2  : plain left-to-right accumulation, norm = sqrt(sum of squares)
-// PARITY PINNING: the oracle is pinned by every known-answer / analytic test the reference
+//   * dot / norm_l2  : 32 interleaved partial sums combined pairwise (SIMD-loop shape), norm = sqrt(sum of squares)
+// PARITY PINNING: the oracle is pinned (a) by every known-answer / analytic test the reference
 // holds for this path (src/algorithms/mod.rs:385-428, tests/correctness.rs:165-325,
-// src/lib.rs:35-84, src/error.rs:69-129) -- see tests/test_oracle_reference_kats.py.
-// Bit-level agreement with faer's internal summation order is UNPINNED (no golden alpha/
-// beta/x vectors exist in the reference repo).
+// src/lib.rs:35-84, src/error.rs:69-129) and (b) by OUTPUTS OF THE REFERENCE ITSELF: fed with
+// the restated StdRng::seed_from_u64(42) right-hand side it reproduces every row of the
+// reference's results/accuracy_*.csv (src/bin/stability.rs) to 1e-14 ... 1e-10 relative on the
+// printed errors (ill-conditioned tails: 3e-4) and follows results/orthogonality_*.csv
+// (src/bin/orthogonality.rs) within the chaotic-amplification envelope -- see
+// tests/test_oracle_reference_kats.py and tests/golden/published_curves.json.
+// What stays open is only the LAST-BIT summation order inside faer's un-vendored kernels (the
+// reference ships no golden alpha/beta/x vectors).
 //
 // All `a - c*b` updates are two roundings (sub(a, mul(c,b))), normalisation multiplies by
 // the rounded reciprocal -- src/algorithms/mod.rs:183-198,277-278,312-315 and
@@ -118,8 +123,24 @@ void csc_matvec(const Csc& a, const R* x, R* y) {
 
 template <class R>
 R dot(const R* a, const R* b, size_t n) {
-  R s = R(0);
-  for (size_t i = 0; i < n; ++i) {
+  // 32 independent partial sums (the shape of a 4-way unrolled 8-lane SIMD loop), combined pairwise, then a
+  // scalar tail.  faer's reduction kernels are not in the tree; the ACCURACY CLASS of this order is pinned by the
+  // reference's published orthogonality curves (results/orthogonality_*.csv): with it the oracle's ||I - V^T V||_F
+  // follows them within a factor 2 from k = 20 to k = 1000, a strict left-to-right sum loses orthogonality
+  // 10-15 x faster (tests/test_oracle_reference_kats.py::test_published_orthogonality_curves).
+  constexpr size_t L = 32;
+  R acc[L];
+  for (size_t l = 0; l < L; ++l) acc[l] = R(0);
+  size_t i = 0;
+  for (; i + L <= n; i += L)
+    for (size_t l = 0; l < L; ++l) {
+      R p = a[i + l] * b[i + l];
+      acc[l] = acc[l] + p;
+    }
+  for (size_t w = L / 2; w >= 1; w /= 2)
+    for (size_t l = 0; l < w; ++l) acc[l] = acc[l] + acc[l + w];
+  R s = acc[0];
+  for (; i < n; ++i) {
     R p = a[i] * b[i];
     s = s + p;
   }
@@ -369,23 +390,31 @@ bool parse_f64(const std::string& s, double& out) {  // <f64 as FromStr> (core::
   return true;
 }
 
+// core::str::from_utf8: shortest-form encodings of scalar values only (no C0/C1 lead bytes, no overlong 3- and 4-byte
+// forms, no surrogates U+D800..DFFF, nothing above U+10FFFF)
 bool valid_utf8(const std::string& s) {
   size_t i = 0, n = s.size();
   while (i < n) {
     unsigned char c = s[i];
-    size_t len = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 0;
+    if (c < 0x80) { ++i; continue; }
+    size_t len = (c >= 0xC2 && c <= 0xDF) ? 2 : (c >> 4) == 14 ? 3 : (c >= 0xF0 && c <= 0xF4) ? 4 : 0;
     if (!len || i + len > n) return false;
     for (size_t k = 1; k < len; ++k)
       if ((((unsigned char)s[i + k]) >> 6) != 2) return false;
+    const unsigned char c1 = s[i + 1];
+    if ((c == 0xE0 && c1 < 0xA0) || (c == 0xED && c1 >= 0xA0) || (c == 0xF0 && c1 < 0x90) || (c == 0xF4 && c1 >= 0x90))
+      return false;
     i += len;
   }
   return true;
 }
 
-// BufRead::lines(): split on '\n', strip one trailing '\r'
+// BufRead::lines(): split on '\n'; a '\r' is stripped only as part of a "\r\n" terminator (a last line without '\n'
+// keeps its trailing '\r')
 bool next_line(std::ifstream& f, std::string& line) {
   if (!std::getline(f, line)) return false;
-  if (!line.empty() && line.back() == '\r') line.pop_back();
+  const bool terminated = !f.eof();  // getline sets eofbit when it ran into the end without finding the delimiter
+  if (terminated && !line.empty() && line.back() == '\r') line.pop_back();
   return true;
 }
 

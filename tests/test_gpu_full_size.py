@@ -98,58 +98,111 @@ def test_wc_full_size_converged_solution_matches_oracle():
     assert helpers.rel(x, helpers.project_out_null(x_true, inst.m, inst.p)) < 1e-10
 
 
-PUBLISHED = [  # results/accuracy_*.csv (see tests/test_oracle_reference_kats.py for the citations)
-    ("exp", "well", 10, 1.64e-4), ("exp", "well", 20, 1.61e-12), ("exp", "well", 30, 3.98e-15),
-    ("inv", "well", 50, 7.72e-2), ("inv", "well", 100, 3.28e-3), ("inv", "well", 200, 5.93e-6),
-    ("exp", "ill", 100, 5.87e-5), ("exp", "ill", 150, 2.42e-10), ("exp", "ill", 180, 2.10e-14),
-    ("inv", "ill", 160, 2.53e-2), ("inv", "ill", 200, 6.57e-6),
-]
+def test_headline_k500_matches_oracle(headline):
+    """THE north-star acceptance gate: `lanczos_two_pass`, f = inv, 500 k arcs "aa", rho = 3, k = 500, b = A (1/sqrt n) 1
+    (src/bin/tradeoff.rs:234-258, src/solvers.rs:133-175): x within 1e-10 relative of the CPU reference path (one oracle
+    solve, a few seconds on one core).  SURVEY 8c(ii): on the aa flavour the null direction is not found by k = 500, so the
+    raw x is compared; the null-space-projected deviation and the residual are checked beside it."""
+    inst, gop, b = headline
+    oop = helpers.oracle_op(inst)
+    b_cpu = helpers.rhs_from_const(oop.apply, inst.n)
+    assert helpers.rel(b, b_cpu) < 1e-15
+    k = 500
+    x_cpu = orc.lanczos_two_pass(oop, b_cpu, k, npo.inv_tk_solver)
+    x_gpu = tpl.lanczos_two_pass(gop, b, k, "inv")
+    assert helpers.rel(x_gpu, x_cpu) <= 1e-10
+    assert helpers.rel(helpers.project_out_null(x_gpu, inst.m, inst.p), helpers.project_out_null(x_cpu, inst.m, inst.p)) <= 1e-10
+    x1_gpu = tpl.lanczos(gop, b, k, "inv")
+    assert helpers.rel(x1_gpu, x_cpu) <= 1e-10
+    for shape_mode in (2, 3):  # the tiled streaming kernels and the gather kernels on the same instance
+        gop.set_mode(shape_mode)
+        assert helpers.rel(tpl.lanczos_two_pass(gop, b, k, "inv"), x_cpu) <= 1e-10, shape_mode
+    gop.set_mode(0)
 
 
-@pytest.mark.parametrize("func,scenario,k,published", PUBLISHED)
-def test_stability_harness(func, scenario, k, published):
-    """src/bin/stability.rs: relative error of both variants against the analytic f(lambda_i) b_i."""
+@pytest.mark.parametrize("fmt", ["kkt", "csr"])
+def test_config2_50k_k500_one_pass_vs_two_pass_matches_oracle(fmt):
+    """BASELINE config 2: 50 k arcs, rho = 3, k = 500, one-pass vs two-pass (results/tradeoff_arcs50k_rho3.csv:11,31), both
+    within 1e-10 of the oracle's two-pass x and of each other."""
+    inst = datagen.gen_kkt(50_000, 3, 1, "aa")
+    assert inst.n == 50_365
+    oop = helpers.oracle_op(inst)
+    if fmt == "kkt":
+        gop = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d)
+    else:
+        gop = tpl.LinOp.from_csc(inst.n, *oop.csc())
+    b = helpers.rhs_from_const(oop.apply, inst.n)
+    x_cpu = orc.lanczos_two_pass(oop, b, 500, npo.inv_tk_solver)
+    x2 = tpl.lanczos_two_pass(gop, b, 500, "inv")
+    x1 = tpl.lanczos(gop, b, 500, "inv")
+    assert helpers.rel(x2, x_cpu) <= 1e-10
+    assert helpers.rel(x1, x_cpu) <= 1e-10
+    assert helpers.rel(x1, x2) <= 1e-12
+    gop.close()
+
+
+@pytest.mark.parametrize("k", [50, 250, 750, 1000])
+def test_config3_k_sweep_points_match_oracle(headline, k):
+    """BASELINE config 3 (k = 50 ... 1000 at 500 k arcs, results/tradeoff_arcs500k_rho3.csv): x vs the oracle at four more
+    points of the sweep.  Mid-convergence points are gated relative to the oracle's own residual."""
+    inst, gop, b = headline
+    oop = helpers.oracle_op(inst)
+    x_cpu = orc.lanczos_two_pass(oop, b, k, npo.inv_tk_solver)
+    x_gpu = tpl.lanczos_two_pass(gop, b, k, "inv")
+    res_cpu = np.linalg.norm(oop.apply(x_cpu) - b) / np.linalg.norm(b)
+    assert helpers.rel(x_gpu, x_cpu) <= max(1e-10, 1e-3 * res_cpu), (k, res_cpu)
+
+
+CURVES = ["inv_well", "inv_ill", "exp_well", "exp_ill"]
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_stability_harness(curve):
+    """src/bin/stability.rs:259-312 on the GPU path: EVERY row of the reference's results/accuracy_*.csv (both variants
+    against the analytic f(lambda_i) b_i, b = StdRng::seed_from_u64(42) uniforms) within the per-curve tolerance of
+    tests/helpers.py, and the two variants equal to rounding (column 4)."""
     import scipy.sparse as sp
 
+    func, scenario = curve.split("_")
     n = 10_000
     eigs = helpers.stability_spectrum(n, func, scenario)
     gop = tpl.LinOp.from_scipy(sp.diags(eigs))
-    oop = orc.SparseColMat.try_new_from_triplets(n, n, np.arange(n), np.arange(n), eigs)
-    b = helpers.seeded_b(n)
+    b = helpers.reference_b(n)
     x_true = (np.exp(eigs) if func == "exp" else 1.0 / eigs) * b
-    x2 = tpl.lanczos_two_pass(gop, b, k, func)
-    x1 = tpl.lanczos(gop, b, k, func)
-    err = helpers.rel(x2, x_true)
-    assert max(published, 1e-15) / 30.0 < max(err, 1e-15) < max(published, 1e-15) * 30.0
-    assert helpers.rel(x1, x2) < 1e-13
-    x_ref = orc.lanczos_two_pass(oop, b, k, helpers.FTK[func])
-    assert abs(err - helpers.rel(x_ref, x_true)) <= 0.5 * err + 1e-12  # same convergence curve as the oracle
+    rows = helpers.published_curves()["accuracy"][curve]["rows"]
+    assert len(rows) == 20
+    for k, pub_std, pub_two, _ in rows:
+        x1 = tpl.lanczos(gop, b, k, func)
+        x2 = tpl.lanczos_two_pass(gop, b, k, func)
+        helpers.check_accuracy_row(curve, k, pub_std, helpers.rel(x1, x_true))
+        helpers.check_accuracy_row(curve, k, pub_two, helpers.rel(x2, x_true))
+        assert helpers.rel(x1, x2) < 2e-15
+    gop.close()
 
 
-@pytest.mark.parametrize("func,scenario", [("exp", "well"), ("inv", "ill")])
-def test_orthogonality_harness(func, scenario):
-    """src/bin/orthogonality.rs:148-232: ||I - V^T V||_F of the stored and the regenerated basis, and their drift
-    (published: drift exactly 0.0, both losses bit-identical; loss 9.45e-15 at k=20 -> O(1) at k=1000)."""
+@pytest.mark.parametrize("curve", CURVES)
+def test_orthogonality_harness(curve):
+    """src/bin/orthogonality.rs:148-232 on the GPU path: ||I - V^T V||_F of the stored and of the regenerated basis, and their
+    drift, against the reference's results/orthogonality_*.csv (drift exactly 0.0, both losses bit-identical; the loss itself
+    is an envelope: x4 at rounding level, x12 once it is amplified -- same bounds as for the oracle)."""
     import scipy.sparse as sp
 
+    func, scenario = curve.split("_")
     n = 10_000
     gop = tpl.LinOp.from_scipy(sp.diags(helpers.stability_spectrum(n, func, scenario)))
-    b = helpers.seeded_b(n)
-    losses = {}
-    for k in (20, 100, 400):
+    b = helpers.reference_b(n)
+    rows = {r[0]: r for r in helpers.published_curves()["orthogonality"][curve]["rows"]}
+    for k in (20, 100, 200, 400, 600, 1000):
         out = alg.lanczos_standard(gop, b, k)
         steps = out.decomposition.steps_taken
+        assert steps == k
         p2 = alg.lanczos_pass_two_with_basis(gop, b, out.decomposition, np.zeros(steps))
         loss_std = np.linalg.norm(np.eye(steps) - out.v_k.T @ out.v_k)
         loss_regen = np.linalg.norm(np.eye(steps) - p2.v_k.T @ p2.v_k)
-        assert np.linalg.norm(out.v_k - p2.v_k) == 0.0
+        assert np.linalg.norm(out.v_k - p2.v_k) == 0.0   # basis_drift_fro
         assert loss_std == loss_regen
         assert np.linalg.norm(p2.x_k) == 0.0  # dummy y = 0 (orthogonality.rs:185-187)
-        losses[k] = loss_std
-    # soft golden curves: results/orthogonality_{exp_well,inv_ill}-conditioned.csv rows k = 20, 100, 400
-    published = {("exp", "well"): {20: 9.450129381865854e-15, 100: 6.200746375824939e-14, 400: 1.4341356746045474e-11},
-                 ("inv", "ill"): {20: 1.0e-14, 100: 3.00357411682582e-14, 400: 0.08480779566223172}}[(func, scenario)]
-    assert losses[20] < 1e-13
-    for k in (100, 400):  # same order of magnitude as the reference's curve (loss growth is chaotic in the last digits)
-        assert published[k] / 50.0 < losses[k] < published[k] * 50.0, (k, losses[k], published[k])
-    assert losses[400] > 10.0 * losses[20]  # orthogonality degrades with k, as in the published curves
+        pub = rows[k][1]
+        bound = 4.0 if k <= 200 else 12.0
+        assert pub / bound < loss_std < pub * bound, (curve, k, pub, loss_std)
+    gop.close()

@@ -119,3 +119,94 @@ def test_callback_early_stop():  # LanczosCallback, lanczos.rs:93-106
     full = alg.lanczos_standard(a, b, 20)
     assert np.array_equal(out.v_k, full.v_k[:, :7])  # per-step launches reproduce the persistent kernel bitwise
     assert np.array_equal(out.decomposition.alphas, full.decomposition.alphas[:7])
+
+
+def test_callback_sees_the_breakdown_step():
+    """lanczos.rs:93-112: the callback runs after EVERY completed step, also the one whose beta is <= tol; the breakdown is
+    looked at afterwards.  diag(2, 3), b = e1 breaks down in step 1 (mod.rs:410-419)."""
+    a = tpl.LinOp.from_dense(np.diag([2.0, 3.0]))
+    seen = []
+    out = alg.lanczos_standard(a, [1, 0], 2, callback=lambda k, v_k, t_k: seen.append((k, len(t_k.alphas), len(t_k.betas))) or True)
+    assert out.decomposition.steps_taken == 1
+    assert seen == [(1, 1, 0)]
+    with pytest.raises(tpl.LanczosError):  # a zero b completes no step: no callback
+        alg.lanczos_standard(a, [0, 0], 2, callback=lambda *args: seen.append("never") or True)
+    assert seen == [(1, 1, 0)]
+
+
+def test_dimension_mismatch_is_an_error_not_an_overrun():
+    """The C entry points take bare pointers; the binding checks every vector against nrows() first and reports the
+    reference's DimensionMismatch (src/error.rs:29-35; faer panics on the same misuse)."""
+    a, b, _ = simple_problem()
+    for fn in (lambda: tpl.lanczos_two_pass(a, b[:3], 3, "inv"), lambda: tpl.lanczos(a, np.ones(5), 3, "inv"),
+               lambda: alg.lanczos_pass_one(a, b[:2], 3), lambda: alg.lanczos_standard(a, np.ones(9), 3),
+               lambda: a.apply(np.ones(3))):
+        with pytest.raises(tpl.LanczosError) as e:
+            fn()
+        assert e.value.kind == "DimensionMismatch"
+    with pytest.raises(tpl.LanczosError) as e:
+        a.apply(np.ones(3))
+    assert str(e.value) == "Dimension mismatch: operator has 4 columns but vector has 3 rows."
+    d = alg.lanczos_pass_one(a, b, 3)
+    short = alg.LanczosDecomposition(d.alphas[:2], d.betas, 3, d.b_norm)
+    with pytest.raises(tpl.LanczosError) as e:
+        alg.lanczos_pass_two(a, b, short, np.ones(3))
+    assert e.value.kind == "ParameterMismatch"
+    short = alg.LanczosDecomposition(d.alphas, d.betas[:1], 3, d.b_norm)
+    with pytest.raises(tpl.LanczosError):
+        alg.lanczos_pass_two(a, b, short, np.ones(3))
+
+
+def test_handles_are_independent_in_shared_memory_size():
+    """A later handle with a small shared-memory footprint must not lower the opt-in cap of the kernels under an earlier
+    handle that needs more (the attribute belongs to the kernel, not to the handle): alternate solves on a large-p and a
+    small-p operator of every incidence shape."""
+    from two_pass_lanczos_b200 import datagen
+
+    big = datagen.gen_kkt(2_000_000, 3, 3, "wc")      # p = 2309: large node segment, tiled kernels with big tiles
+    small = datagen.gen_kkt(3_000, 3, 4, "wc")        # p = 89
+    op_big = tpl.LinOp.from_kkt(big.m, big.p, big.tail, big.head, big.d)
+    b_big = op_big.apply(np.full(big.n, 1.0 / np.sqrt(big.n)))
+    ref = {}
+    for mode in (0, 2, 3):
+        op_big.set_mode(mode)
+        ref[mode] = alg.lanczos_pass_one(op_big, b_big, 12)
+    op_small = tpl.LinOp.from_kkt(small.m, small.p, small.tail, small.head, small.d)  # created AFTER the large one
+    b_small = op_small.apply(np.full(small.n, 1.0 / np.sqrt(small.n)))
+    for mode in (0, 2, 3, 4):
+        op_small.set_mode(mode)
+        alg.lanczos_pass_one(op_small, b_small, 12)
+        x_small = tpl.lanczos_two_pass(op_small, b_small, 12, "exp")
+        assert np.all(np.isfinite(x_small))
+    for mode in (0, 2, 3):  # the large handle still launches, with the same results
+        op_big.set_mode(mode)
+        again = alg.lanczos_pass_one(op_big, b_big, 12)
+        assert np.array_equal(again.alphas, ref[mode].alphas) and np.array_equal(again.betas, ref[mode].betas)
+    op_big.close()
+    op_small.close()
+
+
+def test_cuda_tensor_inputs_are_ordered_after_their_producer():
+    """A CUDA tensor produced on torch's current stream just before the call is consumed correctly without any explicit
+    synchronisation: the operator adopts the current stream (operators.LinOp._vec)."""
+    import torch
+
+    from two_pass_lanczos_b200 import datagen
+
+    inst = datagen.gen_kkt(200_000, 3, 5, "wc")
+    op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d)
+    x0 = np.full(inst.n, 1.0 / np.sqrt(inst.n))
+    b_host = op.apply(x0)
+    expect = tpl.lanczos_two_pass(op, b_host, 25, "exp")
+    side = torch.cuda.Stream()
+    for stream in (torch.cuda.current_stream(), side):
+        with torch.cuda.stream(stream):
+            big = torch.ones(64 << 20, dtype=torch.float64, device="cuda")
+            for _ in range(4):          # a few ms of queued work in front of the producer of b
+                big.mul_(1.0000001)
+            xt = torch.full((inst.n,), 1.0 / np.sqrt(inst.n), dtype=torch.float64, device="cuda")
+            bt = op.apply(xt) * 1.0     # produced on `stream`, consumed by the library right away
+            x = tpl.lanczos_two_pass(op, bt, 25, "exp")
+            got = x.cpu().numpy()
+        assert np.array_equal(got, expect)
+    op.close()

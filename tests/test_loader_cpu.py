@@ -84,7 +84,28 @@ CASES = [  # (dmx text, qfc text, error kind, message)
     (GOOD_DMX, "2\n1\n1\n3.5 \n4\n", "ParseFloat", "Parse error: Failed to parse float from '3.5 '"),
     (GOOD_DMX, "2\n1\n1\n0x10\n4\n", "ParseFloat", "Parse error: Failed to parse float from '0x10'"),
     (GOOD_DMX.encode() + b"c \xff\xfe\n", GOOD_QFC, "Io", None),
+    # BufRead::lines strips '\r' only as part of "\r\n": a last line WITHOUT '\n' keeps it and then fails to parse
+    (GOOD_DMX, "2\r", "ParseInt", "Parse error: Failed to parse integer from 'm'"),
+    (GOOD_DMX, "2\n1\n1\n3.5\n4.5\r", "ParseFloat", "Parse error: Failed to parse float from '4.5\r'"),
+    # core::str::from_utf8 rejects overlong forms, surrogates and code points above U+10FFFF
+    (GOOD_DMX.encode() + b"c \xc0\x80\n", GOOD_QFC, "Io", None),
+    (GOOD_DMX.encode() + b"c \xe0\x80\x80\n", GOOD_QFC, "Io", None),
+    (GOOD_DMX.encode() + b"c \xed\xa0\x80\n", GOOD_QFC, "Io", None),
+    (GOOD_DMX.encode() + b"c \xf0\x80\x80\x80\n", GOOD_QFC, "Io", None),
+    (GOOD_DMX.encode() + b"c \xf4\x90\x80\x80\n", GOOD_QFC, "Io", None),
+    (GOOD_DMX.encode() + b"c \xf5\x80\x80\x80\n", GOOD_QFC, "Io", None),
 ]
+
+
+def test_loader_accepts_valid_multibyte_utf8_and_crlf_last_line(tmp_path):
+    """The strict UTF-8 check still accepts every well-formed sequence (2-, 3-, 4-byte, U+D7FF, U+E000, U+10FFFF), and a
+    "\r\n"-terminated last line loses its '\r' as in BufRead::lines."""
+    ok = "c \u00e9 \u20ac \ud7ff \ue000 \U0001f600 \U0010ffff\n".encode()
+    dmx = _write(tmp_path, "u.dmx", ok + GOOD_DMX.encode())
+    qfc = _write(tmp_path, "u.qfc", "2\r\n1.0\r\n1.0\r\n3.5\r\n4.5\r\n")
+    host = data_loader.load_kkt_host(dmx, qfc)
+    ref = orc.load_kkt_system(dmx, qfc)
+    assert host.num_costs == 2 and np.array_equal(host.csc()[3], ref.a.csc()[2])
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))

@@ -1,7 +1,7 @@
 """`two_pass_lanczos_b200.stdrng`: the ChaCha core against published keystreams (zero key, zero nonce: 20 rounds = the
 classic ChaCha20 vector, 12 rounds = draft-strombergson-chacha-test-vectors TC1), plus the structural properties of the
-seeded uniform stream.  The PCG32 seed expansion and the float conversion have no vector to check against here (see the
-module header: UNPINNED)."""
+seeded uniform stream.  The PCG32 seed expansion and the float conversion are pinned end to end by the reference's published
+accuracy rows (tests/test_oracle_reference_kats.py::test_published_accuracy_rows)."""
 import numpy as np
 
 from two_pass_lanczos_b200 import stdrng

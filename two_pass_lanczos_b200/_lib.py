@@ -44,6 +44,7 @@ SIGNATURES = {
     "tpl_op_from_kkt_system": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "tpl_op_free": (None, [C.c_void_p]),
     "tpl_op_nrows": (C.c_size_t, [C.c_void_p]),
+    "tpl_op_check_len": (C.c_int, [C.c_void_p, C.c_size_t]),
     "tpl_op_format": (C.c_int, [C.c_void_p]),
     "tpl_op_device": (C.c_int, [C.c_void_p]),
     "tpl_op_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

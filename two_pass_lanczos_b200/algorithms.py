@@ -9,7 +9,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import STEP_CB, c_dp
-from .operators import LinOp, _vec_ptr
+from .error import LanczosError
+from .operators import LinOp
 
 
 @dataclass
@@ -45,7 +46,7 @@ def _dp(a):
 
 def lanczos_pass_one(operator: LinOp, b, k: int) -> LanczosDecomposition:
     """src/algorithms/lanczos_two_pass.rs:65-110"""
-    bp, keep, _ = _vec_ptr(b)
+    bp, keep, _ = operator._vec(b)
     al = np.zeros(max(k, 1))
     be = np.zeros(max(k, 1))
     steps, bn = C.c_size_t(), C.c_double()
@@ -55,11 +56,16 @@ def lanczos_pass_one(operator: LinOp, b, k: int) -> LanczosDecomposition:
 
 
 def _pass_two(operator: LinOp, b, dec: LanczosDecomposition, y_k, with_basis: bool):
-    bp, keep, is_torch = _vec_ptr(b)
+    bp, keep, is_torch = operator._vec(b)
     n = operator.nrows()
     y = np.ascontiguousarray(np.asarray(y_k, dtype=np.float64).reshape(-1))
     al = np.ascontiguousarray(dec.alphas, dtype=np.float64)
     be = np.ascontiguousarray(dec.betas, dtype=np.float64)
+    # the C entry point reads steps_taken alphas and steps_taken - 1 betas through bare pointers
+    if len(al) < dec.steps_taken:
+        raise LanczosError(4, f"Parameter mismatch: `alphas` expects size {dec.steps_taken}, but got {len(al)}.")
+    if len(be) < max(dec.steps_taken - 1, 0):
+        raise LanczosError(4, f"Parameter mismatch: `betas` expects size {max(dec.steps_taken - 1, 0)}, but got {len(be)}.")
     al = al if len(al) else np.zeros(1)
     be = be if len(be) else np.zeros(1)
     y_arg = y if len(y) else np.zeros(1)
@@ -90,7 +96,7 @@ def lanczos_pass_two_with_basis(operator: LinOp, b, decomposition: LanczosDecomp
 def lanczos_standard(operator: LinOp, b, k: int, callback=None) -> LanczosOutput:
     """src/algorithms/lanczos.rs:55-156.  `callback(k, v_k, t_k_view) -> bool` follows LanczosCallback
     (mod.rs:82-86); v_k is handed over as a lazily-fetched object with `.to_host()` (it lives in HBM)."""
-    bp, keep, _ = _vec_ptr(b)
+    bp, keep, _ = operator._vec(b)
     n = operator.nrows()
     V = np.zeros((max(k, 1), n))
     al = np.zeros(max(k, 1))

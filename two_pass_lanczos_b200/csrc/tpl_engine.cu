@@ -10,6 +10,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -303,9 +305,20 @@ int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
   return TPL_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the KERNEL (per device), shared by every handle of the
+// process: it is only ever raised, so that a handle created later with a smaller shared-memory footprint cannot lower
+// the cap under an earlier handle whose cooperative launches need more (a launch may always ask for less than the cap).
 template <class K>
 int set_smem(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> high;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = high[{reinterpret_cast<const void*>(kernel), dev}];
+  if (bytes <= cur) return TPL_OK;
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  cur = bytes;
   return TPL_OK;
 }
 
@@ -761,6 +774,13 @@ int tpl_op_from_kkt_system(const tpl_kkt* kkt, int format, int device, tpl_op** 
 }
 
 size_t tpl_op_nrows(const tpl_op* op) { return op ? op->n : 0; }
+int tpl_op_check_len(const tpl_op* op, size_t len) {
+  if (!op) return fail(TPL_ERR_PANIC, "null argument");
+  if (len != op->n)  // src/error.rs:29-35
+    return fail(TPL_ERR_DIMENSION_MISMATCH, "Dimension mismatch: operator has %zu columns but vector has %zu rows.",
+                (size_t)op->n, len);
+  return TPL_OK;
+}
 int tpl_op_format(const tpl_op* op) { return op ? op->format : 0; }
 int tpl_op_device(const tpl_op* op) { return op ? op->device : -1; }
 uint64_t tpl_op_kernel_launches(const tpl_op* op) { return op ? op->launches : 0; }
@@ -1185,10 +1205,12 @@ int run_pass_one(tpl_op* op, const double* b_dev, size_t k, double* V_dev, size_
       if (int rc = launch_pass1(op, a, false)) return rc;
       if (!cb && j + 1 < k) continue;  // mode 1 without a callback: no host round trip needed
       if (int rc = fetch_decomp(op, k, out, status)) return rc;
-      if (status != tpl::ST_RUNNING) break;
-      if (cb && out.steps == j + 1) {
+      // the reference calls the callback after EVERY completed step, also the one whose beta is <= tol, and only then
+      // looks at the breakdown (lanczos.rs:93-112); a zero b never completes a step
+      if (cb && status != tpl::ST_ZERO_B && out.steps == j + 1) {
         if (!cb(out.steps, V_dev, ldv, out.alphas.data(), out.betas.data(), user)) break;
       }
+      if (status != tpl::ST_RUNNING) break;
     }
     CUDA_TRY(cudaEventRecord(op->ev[1], op->stream));
     if (int rc = fetch_decomp(op, k, out, status)) return rc;

@@ -55,7 +55,8 @@ bool read_file(const char* path, std::string& out, std::string& why) {
   return ok;
 }
 
-// iterates `BufRead::lines()`: split at '\n', drop one trailing '\r'
+// iterates `BufRead::lines()`: split at '\n'; a '\r' goes only as part of a "\r\n" terminator (a last line that has no
+// '\n' keeps its trailing '\r', which then fails `parse::<usize>()` / `parse::<f64>()` as in the reference)
 struct LineCursor {
   const char* p;
   const char* end;
@@ -65,21 +66,26 @@ struct LineCursor {
     b = p;
     e = nl ? nl : end;
     p = nl ? nl + 1 : end;
-    if (e > b && e[-1] == '\r') --e;
+    if (nl && e > b && e[-1] == '\r') --e;
     return true;
   }
 };
 
+// core::str::from_utf8: shortest-form encodings of scalar values only (C0/C1 and F5..FF never start a character, no
+// overlong 3- / 4-byte forms, no surrogates, nothing above U+10FFFF)
 bool utf8_ok(const char* b, const char* e) {
   const unsigned char* s = reinterpret_cast<const unsigned char*>(b);
   size_t n = size_t(e - b), i = 0;
   while (i < n) {
     unsigned char c = s[i];
     if (c < 0x80) { ++i; continue; }
-    size_t len = (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 0;
+    size_t len = (c >= 0xC2 && c <= 0xDF) ? 2 : (c >> 4) == 0xE ? 3 : (c >= 0xF0 && c <= 0xF4) ? 4 : 0;
     if (!len || i + len > n) return false;
     for (size_t k = 1; k < len; ++k)
       if ((s[i + k] >> 6) != 0x2) return false;
+    const unsigned char c1 = s[i + 1];
+    if ((c == 0xE0 && c1 < 0xA0) || (c == 0xED && c1 >= 0xA0) || (c == 0xF0 && c1 < 0x90) || (c == 0xF4 && c1 >= 0x90))
+      return false;
     i += len;
   }
   return true;

@@ -28,6 +28,21 @@ class LinOp:
 
     def __init__(self, handle: C.c_void_p):
         self._h = handle
+        self._stream = None  # None = the handle's own stream; else the cudaStream_t it was given
+
+    def _vec(self, v):
+        """`_vec_ptr` plus the two checks a bare pointer cannot carry: the vector has nrows() entries (else the reference's
+        DimensionMismatch, src/error.rs:29-35) and, for a CUDA tensor, the handle works on torch's CURRENT stream so that
+        it is ordered after the kernels that produced the tensor and before the ones that will consume the result."""
+        ptr, keep, is_torch = _vec_ptr(v)
+        _lib.check(_lib.load().tpl_op_check_len(self._h, int(keep.numel()) if is_torch else int(keep.shape[0])))
+        if is_torch and keep.is_cuda:
+            import torch
+
+            cur = int(torch.cuda.current_stream(keep.device).cuda_stream)
+            if self._stream != cur:
+                self.set_stream(cur)
+        return ptr, keep, is_torch
 
     # -- construction ---------------------------------------------------------------------------
     @classmethod
@@ -80,7 +95,7 @@ class LinOp:
         return self.FORMAT.get(_lib.load().tpl_op_format(self._h), "?")
 
     def apply(self, x):
-        xp, keep, is_torch = _vec_ptr(x)
+        xp, keep, is_torch = self._vec(x)
         if is_torch and keep.is_cuda:
             y = keep.new_empty(keep.shape)
             _lib.check(_lib.load().tpl_op_apply(self._h, xp, C.c_void_p(y.data_ptr())))
@@ -92,6 +107,7 @@ class LinOp:
     # -- engine knobs / introspection -----------------------------------------------------------------
     def set_stream(self, cuda_stream: int):
         _lib.check(_lib.load().tpl_op_set_stream(self._h, C.c_void_p(cuda_stream)))
+        self._stream = int(cuda_stream)
 
     def set_mode(self, mode: int):
         _lib.check(_lib.load().tpl_op_set_mode(self._h, mode))

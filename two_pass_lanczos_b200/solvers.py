@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import FTK_FN
-from .operators import LinOp, _vec_ptr
+from .operators import LinOp
 
 # Host f(T_k) e1 solvers implemented in the library (C++); usable wherever a closure is expected.
 INV, EXP, SQUARE = "inv", "exp", "square"
@@ -42,7 +42,7 @@ def _wrap_closure(f_tk_solver, errors: list):
 
 
 def _solve(entry: str, operator: LinOp, b, k: int, f_tk_solver):
-    bp, keep, is_torch = _vec_ptr(b)
+    bp, keep, is_torch = operator._vec(b)
     n = operator.nrows()
     if is_torch and keep.is_cuda:
         x = keep.new_empty(n)
@@ -96,7 +96,7 @@ def lanczos_two_pass_inv_adaptive(operator: LinOp, b, k_max: int, rtol: float):
     """A x = b with the number of steps chosen from the residual estimates of ONE pass 1: returns
     (x, k_used, residual_estimate).  k_used is the first j <= k_max whose estimate is <= rtol ||b|| (else the best j);
     pass 2 regenerates only k_used basis vectors."""
-    bp, keep, is_torch = _vec_ptr(b)
+    bp, keep, is_torch = operator._vec(b)
     n = operator.nrows()
     if is_torch and keep.is_cuda:
         x = keep.new_empty(n)
