@@ -67,20 +67,9 @@ def ortho_horizon(V: np.ndarray, thresh: float = 1e-8) -> int:
 
 def stability_spectrum(n: int, func: str, scenario: str) -> np.ndarray:
     """diagonal spectra of src/bin/stability.rs:98-146 (identical in orthogonality.rs:91-146)."""
-    i = np.arange(n, dtype=np.float64)
-    d = float(max(n - 1, 1))
-    if func == "exp" and scenario == "well":
-        return -10.0 + (9.9 / d) * i
-    if func == "exp" and scenario == "ill":
-        return -1000.0 + (999.9 / d) * i
-    if func == "inv" and scenario == "well":
-        return 0.1 + (99.9 / d) * i
-    if func == "inv" and scenario == "ill":
-        mid = n // 2
-        e = np.where(i < mid, 0.1 + (0.9 / max(mid - 1, 1)) * i, -1.0 + (0.9 / max(n - mid - 1, 1)) * (i - mid))
-        e[mid] = 1e-8
-        return e
-    raise ValueError((func, scenario))
+    from two_pass_lanczos_b200 import experiments
+
+    return experiments.diagonal_spectrum(n, func, scenario)
 
 
 def published_curves() -> dict:
@@ -105,6 +94,15 @@ def check_accuracy_row(curve: str, k: int, published: float, measured: float) ->
         assert abs(measured - published) <= ACCURACY_RTOL[curve] * published, (curve, k, published, measured)
     else:
         assert measured <= 20.0 * ACCURACY_FLOOR, (curve, k, published, measured)
+
+
+def cpu_spread(inst: datagen.KKTInstance, b: np.ndarray, k: int, x_cpu: np.ndarray, ftk=None) -> float:
+    """How far two LEGITIMATE CPU evaluations of the same reference path differ on this problem: the numpy restatement (CSR row
+    sums, pairwise dot products) against the C++ oracle's x.  On converged, well-conditioned problems this is ~1e-15; on an
+    ill-conditioned or unconverged one (50 k arcs 'aa' at k = 500: 2e-5) it is the sensitivity of x to the last bit of the
+    summation order, which no implementation -- faer included -- can be asked to beat."""
+    a_sp = npo.kkt_matrix(inst.m, inst.p, inst.tail.astype(np.int64), inst.head.astype(np.int64), inst.d)
+    return rel(npo.lanczos_two_pass(a_sp, b, k, ftk or npo.inv_tk_solver), x_cpu)
 
 
 FTK = {"inv": npo.inv_tk_solver, "exp": npo.exp_tk_solver, "square": npo.square_tk_solver}
