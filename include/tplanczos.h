@@ -147,11 +147,14 @@ uint64_t tpl_op_device_bytes(const tpl_op* op);
  * per-SM slice of the operator fits (2-D cell partition first, contiguous chunks second), streaming otherwise;
  * 1 = one cooperative launch per Lanczos step (streaming kernels; what a step callback uses); 2 = persistent streaming
  * kernels with tiled node sums even when a resident shape would fit; 3 = streaming kernels with gathered node rows;
- * 4 = chunk-resident kernels even when the cell partition would fit.  All modes run the same per-element arithmetic;
+ * 4 = chunk-resident kernels even when the cell partition would fit; 5 = blocked streaming kernels (node-block partition,
+ * cell-order vectors, bulk-copy input ring) even when a resident shape would fit.  In mode 0 the streaming regime prefers
+ * the blocked kernels over the tiled ones.  All modes run the same per-element arithmetic;
  * they differ in the (fixed) order in which a node row is summed, i.e. by rounding only. */
 int tpl_op_set_mode(tpl_op* op, int mode);
-/* Name of the kernel family a whole-pass solve through this handle runs: "cells", "chunks", "tiled", "gather", "csr" or
- * "sharded" (static string). */
+/* Name of the kernel family a whole-pass solve through this handle runs: "cells", "chunks", "blocked", "tiled", "gather",
+ * "csr", "dense", "sharded" (NCCL phase kernels), "sharded-fused" (tiled kernels spanning all ranks) or "sharded-blocked"
+ * (blocked kernels spanning all ranks) (static string). */
 const char* tpl_op_kernel_shape(const tpl_op* op);
 /* Host-only: builds the tile entry lists of the tiled streaming kernels for `ctas` CTAs and tiles of `tile_arcs` arcs on
  * `threads` host threads (0 = automatic) and checks them (every non-loop arc once on its head and once on its tail node
@@ -159,6 +162,15 @@ const char* tpl_op_kernel_shape(const tpl_op* op);
  * entries incl. padding, pieces, padding entries, longest per-thread list, hash of the lists, fold threads}. */
 int tpl_tiles_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, uint32_t tile_arcs, int threads,
                    uint64_t stats[8]);
+/* Host-only: builds the blocked streaming layout (2-D node-block partition, cell-order operator, tile lists over local node
+ * ids) for a grid of at most `ctas` CTAs with `smem_limit` bytes of shared memory each, on `threads` host threads (0 =
+ * automatic), and checks it (gidx a bijection, every packed tail/head word decodes to its arc, cells sorted by tail and
+ * padded to whole stages, every non-loop arc once on its tail and once on its head in the lists of its tile).
+ * stats = {fits, tail blocks, head blocks, largest tail block, largest head block, padded arcs, tile arcs, tiles of the
+ * largest cell, ring slots (pass 1 | pass 2 << 8 | pass 2 with basis << 16), largest cell, smallest cell, list entries incl.
+ * padding, pieces, hash of the layout, check code (0 = consistent), shared-memory bytes (pass 2)}. */
+int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len, int ctas,
+                    size_t smem_limit, int threads, uint64_t stats[16]);
 /* Diagnostics (host only, no device needed): builds the 2-D cell partition the resident kernels would use on a grid
  * of `ctas` CTAs with `smem_limit` bytes of shared memory each and checks its tables on the host.
  * stats = {fits, tail blocks, head blocks, arc slots per cell, node lines, most entry rows, most node-sum groups,

@@ -29,7 +29,7 @@ def main():
     ident = sharding.broadcast_unique_id(dist, rank)
     op = sharding.sharded_linop(m, p, inst.tail, inst.head, inst.d, rank, world, ident, device=local,
                                dist=dist if fused else None)
-    assert op.kernel_shape() == ("sharded-fused" if fused and world > 1 else "sharded")
+    assert op.kernel_shape() in (("sharded-blocked", "sharded-fused") if fused and world > 1 else ("sharded",))
     lo, hi = op.arc_lo, op.arc_hi
     info = op.shard_info()
     assert info == {"rank": rank, "world": world, "local_arcs": hi - lo, "nodes": p}

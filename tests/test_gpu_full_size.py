@@ -40,13 +40,13 @@ def test_headline_two_pass_residual_and_variants(headline):
 
 def test_kernel_shapes_by_size(headline):
     """The headline instance runs on the cell kernels; 650k arcs (cells too large) on the chunk-resident or the tiled ones,
-    whichever fits; 2M arcs on the tiled streaming ones; every mode switch reports what it selects."""
+    whichever fits; 2M arcs on the blocked streaming ones; every mode switch reports what it selects."""
     inst, gop, b = headline
     assert gop.kernel_shape() == "cells"
-    for mode, shape in ((4, "chunks"), (2, "tiled"), (3, "gather"), (1, "gather"), (0, "cells")):
+    for mode, shape in ((4, "chunks"), (5, "blocked"), (2, "tiled"), (3, "gather"), (1, "gather"), (0, "cells")):
         gop.set_mode(mode)
         assert gop.kernel_shape() == shape
-    for m, shapes in ((650_000, ("chunks", "tiled")), (2_000_000, ("tiled",))):
+    for m, shapes in ((650_000, ("chunks", "blocked")), (2_000_000, ("blocked",))):
         big = datagen.gen_kkt(m, 3, 2, "wc")
         op = tpl.LinOp.from_kkt(big.m, big.p, big.tail, big.head, big.d)
         assert op.kernel_shape() in shapes, op.kernel_shape()
@@ -114,7 +114,7 @@ def test_headline_k500_matches_oracle(headline):
     assert helpers.rel(helpers.project_out_null(x_gpu, inst.m, inst.p), helpers.project_out_null(x_cpu, inst.m, inst.p)) <= 1e-10
     x1_gpu = tpl.lanczos(gop, b, k, "inv")
     assert helpers.rel(x1_gpu, x_cpu) <= 1e-10
-    for shape_mode in (2, 3):  # the tiled streaming kernels and the gather kernels on the same instance
+    for shape_mode in (5, 2, 3):  # the blocked and the tiled streaming kernels and the gather kernels on the same instance
         gop.set_mode(shape_mode)
         assert helpers.rel(tpl.lanczos_two_pass(gop, b, k, "inv"), x_cpu) <= 1e-10, shape_mode
     gop.set_mode(0)

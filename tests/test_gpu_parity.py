@@ -24,18 +24,22 @@ def golden_instances():
     return sorted(glob.glob(os.path.join(helpers.GOLDEN, "netgen1000", "*.dmx")))
 
 
-# incidence operator in its four execution shapes (tpl_op_set_mode): shared-memory resident on the 2-D cell partition
-# (default at these sizes), resident on contiguous chunks, streaming with tiled node sums (what large instances use),
-# streaming with gathered node rows (generic fallback)
-FORMATS = ["incidence", "incidence-chunks", "incidence-tiled", "incidence-gather", "csr"]
+# incidence operator in its five execution shapes (tpl_op_set_mode): shared-memory resident on the 2-D cell partition
+# (default at these sizes), resident on contiguous chunks, blocked streaming (node-block partition, cell-order vectors,
+# bulk-copy input ring: what large instances use), streaming with tiled node sums, streaming with gathered node rows
+# (generic fallback)
+FORMATS = ["incidence", "incidence-chunks", "incidence-blocked", "incidence-tiled", "incidence-gather", "csr"]
+MODES = {"incidence": 0, "incidence-chunks": 4, "incidence-blocked": 5, "incidence-tiled": 2, "incidence-gather": 3}
 
 
 def gpu_ops(inst):
     cp, ri, va = datagen.kkt_csc(inst)
     ops = {"csr": tpl.LinOp.from_csc(inst.n, cp, ri, va)}
-    for name, mode in (("incidence", 0), ("incidence-chunks", 4), ("incidence-tiled", 2), ("incidence-gather", 3)):
+    for name, mode in MODES.items():
         ops[name] = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d)
         ops[name].set_mode(mode)
+        if name == "incidence-blocked":
+            assert ops[name].kernel_shape() == "blocked"
     return ops
 
 
@@ -163,7 +167,7 @@ def test_golden_fixtures_through_the_loader(dmx, flavour, ext, fmt, golden_dir):
     key = f"{os.path.basename(dmx)[:-4]}.{flavour}"
     kkt = data_loader.load_kkt_system(dmx, dmx[:-3] + ext, fmt=fmt.split("-")[0])
     assert kkt.a.format == fmt.split("-")[0]
-    kkt.a.set_mode({"incidence-chunks": 4, "incidence-tiled": 2, "incidence-gather": 3}.get(fmt, 0))
+    kkt.a.set_mode(MODES.get(fmt, 0))
     assert [kkt.num_nodes, kkt.num_arcs] == list(g[key + ".nnz"][1:])
     b = g[key + ".b"]
     dec = alg.lanczos_pass_one(kkt.a, b, 30)
@@ -238,7 +242,7 @@ def test_device_resident_vectors():
     assert np.array_equal(y.cpu().numpy(), gop.apply(b))
 
 
-@pytest.mark.parametrize("fmt", ["incidence", "incidence-chunks", "incidence-tiled", "incidence-gather"])
+@pytest.mark.parametrize("fmt", ["incidence", "incidence-chunks", "incidence-blocked", "incidence-tiled", "incidence-gather"])
 def test_irregular_random_graph(fmt):
     """Arcs in no particular order, self-loops, parallel arcs, isolated nodes and a short D (the loader's quirk): every
     execution shape of the incidence operator against the oracle on the same triplets."""
@@ -257,7 +261,7 @@ def test_irregular_random_graph(fmt):
         m + p, m + p, np.concatenate([j, m + t, m + h, j, j]), np.concatenate([j, j, j, m + t, m + h]),
         np.concatenate([d, ones, -ones, ones, -ones]))
     gop = tpl.LinOp.from_kkt(m, p, tail, head, d[: m - 500])
-    gop.set_mode({"incidence-chunks": 4, "incidence-tiled": 2, "incidence-gather": 3}.get(fmt, 0))
+    gop.set_mode(MODES.get(fmt, 0))
     x = rng.standard_normal(m + p)
     assert helpers.rel(gop.apply(x), oop.apply(x)) < 1e-14
     b = helpers.seeded_b(m + p)

@@ -1,0 +1,617 @@
+// tpl_blocks.cuh -- BLOCKED streaming kernels of the KKT incidence operator: the 2-D node-block partition of the cell
+// kernels (tpl_cells.cuh) applied to the streaming regime, with an asynchronous bulk-copy input ring.
+//
+// Why: the tiled kernels of tpl_tiles.cuh keep two p-long f64 arrays (node values, node accumulators) in
+// shared memory -- 184 KB at 50M arcs -- which leaves 2048-arc tiles, and they stage six input streams through registers
+// with 2 arcs per thread in flight.  Both made pass 2 latency-bound at 0.59 of the HBM roofline.  Here
+//   * the nodes are cut into GR contiguous TAIL blocks (balanced by out-degree) and GC contiguous HEAD blocks (balanced by
+//     in-degree); CTA (r, c) owns the arcs with tail in block r and head in block c.  It therefore stages only the node
+//     values of two blocks (p/GR + p/GC instead of p) and accumulates only their sums: 31 KB instead of 184 KB at 50M arcs;
+//   * the operator (d, packed local tail/head word) and the arc part of every Lanczos vector live in HBM in CELL ORDER
+//     (cell after cell, inside a cell by tail, every cell padded to a multiple of 128 arcs); b is gathered into that order
+//     once at the start of a pass and x scattered back once at its end (gidx);
+//   * the sweeps that also fold node sums (phase B of pass 1, the single sweep of pass 2) read their inputs through a ring
+//     of shared-memory slots filled by cp.async.bulk (global -> shared, completion on an mbarrier): every compute warp owns
+//     kBRing slots of 128 arcs, its lane 0 issues the bulk copies of stage k + ring as soon as stage k is consumed.  No
+//     registers are tied up by loads in flight (3 x 8 x 4.6 KB = 110 KB per SM in pass 2);
+//   * the node sums of a tile are folded by the fold warps exactly as in tpl_tiles.cuh (same list format, over LOCAL node
+//     ids: tails [0, PT), heads [PT, PT + PH)), tiles of up to 4096 arcs;
+//   * per step a CTA publishes PT + PH partial sums, destination-indexed: the owner of a node row finds the GC + GR
+//     contributions of every rank in consecutive words and adds them in a fixed order.  A node collects 24 partials per
+//     rank instead of 148, and a sharded operator moves 24 p doubles per rank per step over NVLink instead of 148 p.
+// Arithmetic: the same per-element expressions as every other shape (rec_sub, the reference's CSC order inside an arc row,
+// lazy scaling by the rounded reciprocal); pass 1, the one-pass variant and pass 2 share the lists and therefore regenerate
+// bit-identical vectors.  alpha / beta differ from the other shapes by rounding only (different fixed summation order).
+#pragma once
+#include "tpl_tiles.cuh"
+
+namespace tpl {
+
+constexpr int kBStage = 128;                 // arcs of one warp-stage (4 per lane)
+constexpr int kBComputeWarps = kStreamWarps; // warps 0..7 compute, warps 8..15 fold (as in tpl_tiles.cuh)
+constexpr int kBMaxRing = 4;
+constexpr uint32_t kBLoop = 0x80000000u;     // th word: self-loop or padding (no incidence entries)
+constexpr uint32_t kBTailFirst = 0x40000000u;  // th word: global tail index < global head index (CSC accumulation order)
+constexpr uint32_t kBPad = 0xffffffffu;      // gidx of a padding slot
+
+struct BlockOp {
+  uint32_t GR, GC;   // tail blocks x head blocks; the grid has GR * GC CTAs, CTA c = r * GC + cc
+  uint32_t PT, PH;   // largest tail / head block: local node ids are tails [0, PT), heads [PT, PT + PH)
+  uint32_t Mpad;     // arcs in cell order, padding included; the node part of a cell-order vector starts here
+  uint32_t ring1, ring2, ring2v;  // ring slots per compute warp: pass 1, pass 2, pass 2 with a basis
+  uint32_t m;        // arcs in natural order (node part of a natural-order vector starts here)
+  const uint32_t* cell_off;  // [G + 1] first cell-order position of every cell (multiples of kBStage)
+  const uint32_t* tbs;       // [GR + 1] first node of every tail block
+  const uint32_t* hbs;       // [GC + 1] first node of every head block
+  const double* d;           // [Mpad] quadratic costs in cell order (0 in padding and beyond the loader's short D)
+  const uint32_t* th;        // [Mpad] tail_local | head_local << 15 | kBTailFirst | kBLoop
+  const uint32_t* gidx;      // [Mpad] natural arc index of a cell-order position (kBPad in padding)
+  double* xc;                // [Mpad] arc part of x in cell order (pass 2 workspace)
+  TileOp tl;                 // tile lists over local node ids (T, ntile, thdr, lent, piece), R, and the exchange buffers:
+                             // tl.fab.partials[rank] is [2][Bp][world * (GC + GR)], destination-indexed
+};
+
+struct BlockSmem {
+  SmArr node, acc, wt;
+  uint32_t wt_stride;
+  uint32_t ring;   // shared-window address of the slot area: [compute warp][slot][slot_bytes]
+  uint32_t mbar;   // [compute warp][kBMaxRing] mbarriers
+};
+__host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4; }
+// pass 1 never needs node values and accumulators at the same time (they alias), pass 2 needs both
+__host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, bool pass2, bool with_v) {
+  const size_t slot = pass2 ? block_slot_bytes(4, with_v ? 2 : 1) : block_slot_bytes(2, 0);
+  return ((pass2 ? 2 : 1) * (size_t)PL + 2 * ((size_t)T + kMaxPieces)) * sizeof(double) + (size_t)kBComputeWarps * ring * slot +
+         (size_t)kBComputeWarps * kBMaxRing * 8 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
+}
+__device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, bool pass2) {
+  // bulk copies need 16-byte aligned shared-memory addresses: PL and T + kMaxPieces are even (host), the base is rounded up
+  const uint32_t b = ((uint32_t)__cvta_generic_to_shared(base) + 15u) & ~15u;
+  BlockSmem s;
+  s.node.a = b;
+  s.acc.a = pass2 ? b + PL * 8u : b;
+  s.wt.a = s.acc.a + PL * 8u;
+  s.wt_stride = (T + kMaxPieces) * 8u;
+  s.mbar = s.wt.a + 2u * s.wt_stride;
+  s.ring = s.mbar + kBComputeWarps * kBMaxRing * 8u;
+  return s;
+}
+
+// ---------------------------------------------------------------------------- mbarrier / bulk-copy primitives (PTX)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  unsigned int spins = 0;
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > kSpinLimit) __trap();  // a bulk copy that never lands must not hang the GPU
+  }
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+// orders this thread's earlier generic-proxy accesses (st.global of a vector, ld.shared of a ring slot) before later
+// async-proxy accesses (the bulk copies that re-read that vector / refill that slot)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ double sm_ld_at(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t sm_ld_u32_at(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// (A x)_j of an arc row in the reference's CSC accumulation order (arc_row of tpl_kernels.cuh with the order and the
+// self-loop test precomputed in the th word)
+__device__ __forceinline__ double arc_row_b(double dj, double xj, uint32_t th, double xt, double xh) {
+  double acc = __dmul_rn(dj, xj);
+  if (th & kBLoop) {
+  } else if (th & kBTailFirst) {
+    acc = __dadd_rn(acc, xt);
+    acc = __dsub_rn(acc, xh);
+  } else {
+    acc = __dsub_rn(acc, xh);
+    acc = __dadd_rn(acc, xt);
+  }
+  return acc;
+}
+
+struct BlockCtx {
+  uint32_t r, cc;     // this CTA's tail / head block
+  uint32_t c0, c1;    // its cell-order range (c1 - c0 is a multiple of kBStage)
+  uint32_t t0, nt;    // first node and size of its tail block
+  uint32_t h0, nh;    // first node and size of its head block
+  uint32_t ulo, uhi;  // node rows it owns
+  uint32_t nst;       // stages of the cell
+  uint32_t ntiles;    // tiles of the cell
+};
+__device__ __forceinline__ BlockCtx block_ctx(const BlockOp& bo, uint32_t p) {
+  BlockCtx c;
+  c.r = blockIdx.x / bo.GC;
+  c.cc = blockIdx.x % bo.GC;
+  c.c0 = __ldg(bo.cell_off + blockIdx.x);
+  c.c1 = __ldg(bo.cell_off + blockIdx.x + 1);
+  c.t0 = __ldg(bo.tbs + c.r);
+  c.nt = __ldg(bo.tbs + c.r + 1) - c.t0;
+  c.h0 = __ldg(bo.hbs + c.cc);
+  c.nh = __ldg(bo.hbs + c.cc + 1) - c.h0;
+  c.ulo = min(p, (bo.tl.fab.rank * gridDim.x + blockIdx.x) * bo.tl.R);
+  c.uhi = min(p, c.ulo + bo.tl.R);
+  c.nst = (c.c1 - c.c0) / kBStage;
+  c.ntiles = (c.c1 - c.c0 + bo.tl.T - 1) / bo.tl.T;
+  return c;
+}
+
+// node values of the CTA's two blocks -> s.node (local ids), scaled by `sc` (one rounding, the reference's in-place scaling)
+__device__ __forceinline__ void stage_block_nodes(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, const double* Xnode, double sc) {
+  for (uint32_t i = threadIdx.x; i < c.nt; i += kBlock) sm_st(s.node, i, __dmul_rn(__ldcg(Xnode + c.t0 + i), sc));
+  for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) sm_st(s.node, bo.PT + i, __dmul_rn(__ldcg(Xnode + c.h0 + i), sc));
+}
+__device__ __forceinline__ void zero_block_acc(const BlockOp& bo, const BlockSmem& s) {
+  for (uint32_t i = threadIdx.x; i < bo.PT + bo.PH; i += kBlock) sm_st(s.acc, i, 0.0);
+}
+
+// This CTA's partial sums (s.acc) -> the owners' buffers, parity `par`.  Destination-indexed: node u of rank rk keeps
+// world * (GC + GR) consecutive words; rank s, cell (r, cc) writes the tail side of its nodes to word s * (GC + GR) + cc and
+// the head side to word s * (GC + GR) + GC + r.  Every word is written exactly once per step (a cell writes all nodes of
+// its two blocks, zeros included), so nothing has to be cleared.  Caller synchronised before.
+__device__ __forceinline__ void publish_block_partials(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t par) {
+  const Fabric& f = bo.tl.fab;
+  const uint32_t per = bo.GC + bo.GR, SL = f.world * per;
+  for (uint32_t i = threadIdx.x; i < c.nt; i += kBlock) {
+    const uint32_t u = c.t0 + i, rk = u / f.Bp;
+    __stcg(f.partials[rk] + ((size_t)par * f.Bp + (u - rk * f.Bp)) * SL + f.rank * per + c.cc, sm_ld(s.acc, i));
+  }
+  for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) {
+    const uint32_t u = c.h0 + i, rk = u / f.Bp;
+    __stcg(f.partials[rk] + ((size_t)par * f.Bp + (u - rk * f.Bp)) * SL + f.rank * per + bo.GC + c.r, sm_ld(s.acc, bo.PT + i));
+  }
+}
+// T_u = sum of the world * (GC + GR) partials of an owned node: lanes stride the words, xor tree -- a fixed order
+__device__ __forceinline__ double block_node_total(const BlockOp& bo, uint32_t par, uint32_t u, int lane) {
+  const Fabric& f = bo.tl.fab;
+  const uint32_t SL = f.world * (bo.GC + bo.GR);
+  const double* Pin = f.partials[f.rank] + ((size_t)par * f.Bp + (u - f.rank * f.Bp)) * SL;
+  double a = 0.0;
+  for (uint32_t q = lane; q < SL; q += 32) a = __dadd_rn(a, __ldcg(Pin + q));
+  return warp_sum(a);
+}
+
+// ---------------------------------------------------------------------------- the folding sweep
+// One sweep over the CTA's cell that produces a new arc vector AND its node sums.  Compute warp w owns the stages
+// g = w, w + 8, w + 16, ... of the cell (a stage = 128 consecutive cell-order arcs) and a private ring of RING slots; lane 0
+// issues the bulk copies of N8 8-byte arrays and N4 4-byte arrays per stage.  `consume(pos, slot, wt_addr, lane)` handles
+// the arcs pos + lane + 32 q (q < 4): it reads array a of the slot at slot + a * 1024 (+ 8 * index) (4-byte arrays behind
+// the 8-byte ones), stores its results to global memory and the new arc value of arc q to wt_addr + 8 * (lane + 32 q).
+// A tile (T arcs) is complete when all compute warps have arrived; the fold warps then add its node sums into s.acc while
+// the compute warps fill the other tile buffer (named barriers as in tile_loop).  `kbase` counts the stages this warp has
+// consumed since the kernel started: slot and mbarrier parity follow from it, the mbarriers are initialised once.
+template <int N8, int N4, class CONSUME>
+__device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, int RING, uint32_t slot_bytes,
+                                           const double* const (&src8)[N8], const uint32_t* const (&src4)[N4 ? N4 : 1],
+                                           CONSUME consume, uint32_t& kbase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t SPT = bo.tl.T / kBStage;  // stages per tile (a multiple of 8)
+  if (warp < kBComputeWarps) {
+    const uint32_t nk = c.nst > (uint32_t)warp ? (c.nst - warp + kBComputeWarps - 1) / kBComputeWarps : 0;  // my stages
+    const uint32_t ring0 = s.ring + (uint32_t)warp * RING * slot_bytes, bar0 = s.mbar + (uint32_t)warp * kBMaxRing * 8u;
+    constexpr uint32_t kTx = N8 * kBStage * 8 + N4 * kBStage * 4;
+    auto issue = [&](uint32_t k) __attribute__((always_inline)) {  // lane 0 only
+      const uint32_t sl = (kbase + k) % RING, bar = bar0 + sl * 8u, dst = ring0 + sl * slot_bytes;
+      const size_t pos = (size_t)c.c0 + ((size_t)k * kBComputeWarps + warp) * kBStage;
+      mbar_expect_tx(bar, kTx);
+#pragma unroll
+      for (int a = 0; a < N8; ++a) bulk_g2s(dst + a * (kBStage * 8), src8[a] + pos, kBStage * 8, bar);
+#pragma unroll
+      for (int a = 0; a < N4; ++a) bulk_g2s(dst + N8 * (kBStage * 8) + a * (kBStage * 4), src4[a] + pos, kBStage * 4, bar);
+    };
+    if (lane == 0)
+      for (uint32_t k = 0; k < (uint32_t)RING && k < nk; ++k) issue(k);
+    uint32_t k = 0;
+    for (uint32_t t = 0; t < c.ntiles; ++t) {
+      if (t >= 2) bar_sync_n(kBarEmpty + (t & 1u), kBlock);  // the fold of tile t - 2 has left this buffer
+      const uint32_t wt0 = s.wt.a + (t & 1u) * s.wt_stride;
+      for (uint32_t i = 0; i < SPT / kBComputeWarps; ++i) {
+        const uint32_t g = t * SPT + i * kBComputeWarps + warp;
+        if (g >= c.nst) break;
+        const uint32_t sl = (kbase + k) % RING;
+        mbar_wait(bar0 + sl * 8u, ((kbase + k) / RING) & 1u);
+        consume(c.c0 + g * kBStage, ring0 + sl * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), lane);
+        __syncwarp();  // every lane has read its slot words
+        if (lane == 0 && k + RING < nk) issue(k + RING);
+        ++k;
+      }
+      bar_arrive_n(kBarFull + (t & 1u), kBlock);
+    }
+    kbase += nk;
+    // drain: every arrival of the fold warps is matched by a wait, so that the barriers are clean for the next sweep
+    for (uint32_t u = c.ntiles > 2 ? c.ntiles - 2 : 0; u < c.ntiles; ++u) bar_sync_n(kBarEmpty + (u & 1u), kBlock);
+    fence_proxy_async();  // the vector just written is bulk-copied by the next sweep (after the grid barrier in between)
+  } else {
+    const uint32_t tile0 = blockIdx.x * bo.tl.ntile;
+    const TileSmem ts{s.node, s.acc, s.wt, s.wt_stride};
+    TileHdr hdr = tile_hdr(bo.tl, tile0);
+    FoldRegs fr;
+    if (c.ntiles) {
+      fold_request(bo.tl, hdr, 0, fr.ent);
+      piece_request(bo.tl, hdr, fr.pc);
+    }
+    for (uint32_t t = 0; t < c.ntiles; ++t) {
+      TileHdr next = hdr;
+      if (t + 1 < c.ntiles) next = tile_hdr(bo.tl, tile0 + t + 1);
+      const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
+      bar_sync_n(kBarFull + (t & 1u), kBlock);
+      tile_node_sums(bo.tl, ts, wt, hdr, next, t + 1 < c.ntiles, fr);
+      bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
+      hdr = next;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void init_block_mbarriers(const BlockSmem& s) {
+  if (threadIdx.x < kBComputeWarps * kBMaxRing) mbar_init(s.mbar + threadIdx.x * 8u, 1);
+  fence_mbar_init();
+  __syncthreads();
+}
+
+// node partial sums of an arbitrary cell-order arc vector X over the CTA's cell (init: the un-normalised b)
+__device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, int RING, uint32_t slot_bytes,
+                                              const double* X, uint32_t& kbase) {
+  zero_block_acc(bo, s);
+  __syncthreads();
+  const double* const src8[1] = {X};
+  const uint32_t* const src4[1] = {nullptr};
+  fold_sweep<1, 0>(
+      bo, s, c, RING, slot_bytes, src8, src4,
+      [&](uint32_t, uint32_t slot, uint32_t wt, int lane) __attribute__((always_inline)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t e = (lane + 32 * q) * 8u;
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt + e), "d"(sm_ld_at(slot + e)) : "memory");
+        }
+      },
+      kbase);
+}
+
+// =============================================================================================
+// pass 1 / one-pass basis generation
+// =============================================================================================
+template <bool WITH_V>
+__global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const IncidenceOp op, const BlockOp bo, const Pass1Args a) {
+  extern __shared__ double smem[];
+  __shared__ CtaShared sh;
+  const uint32_t PL = bo.PT + bo.PH, p = op.p, m = bo.m, M = bo.Mpad;
+  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, false);
+  const BlockCtx c = block_ctx(bo, p);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int RING = (int)bo.ring1;
+  const uint32_t slot_bytes = (uint32_t)block_slot_bytes(2, 0);
+  const TileOp& to = bo.tl;
+  init_block_mbarriers(s);
+
+  unsigned int epoch = a.st->epoch;
+  uint32_t kbase = 0;
+  int steps = 0, status = ST_RUNNING, rot = 0;
+  double sc = 1.0, sp = 1.0, bp = 0.0, bnorm = 0.0;
+  GridSync gs = a.gs;
+  double* const buf0 = a.buf[0];
+  double* const buf1 = a.buf[1];
+  double* const buf2 = a.buf[2];
+  auto pick = [&](int r) { return r == 0 ? buf0 : (r == 1 ? buf1 : buf2); };
+  {
+    // K0: b gathered into cell order, ||b||, W_cur = b, W_prev = 0, partial node sums of b for step 0
+    double* Wp = pick(0);
+    double* Wc = pick(1);
+    double acc = 0.0;
+    for (uint32_t i = c.c0 + threadIdx.x; i < c.c1; i += kBlock) {
+      const uint32_t g = __ldg(bo.gidx + i);
+      const double bi = g != kBPad ? __ldg(a.b + g) : 0.0;
+      __stcg(Wc + i, bi);
+      __stcg(Wp + i, 0.0);
+      acc = fma(bi, bi, acc);
+    }
+    for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
+      const double bi = __ldg(a.b + m + u);
+      __stcg(Wc + M + u, bi);
+      __stcg(Wp + M + u, 0.0);
+      publish_node(to, p, 1, u, bi);  // parity of "step -1"
+      acc = fma(bi, bi, acc);
+    }
+    fence_proxy_async();
+    __syncthreads();  // the cell's share of W_cur is written (and fenced towards the async proxy) before it is bulk-copied
+    block_sums_of(bo, s, c, RING, slot_bytes, Wc, kbase);
+    publish_block_partials(bo, s, c, 0);
+    bnorm = sqrt(tile_sync<true>(acc, to, a.gs, epoch, sh));
+    if (bnorm <= a.tol) status = ST_ZERO_B;
+    sc = 1.0 / bnorm;
+  }
+  if (status == ST_RUNNING) {
+    for (int j = 0; j < a.j_end; ++j) {
+      const double* Wp = pick(rot);
+      const double* Wc = pick((rot + 1) % 3);
+      double* Wn = pick((rot + 2) % 3);
+      const double* Xnode = local_nodebuf(to, p, (j + 1) & 1);  // node part of the current vector (un-normalised)
+      double* Vcol = WITH_V ? a.V + (size_t)j * a.ldv : nullptr;
+
+      // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
+      stage_block_nodes(bo, s, c, Xnode, sc);
+      __syncthreads();
+      if (WITH_V) {  // node part of the basis column: replicated on every rank, each CTA writes its share
+        uint32_t vlo, vhi;
+        cta_chunk(p, vlo, vhi);
+        for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) __stcs(Vcol + m + u, __dmul_rn(__ldcg(Xnode + u), sc));
+      }
+      double acc = 0.0;
+      for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
+        const double t = __dmul_rn(sc, block_node_total(bo, j & 1, u, lane));
+        if (lane == 0) {
+          const double v = __dmul_rn(__ldcg(Xnode + u), sc);
+          const double vp = __dmul_rn(__ldcg(Wp + M + u), sp);
+          const double wt = rec_sub(t, bp, vp);
+          acc = fma(v, wt, acc);
+          __stcg(Wn + M + u, wt);
+        }
+      }
+      for (uint32_t base = c.c0; base < c.c1; base += kUnroll * kBlock) {
+        double wc[kUnroll], wp[kUnroll], dd[kUnroll];
+        uint32_t th[kUnroll], gi[kUnroll];
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = min(base + q * kBlock + threadIdx.x, c.c1 - 1);  // unconditional loads (see tpl_tiles.cuh)
+          wc[q] = __ldcg(Wc + i);
+          wp[q] = __ldcg(Wp + i);
+          dd[q] = __ldg(bo.d + i);
+          th[q] = __ldg(bo.th + i);
+          if (WITH_V) gi[q] = __ldg(bo.gidx + i);
+        }
+#pragma unroll
+        for (int q = 0; q < kUnroll; ++q) {
+          const uint32_t i = base + q * kBlock + threadIdx.x;
+          if (i < c.c1) {
+            const double v = __dmul_rn(wc[q], sc);
+            const double vp = __dmul_rn(wp[q], sp);
+            const double xt = sm_ld(s.node, th[q] & 0x7fffu), xh = sm_ld(s.node, bo.PT + ((th[q] >> 15) & 0x7fffu));
+            const double wt = rec_sub(arc_row_b(dd[q], v, th[q], xt, xh), bp, vp);
+            acc = fma(v, wt, acc);
+            __stcg(Wn + i, wt);
+            if (WITH_V)
+              if (gi[q] != kBPad) __stcs(Vcol + gi[q], v);
+          }
+        }
+      }
+      fence_proxy_async();  // w~ is bulk-copied by phase B
+      const double alpha = tile_sync<true, false>(acc, to, gs, epoch, sh);
+
+      // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
+      acc = 0.0;
+      zero_block_acc(bo, s);  // (aliases s.node: phase A is over)
+      for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
+        const double v = __dmul_rn(__ldcg(Wc + M + u), sc);
+        const double w = rec_sub(__ldcg(Wn + M + u), alpha, v);
+        __stcg(Wn + M + u, w);
+        publish_node(to, p, j & 1, u, w);
+        acc = fma(w, w, acc);
+      }
+      __syncthreads();  // accumulators are zero before the first fold
+      {
+        const double* const src8[2] = {Wn, Wc};
+        const uint32_t* const src4[1] = {nullptr};
+        fold_sweep<2, 0>(
+            bo, s, c, RING, slot_bytes, src8, src4,
+            [&](uint32_t pos, uint32_t slot, uint32_t wt, int ln) __attribute__((always_inline)) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t e = (ln + 32 * q) * 8u;
+                const double w = rec_sub(sm_ld_at(slot + e), alpha, __dmul_rn(sm_ld_at(slot + kBStage * 8 + e), sc));
+                __stcg(Wn + pos + ln + 32 * q, w);
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt + e), "d"(w) : "memory");
+                acc = fma(w, w, acc);
+              }
+            },
+            kbase);
+      }
+      publish_block_partials(bo, s, c, (j + 1) & 1);
+      const double beta = sqrt(tile_sync<true>(acc, to, gs, epoch, sh));
+
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.alphas[j] = alpha;
+        a.betas[j] = beta;
+      }
+      steps = j + 1;
+      if (beta <= a.tol) {
+        status = ST_BREAKDOWN;
+        break;
+      }
+      sp = sc;
+      sc = 1.0 / beta;
+      bp = beta;
+      rot = (rot + 1) % 3;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    State st;
+    st.s_cur = sc;
+    st.s_prev = sp;
+    st.beta_prev = bp;
+    st.b_norm = bnorm;
+    st.epoch = epoch;
+    st.rot = rot;
+    st.steps = steps;
+    st.status = status;
+    *a.st = st;
+  }
+}
+
+// =============================================================================================
+// pass 2: one sweep and one grid barrier per step
+// =============================================================================================
+template <bool WITH_V>
+__global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const IncidenceOp op, const BlockOp bo, const Pass2Args a) {
+  extern __shared__ double smem[];
+  __shared__ CtaShared sh;
+  const uint32_t PL = bo.PT + bo.PH, p = op.p, m = bo.m, M = bo.Mpad;
+  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, true);
+  const BlockCtx c = block_ctx(bo, p);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int RING = (int)(WITH_V ? bo.ring2v : bo.ring2);
+  const uint32_t slot_bytes = (uint32_t)block_slot_bytes(4, WITH_V ? 2 : 1);
+  const TileOp& to = bo.tl;
+  init_block_mbarriers(s);
+  uint32_t vlo, vhi;  // share of the (replicated) node part of x / V this CTA writes
+  cta_chunk(p, vlo, vhi);
+  unsigned int epoch = a.st->epoch;
+  uint32_t kbase = 0;
+  double* const buf0 = a.buf[0];
+  double* const buf1 = a.buf[1];
+  double* const buf2 = a.buf[2];
+  double* const xc = bo.xc;
+  auto pick = [&](int r) { return r == 0 ? buf0 : (r == 1 ? buf1 : buf2); };
+  int rot = 0;
+  double sc_cur = 1.0 / a.b_norm;  // scale of the vector whose un-normalised partial node sums are in `partials`
+  {
+    // v_1 = b * (1/||b||) gathered into cell order, x = y_0 v_1; partial node sums of the un-normalised b (scaled afterwards,
+    // exactly as pass 1 does with its lazily scaled w: bit-identical node rows)
+    const double inv = 1.0 / a.b_norm;
+    const double y0 = __ldg(a.y);
+    double* Vp = buf0;
+    double* Vc = buf1;
+    double* Braw = buf2;
+    for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
+      const double v = __dmul_rn(__ldg(a.b + m + u), inv);
+      __stcg(Vc + M + u, v);
+      __stcg(Vp + M + u, 0.0);
+      publish_node(to, p, 1, u, v);
+    }
+    for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
+      const double v = __dmul_rn(__ldg(a.b + m + u), inv);
+      __stcg(a.x + m + u, __dmul_rn(v, y0));
+      if (WITH_V) __stcs(a.V + m + u, v);
+    }
+    for (uint32_t i = c.c0 + threadIdx.x; i < c.c1; i += kBlock) {
+      const uint32_t g = __ldg(bo.gidx + i);
+      const double bi = g != kBPad ? __ldg(a.b + g) : 0.0;
+      const double v = __dmul_rn(bi, inv);
+      __stcg(Braw + i, bi);
+      __stcg(Vc + i, v);
+      __stcg(Vp + i, 0.0);
+      __stcg(xc + i, __dmul_rn(v, y0));
+      if (WITH_V)
+        if (g != kBPad) __stcs(a.V + g, v);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    block_sums_of(bo, s, c, RING, slot_bytes, Braw, kbase);
+    publish_block_partials(bo, s, c, 0);
+    tile_sync<false>(0.0, to, a.gs, epoch, sh);
+  }
+  for (int j = 0; j + 1 < a.steps; ++j) {
+    const double* Vp = pick(rot);
+    const double* Vc = pick((rot + 1) % 3);
+    double* Vn = pick((rot + 2) % 3);
+    const double* Xnode = local_nodebuf(to, p, (j + 1) & 1);
+    double* Vcol = WITH_V ? a.V + (size_t)(j + 1) * a.ldv : nullptr;
+    const double alpha = __ldg(a.alphas + j);
+    const double beta = __ldg(a.betas + j);
+    const double bp = j == 0 ? 0.0 : __ldg(a.betas + j - 1);
+    const double sinv = 1.0 / beta;
+    const double yj = __ldg(a.y + j + 1);
+
+    stage_block_nodes(bo, s, c, Xnode, 1.0);
+    zero_block_acc(bo, s);
+    if (j > 0) {
+      // the published node values are v_{j+1}, regenerated by the previous step: their share of x (and of the basis column)
+      // is added here, by every rank for its replica (each CTA its share of the nodes)
+      const double yprev = __ldg(a.y + j);
+      for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
+        const double vn = __ldcg(Xnode + u);
+        __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(yprev, vn)));
+        if (WITH_V) __stcs(a.V + (size_t)j * a.ldv + m + u, vn);
+      }
+    }
+    for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
+      const double t = __dmul_rn(sc_cur, block_node_total(bo, j & 1, u, lane));
+      if (lane == 0) {
+        const double w = rec_sub(rec_sub(t, bp, __ldcg(Vp + M + u)), alpha, __ldcg(Xnode + u));
+        const double vn = __dmul_rn(w, sinv);
+        __stcg(Vn + M + u, vn);
+        publish_node(to, p, j & 1, u, vn);
+      }
+    }
+    __syncthreads();  // node values are staged, accumulators are zero
+    {
+      const double* const src8[4] = {Vc, Vp, xc, bo.d};
+      const uint32_t* const src4[2] = {bo.th, bo.gidx};
+      const uint32_t* const src4n[1] = {bo.th};
+      auto body = [&](uint32_t pos, uint32_t slot, uint32_t wt, int ln) __attribute__((always_inline)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t e = (ln + 32 * q) * 8u, e4 = (ln + 32 * q) * 4u;
+          const double v = sm_ld_at(slot + e);
+          const double vp = sm_ld_at(slot + kBStage * 8 + e);
+          const double xx = sm_ld_at(slot + 2 * kBStage * 8 + e);
+          const double dd = sm_ld_at(slot + 3 * kBStage * 8 + e);
+          const uint32_t th = sm_ld_u32_at(slot + 4 * kBStage * 8 + e4);
+          const double xt = sm_ld(s.node, th & 0x7fffu), xh = sm_ld(s.node, bo.PT + ((th >> 15) & 0x7fffu));
+          const double w = rec_sub(rec_sub(arc_row_b(dd, v, th, xt, xh), bp, vp), alpha, v);
+          const double vn = __dmul_rn(w, sinv);
+          const uint32_t i = pos + ln + 32 * q;
+          __stcg(Vn + i, vn);
+          __stcg(xc + i, __dadd_rn(xx, __dmul_rn(yj, vn)));
+          if (WITH_V) {
+            const uint32_t g = sm_ld_u32_at(slot + 4 * kBStage * 8 + kBStage * 4 + e4);
+            if (g != kBPad) __stcs(Vcol + g, vn);
+          }
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt + e), "d"(w) : "memory");
+        }
+      };
+      if (WITH_V)
+        fold_sweep<4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, kbase);
+      else
+        fold_sweep<4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, kbase);
+    }
+    publish_block_partials(bo, s, c, (j + 1) & 1);
+    tile_sync<false>(0.0, to, a.gs, epoch, sh);
+    rot = (rot + 1) % 3;
+    sc_cur = sinv;
+  }
+  if (a.steps > 1) {  // node part of the last regenerated vector v_steps (published by the last step, parity (steps - 2) & 1)
+    const double* Xnode = local_nodebuf(to, p, (a.steps - 2) & 1);
+    const double ylast = __ldg(a.y + a.steps - 1);
+    for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
+      const double vn = __ldcg(Xnode + u);
+      __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(ylast, vn)));
+      if (WITH_V) __stcs(a.V + (size_t)(a.steps - 1) * a.ldv + m + u, vn);
+    }
+  }
+  // x back to natural order: every CTA scatters the arcs of its own cell
+  for (uint32_t i = c.c0 + threadIdx.x; i < c.c1; i += kBlock) {
+    const uint32_t g = __ldg(bo.gidx + i);
+    if (g != kBPad) __stcg(a.x + g, __ldcg(xc + i));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.st->epoch = epoch;
+}
+
+}  // namespace tpl

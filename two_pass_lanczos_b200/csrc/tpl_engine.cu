@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "tpl_internal.h"
+#include "tpl_blocks.cuh"
+#include "tpl_blocks_host.h"
 #include "tpl_cells_host.h"
 #include "tpl_dense.cuh"
 #include "tpl_kernels.cuh"
@@ -170,12 +172,17 @@ struct tpl_op {
   size_t cell_xchg_bytes = 0;
   bool tiled_ok = false;       // streaming kernels with tiled node sums are usable (shared-memory budget)
   tpl::TileOp tile{};
-  void* fab_block = nullptr;   // this rank's exchange buffers (partials | node values | slots), one allocation = one IPC handle
-  size_t fab_bytes = 0;
+  void* tile_block = nullptr;  // exchange buffers of the tiled kernels (partials | node values | slots)
+  void* blk_block = nullptr;   // exchange buffers of the blocked kernels
+  void* fab_block = nullptr;   // sharded handle: the exchange block of the family that runs fused (one allocation = one IPC handle)
   std::vector<void*> fab_peers;  // peer blocks opened through CUDA IPC
   bool fab_connected = false;  // world > 1 and every peer's block is mapped: the persistent tiled kernels span all ranks
   unsigned fab_epoch = 0;      // barrier epoch the next fused pass starts from (never reset: peers write into our slots)
   size_t smem_tile1 = 0, smem_tile2 = 0;
+  bool blocked_ok = false;     // blocked streaming kernels (tpl_blocks.cuh): 2-D node-block partition, cell-order vectors
+  tpl::BlockOp blk{};
+  size_t smem_blk1 = 0, smem_blk2 = 0, smem_blk2v = 0;
+  double* bbuf[3] = {nullptr, nullptr, nullptr};  // the three rotating vectors in cell order: [Mpad arcs | p nodes]
   double* h_pin = nullptr;  // pinned mirror of coef_d
   double* V_int = nullptr;
   size_t V_int_elems = 0;
@@ -359,30 +366,48 @@ int ensure_coef(tpl_op* op, size_t k) {
   return TPL_OK;
 }
 
-// (Re)allocates this rank's exchange block of the tiled kernels for `world` ranks and points the fabric at it.
-int setup_fabric(tpl_op* op, int rank, int world) {
-  const size_t p = op->inc.p, G = (size_t)op->G;
-  tpl::Fabric& f = op->tile.fab;
-  if (op->fab_block) {
-    if (int rc = dev_free(op, op->fab_block)) return rc;
-    op->fab_block = nullptr;
+// Exchange block of one kernel family (partial node sums | node values | barrier slots) for `world` ranks; every family
+// has a local one (world = 1: the single-GPU kernels are the fused path with one rank).  The fused multi-GPU passes run on
+// ONE family per handle -- the blocked streaming kernels when their layout exists, else the tiled ones -- whose block is
+// then re-allocated for `world` ranks and exported (op->fab_block).
+tpl::Fabric& active_fabric(tpl_op* op) { return op->blocked_ok ? op->blk.tl.fab : op->tile.fab; }
+void fabric_layout(const tpl_op* op, bool blocked, const tpl::Fabric& f, size_t& part, size_t& nodes) {
+  part = blocked ? 2 * (size_t)f.Bp * f.world * (op->blk.GC + op->blk.GR) : 2 * (size_t)f.Gtot * f.Bp;
+  nodes = 2 * (size_t)op->inc.p + 2;
+}
+int alloc_fabric(tpl_op* op, bool blocked, int rank, int world, void** block_slot) {
+  const size_t p = op->inc.p;
+  const size_t G = blocked ? (size_t)op->blk.GR * op->blk.GC : (size_t)op->G;  // CTAs of the kernels that use it
+  tpl::Fabric& f = blocked ? op->blk.tl.fab : op->tile.fab;
+  if (*block_slot) {
+    if (int rc = dev_free(op, *block_slot)) return rc;
+    *block_slot = nullptr;
   }
-  op->tile.R = (uint32_t)std::max<size_t>(1, (p + (size_t)world * G - 1) / ((size_t)world * G));
+  const uint32_t R = (uint32_t)std::max<size_t>(1, (p + (size_t)world * G - 1) / ((size_t)world * G));
+  (blocked ? op->blk.tl.R : op->tile.R) = R;
   f = tpl::Fabric{};
   f.rank = rank;
   f.world = world;
   f.Gtot = (uint32_t)(world * G);
-  f.Bp = (uint32_t)(G * op->tile.R);
-  const size_t part = 2 * (size_t)f.Gtot * f.Bp, nodes = 2 * p + 2;
+  f.Bp = (uint32_t)(G * R);
+  size_t part, nodes;
+  fabric_layout(op, blocked, f, part, nodes);
   const size_t bytes = (part + nodes) * sizeof(double) + 2 * (size_t)f.Gtot * sizeof(uint4);
   char* block = nullptr;
   if (int rc = dev_alloc(op, &block, bytes)) return rc;
   CUDA_TRY(cudaMemset(block, 0, bytes));
-  op->fab_block = block;
-  op->fab_bytes = bytes;
+  *block_slot = block;
   f.partials[rank] = reinterpret_cast<double*>(block);
   f.nodebuf[rank] = f.partials[rank] + part;
   f.slots[rank] = reinterpret_cast<uint4*>(f.nodebuf[rank] + nodes);
+  return TPL_OK;
+}
+int setup_local_fabric(tpl_op* op, bool blocked) { return alloc_fabric(op, blocked, 0, 1, blocked ? &op->blk_block : &op->tile_block); }
+// sharded handle: the active family's block for `world` ranks (the other family is switched off by the caller)
+int setup_fabric(tpl_op* op, int rank, int world) {
+  void** slot = op->blocked_ok ? &op->blk_block : &op->tile_block;
+  if (int rc = alloc_fabric(op, op->blocked_ok, rank, world, slot)) return rc;
+  op->fab_block = *slot;
   return TPL_OK;
 }
 
@@ -448,6 +473,17 @@ int finish_setup(tpl_op* op) {
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t1, tpl::pass1_tiled_kernel<true>, tpl::kBlock, op->smem_tile1));
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t2, tpl::pass2_tiled_kernel<true>, tpl::kBlock, op->smem_tile2));
       if (t1 < 1 || t2 < 1) op->tiled_ok = false;
+    }
+    if (op->blocked_ok) {
+      if (int rc = set_smem(tpl::pass1_blocked_kernel<false>, op->smem_blk1)) return rc;
+      if (int rc = set_smem(tpl::pass1_blocked_kernel<true>, op->smem_blk1)) return rc;
+      if (int rc = set_smem(tpl::pass2_blocked_kernel<false>, op->smem_blk2)) return rc;
+      if (int rc = set_smem(tpl::pass2_blocked_kernel<true>, op->smem_blk2v)) return rc;
+      int b1 = 0, b2 = 0, b3 = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, tpl::pass1_blocked_kernel<true>, tpl::kBlock, op->smem_blk1));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, tpl::pass2_blocked_kernel<false>, tpl::kBlock, op->smem_blk2));
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, tpl::pass2_blocked_kernel<true>, tpl::kBlock, op->smem_blk2v));
+      if (b1 < 1 || b2 < 1 || b3 < 1) op->blocked_ok = false;
     }
   } else if (op->format == 3) {
     if (int rc = set_smem(tpl::pass1_dense_kernel<false>, smem)) return rc;
@@ -718,6 +754,39 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       }
     }
   }
+  // blocked streaming shape (tpl_blocks.cuh): node blocks, cell-order operator, tile lists over local node ids
+  if (!rc && m >= 1 && p >= 1) {
+    int max_optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
+    tpl::HostBlocks hb;
+    tpl::build_blocks(m, p, tail, head, d, d_len, op->G, (size_t)max_optin, hb);
+    if (hb.ok) {
+      tpl::BlockOp& bo = op->blk;
+      bo = tpl::BlockOp{};
+      bo.GR = hb.GR; bo.GC = hb.GC; bo.PT = hb.PT; bo.PH = hb.PH; bo.Mpad = hb.Mpad; bo.m = (uint32_t)m;
+      bo.ring1 = hb.ring1; bo.ring2 = hb.ring2; bo.ring2v = hb.ring2v;
+      bo.tl.T = hb.T;
+      bo.tl.ntile = hb.ntile;
+      rc = dev_upload(op, &bo.cell_off, hb.cell_off);
+      if (!rc) rc = dev_upload(op, &bo.tbs, hb.tbs);
+      if (!rc) rc = dev_upload(op, &bo.hbs, hb.hbs);
+      if (!rc) rc = dev_upload(op, &bo.d, hb.d);
+      if (!rc) rc = dev_upload(op, &bo.th, hb.th);
+      if (!rc) rc = dev_upload(op, &bo.gidx, hb.gidx);
+      if (!rc) rc = dev_upload(op, &bo.tl.thdr, hb.thdr);
+      if (!rc) rc = dev_upload(op, &bo.tl.lent, hb.lent);
+      if (!rc) rc = dev_upload(op, &bo.tl.piece, hb.piece);
+      if (!rc) rc = dev_alloc(op, &bo.xc, (size_t)hb.Mpad);
+      for (auto& bb : op->bbuf)
+        if (!rc) rc = dev_alloc(op, &bb, (size_t)hb.Mpad + p);
+      const uint32_t PL = hb.PT + hb.PH;
+      op->smem_blk1 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring1, false, false);
+      op->smem_blk2 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2, true, false);
+      op->smem_blk2v = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2v, true, true);
+      op->blocked_ok = !rc;
+      if (!rc) rc = setup_local_fabric(op, true);
+    }
+  }
   // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of the stream batch, at most
   // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
   if (!rc && p >= 1 && p < (1u << 17)) {
@@ -737,7 +806,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
         rc = dev_upload(op, &op->tile.thdr, ht.thdr);
         if (!rc) rc = dev_upload(op, &op->tile.lent, ht.lent);
         if (!rc) rc = dev_upload(op, &op->tile.piece, ht.piece);
-        if (!rc) rc = setup_fabric(op, 0, 1);
+        if (!rc) rc = setup_local_fabric(op, false);
         op->smem_tile1 = tpl::tile_smem_bytes((uint32_t)p, T, false);
         op->smem_tile2 = tpl::tile_smem_bytes((uint32_t)p, T, true);
         op->tiled_ok = !rc;
@@ -866,6 +935,46 @@ int tpl_tiles_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* hea
   return TPL_OK;
 }
 
+int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len, int ctas,
+                    size_t smem_limit, int threads, uint64_t stats[16]) {
+  tpl::clear_error();
+  if (!tail || !head || !stats || (d_len && !d)) return fail(TPL_ERR_PANIC, "null argument");
+  if (d_len > m) return tpl::fail_parameter_mismatch("d", m, d_len);
+  for (size_t j = 0; j < m; ++j)
+    if (tail[j] >= p || head[j] >= p)
+      return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  tpl::HostBlocks hb;
+  tpl::build_blocks(m, p, tail, head, d, d_len, ctas, smem_limit, hb, threads);
+  std::fill(stats, stats + 16, 0ull);
+  stats[0] = hb.ok;
+  if (!hb.ok) return TPL_OK;
+  stats[1] = hb.GR;
+  stats[2] = hb.GC;
+  stats[3] = hb.PT;
+  stats[4] = hb.PH;
+  stats[5] = hb.Mpad;
+  stats[6] = hb.T;
+  stats[7] = hb.ntile;
+  stats[8] = hb.ring1 | ((uint64_t)hb.ring2 << 8) | ((uint64_t)hb.ring2v << 16);
+  uint64_t cmax = 0, cmin = ~0ull, hsh = 1469598103934665603ull;
+  for (uint32_t c = 0; c + 1 < hb.cell_off.size(); ++c) {
+    cmax = std::max<uint64_t>(cmax, hb.cell_off[c + 1] - hb.cell_off[c]);
+    cmin = std::min<uint64_t>(cmin, hb.cell_off[c + 1] - hb.cell_off[c]);
+  }
+  stats[9] = cmax;
+  stats[10] = cmin;
+  stats[11] = hb.lent.size();
+  stats[12] = hb.piece.size();
+  for (uint32_t e : hb.lent) hsh = (hsh ^ e) * 1099511628211ull;
+  for (uint32_t e : hb.piece) hsh = (hsh ^ e) * 1099511628211ull;
+  for (uint32_t e : hb.th) hsh = (hsh ^ e) * 1099511628211ull;
+  for (uint32_t e : hb.gidx) hsh = (hsh ^ e) * 1099511628211ull;
+  stats[13] = hsh;
+  stats[14] = (uint64_t)tpl::check_blocks(m, p, tail, head, d, d_len, hb);
+  stats[15] = tpl::block_smem_bytes(hb.PT + hb.PH, hb.T, (int)hb.ring2, true, false);
+  return TPL_OK;
+}
+
 int tpl_cells_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int ctas, size_t smem_limit,
                    uint64_t stats[16]) {
   tpl::clear_error();
@@ -907,7 +1016,7 @@ int tpl_cells_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* hea
 }
 
 int tpl_op_set_mode(tpl_op* op, int mode) {
-  if (!op || mode < 0 || mode > 4) return fail(TPL_ERR_PANIC, "invalid mode");
+  if (!op || mode < 0 || mode > 5) return fail(TPL_ERR_PANIC, "invalid mode");
   op->mode = mode;
   return TPL_OK;
 }
@@ -970,16 +1079,19 @@ int launch_cells(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
   op->launches += 1;
   return TPL_OK;
 }
+// mode 0: blocked streaming kernels before the tiled ones (mode 5 forces them, mode 2 forces the tiled ones)
+bool use_blocked(const tpl_op* op) { return op->format == 2 && op->blocked_ok && (op->mode == 0 || op->mode == 5); }
 bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op->mode == 0 || op->mode == 2); }
 
 }  // namespace
 static const char* shape_name(const tpl_op* op) {
-  if (op->comm) return op->fab_connected && op->mode == 0 ? "sharded-fused" : "sharded";
+  if (op->comm) return op->fab_connected && op->mode == 0 ? (op->blocked_ok ? "sharded-blocked" : "sharded-fused") : "sharded";
   if (op->format == 3) return "dense";
   if (op->format != 2) return "csr";
   if (op->mode == 1) return "gather";
   if (use_cells(op)) return "cells";
   if (use_resident(op)) return "chunks";
+  if (use_blocked(op)) return "blocked";
   if (use_tiled(op)) return "tiled";
   return "gather";
 }
@@ -994,6 +1106,16 @@ int launch_tiled(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
   return TPL_OK;
 }
 
+template <class KERNEL, class ARGS>
+int launch_blocked(tpl_op* op, KERNEL kernel, ARGS args, size_t smem) {
+  for (int i = 0; i < 3; ++i) args.buf[i] = op->bbuf[i];  // the rotating vectors live in cell order
+  void* params[] = {&op->inc, &op->blk, &args};
+  CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(op->blk.GR * op->blk.GC), dim3(tpl::kBlock),
+                                       params, smem, op->stream));
+  op->launches += 1;
+  return TPL_OK;
+}
+
 int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   const bool with_v = a.V != nullptr;
   if (whole_pass && use_cells(op))
@@ -1002,6 +1124,9 @@ int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   if (whole_pass && use_resident(op))
     return with_v ? launch_resident(op, tpl::pass1_resident_kernel<true>, a, op->smem_res1)
                   : launch_resident(op, tpl::pass1_resident_kernel<false>, a, op->smem_res1);
+  if (whole_pass && use_blocked(op))
+    return with_v ? launch_blocked(op, tpl::pass1_blocked_kernel<true>, a, op->smem_blk1)
+                  : launch_blocked(op, tpl::pass1_blocked_kernel<false>, a, op->smem_blk1);
   if (whole_pass && use_tiled(op))
     return with_v ? launch_tiled(op, tpl::pass1_tiled_kernel<true>, a, op->smem_tile1)
                   : launch_tiled(op, tpl::pass1_tiled_kernel<false>, a, op->smem_tile1);
@@ -1021,6 +1146,9 @@ int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   if (use_resident(op))
     return with_v ? launch_resident(op, tpl::pass2_resident_kernel<true>, a, op->smem_res2)
                   : launch_resident(op, tpl::pass2_resident_kernel<false>, a, op->smem_res2);
+  if (use_blocked(op))
+    return with_v ? launch_blocked(op, tpl::pass2_blocked_kernel<true>, a, op->smem_blk2v)
+                  : launch_blocked(op, tpl::pass2_blocked_kernel<false>, a, op->smem_blk2);
   if (use_tiled(op))
     return with_v ? launch_tiled(op, tpl::pass2_tiled_kernel<true>, a, op->smem_tile2)
                   : launch_tiled(op, tpl::pass2_tiled_kernel<false>, a, op->smem_tile2);
@@ -1558,7 +1686,8 @@ int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end
   op->cells_ok = false;
   op->rank = rank;
   op->world = world;
-  if (op->tiled_ok && world <= tpl::kMaxRanks)
+  if (op->blocked_ok) op->tiled_ok = false;  // one family runs fused (and owns the exported exchange block)
+  if ((op->tiled_ok || op->blocked_ok) && world <= tpl::kMaxRanks)
     if (int rc = setup_fabric(op, rank, world)) return bail(rc);
   if (int rc = dev_alloc(op, &op->red_d, 2 * (p + 1))) return bail(rc);
   if (int rc = dev_alloc(op, &op->red2_d, 1)) return bail(rc);
@@ -1577,8 +1706,8 @@ int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end
 int tpl_op_fabric_export(tpl_op* op, uint8_t handle[64]) {
   tpl::clear_error();
   if (!op || !handle) return fail(TPL_ERR_PANIC, "null argument");
-  if (!op->comm || !op->tiled_ok || !op->fab_block || op->world > tpl::kMaxRanks)
-    return fail(TPL_ERR_COMM, "the operator has no exchange block (not sharded, or the tiled kernels do not fit)");
+  if (!op->comm || !(op->tiled_ok || op->blocked_ok) || !op->fab_block || op->world > tpl::kMaxRanks)
+    return fail(TPL_ERR_COMM, "the operator has no exchange block (not sharded, or neither the blocked nor the tiled kernels fit)");
   DeviceGuard g(op->device);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t h;
@@ -1594,8 +1723,9 @@ int tpl_op_fabric_import(tpl_op* op, const uint8_t* handles, int count) {
   if (count != op->world) return tpl::fail_parameter_mismatch("handles", (size_t)op->world, (size_t)count);
   if (op->fab_connected) return TPL_OK;
   DeviceGuard g(op->device);
-  tpl::Fabric& f = op->tile.fab;
-  const size_t part = 2 * (size_t)f.Gtot * f.Bp, nodes = 2 * (size_t)op->inc.p + 2;
+  tpl::Fabric& f = active_fabric(op);
+  size_t part, nodes;
+  fabric_layout(op, op->blocked_ok, f, part, nodes);
   for (int r = 0; r < op->world; ++r) {
     if (r == op->rank) continue;
     cudaIpcMemHandle_t h;
