@@ -1,4 +1,4 @@
-"""Small, fixed workload for ncu: one two-pass solve on the headline instance.  usage: profile_target.py [k] [arcs]"""
+"""Small, fixed workload for ncu: two-pass solves on a synthetic instance.  usage: profile_target.py [k] [arcs] [reps] [mode]"""
 import os
 import sys
 
@@ -12,9 +12,12 @@ from two_pass_lanczos_b200 import datagen  # noqa: E402
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 arcs = int(sys.argv[2]) if len(sys.argv) > 2 else 500_000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 inst = datagen.gen_kkt(arcs, 3, 1, "aa")
 op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d)
 b = op.apply(np.full(inst.n, 1.0 / np.sqrt(inst.n)))
+op.set_mode(mode)
+print(op.kernel_shape())
 for _ in range(reps):
     x = tpl.lanczos_two_pass(op, b, k, "inv")
     print(op.last_timing())

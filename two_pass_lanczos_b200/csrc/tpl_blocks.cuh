@@ -57,11 +57,15 @@ struct BlockSmem {
   uint32_t ring;   // shared-window address of the slot area: [compute warp][slot][slot_bytes]
   uint32_t mbar;   // [compute warp][kBMaxRing] mbarriers
 };
+// List padding is a harmless entry instead of a branch: it adds the tile's ZERO slot (index T + kMaxPieces - 1, written once;
+// the host keeps at most kMaxPieces - 1 pieces per tile) into the DUMMY accumulator (local node id PL).
+constexpr uint32_t kBAccPad = 2;  // accumulator slots behind the PL real ones (dummy + alignment)
+__host__ __device__ inline uint32_t block_pad_entry(uint32_t PL, uint32_t T) { return (PL << 15) | (T + kMaxPieces - 1); }
 __host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4; }
 // pass 1 never needs node values and accumulators at the same time (they alias), pass 2 needs both
 __host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, bool pass2, bool with_v) {
   const size_t slot = pass2 ? block_slot_bytes(4, with_v ? 2 : 1) : block_slot_bytes(2, 0);
-  return ((pass2 ? 2 : 1) * (size_t)PL + 2 * ((size_t)T + kMaxPieces)) * sizeof(double) + (size_t)kBComputeWarps * ring * slot +
+  return ((pass2 ? 2 : 1) * ((size_t)PL + kBAccPad) + 2 * ((size_t)T + kMaxPieces)) * sizeof(double) + (size_t)kBComputeWarps * ring * slot +
          (size_t)kBComputeWarps * kBMaxRing * 8 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
 }
 __device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, bool pass2) {
@@ -69,8 +73,8 @@ __device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uin
   const uint32_t b = ((uint32_t)__cvta_generic_to_shared(base) + 15u) & ~15u;
   BlockSmem s;
   s.node.a = b;
-  s.acc.a = pass2 ? b + PL * 8u : b;
-  s.wt.a = s.acc.a + PL * 8u;
+  s.acc.a = pass2 ? b + (PL + kBAccPad) * 8u : b;
+  s.wt.a = s.acc.a + (PL + kBAccPad) * 8u;
   s.wt_stride = (T + kMaxPieces) * 8u;
   s.mbar = s.wt.a + 2u * s.wt_stride;
   s.ring = s.mbar + kBComputeWarps * kBMaxRing * 8u;
@@ -112,30 +116,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-__device__ __forceinline__ double sm_ld_at(uint32_t addr) {
+// ld / st.shared with a compile-time byte offset (one instruction each, [reg + imm]).  `volatile` keeps them in program order
+// relative to the mbarrier wait and the named barriers (volatile asm with a memory clobber); without a clobber of their own
+// the compiler is free to schedule the arithmetic of the four arcs of a lane between them.
+template <int OFF>
+__device__ __forceinline__ double lds64(uint32_t addr) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
   return v;
 }
-__device__ __forceinline__ uint32_t sm_ld_u32_at(uint32_t addr) {
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v));
+}
+__device__ __forceinline__ double lds64_at(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
 
-// (A x)_j of an arc row in the reference's CSC accumulation order (arc_row of tpl_kernels.cuh with the order and the
-// self-loop test precomputed in the th word)
+// (A x)_j of an arc row in the reference's CSC accumulation order (arc_row of tpl_kernels.cuh), branch-free: the th word says
+// whether the tail column comes first; a - x and a + (-x) are the same IEEE operation, and a self-loop / padding slot adds
+// +0.0 twice (its merged incidence entry is an explicit zero).
 __device__ __forceinline__ double arc_row_b(double dj, double xj, uint32_t th, double xt, double xh) {
-  double acc = __dmul_rn(dj, xj);
-  if (th & kBLoop) {
-  } else if (th & kBTailFirst) {
-    acc = __dadd_rn(acc, xt);
-    acc = __dsub_rn(acc, xh);
-  } else {
-    acc = __dsub_rn(acc, xh);
-    acc = __dadd_rn(acc, xt);
-  }
-  return acc;
+  const double nxh = -xh;
+  const bool loop = (th & kBLoop) != 0, tf = (th & kBTailFirst) != 0;
+  const double first = loop ? 0.0 : (tf ? xt : nxh);
+  const double second = loop ? 0.0 : (tf ? nxh : xt);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dj, xj), first), second);
 }
 
 struct BlockCtx {
@@ -170,7 +184,7 @@ __device__ __forceinline__ void stage_block_nodes(const BlockOp& bo, const Block
   for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) sm_st(s.node, bo.PT + i, __dmul_rn(__ldcg(Xnode + c.h0 + i), sc));
 }
 __device__ __forceinline__ void zero_block_acc(const BlockOp& bo, const BlockSmem& s) {
-  for (uint32_t i = threadIdx.x; i < bo.PT + bo.PH; i += kBlock) sm_st(s.acc, i, 0.0);
+  for (uint32_t i = threadIdx.x; i < bo.PT + bo.PH + kBAccPad; i += kBlock) sm_st(s.acc, i, 0.0);
 }
 
 // This CTA's partial sums (s.acc) -> the owners' buffers, parity `par`.  Destination-indexed: node u of rank rk keeps
@@ -199,6 +213,82 @@ __device__ __forceinline__ double block_node_total(const BlockOp& bo, uint32_t p
   return warp_sum(a);
 }
 
+// ---------------------------------------------------------------------------- node sums of a tile (fold warps)
+// The lists of the blocked kernels keep a fold thread's entries SORTED BY NODE (tpl_blocks_host.h): the thread loads the tile
+// values of a whole batch first (independent ld.shared), adds the values of one node in a register and touches the shared
+// accumulator once per node and tile -- a dependent ld / add / st chain per ENTRY (the fold of tpl_tiles.cuh) was
+// latency-bound at ~45 instructions and ~70 cycles per entry.  Padding entries add the tile's zero slot into the dummy
+// accumulator: no branch.  `fr` holds the tile's first list batch and its piece words on entry, those of tile `next` on return.
+__device__ __forceinline__ void block_fold_request(const TileOp& to, const TileHdr& h, uint32_t q0, uint32_t pad, uint32_t (&ent)[kPre]) {
+  const uint32_t* mine = to.lent + h.e0 + (threadIdx.x - kStreamThreads);
+#pragma unroll
+  for (int q = 0; q < kPre; ++q) ent[q] = q0 + q < h.L ? __ldg(mine + (size_t)(q0 + q) * kFoldThreads) : pad;
+}
+__device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSmem& s, uint32_t wt, const TileHdr& h, const TileHdr& next,
+                                                bool has_next, FoldRegs& fr, uint32_t dummy) {
+  const uint32_t pad = block_pad_entry(dummy, to.T);
+  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
+  if (h.q1 > h.q0) {  // same-tail runs of the tile, one warp per piece: four lane-strided chains, xor tree
+    uint32_t i = 0;
+    for (uint32_t q = h.q0 + fwarp; q < h.q1; q += kFoldWarps, ++i) {
+      const uint32_t pc = __shfl_sync(0xffffffffu, i < 32 ? fr.pc[0] : fr.pc[1], i & 31);
+      const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
+      const uint32_t w = wt + first * 8u;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (uint32_t e = lane; e < len; e += 128) {
+        const double x0 = lds64_at(w + e * 8u);
+        const double x1 = e + 32 < len ? lds64_at(w + (e + 32) * 8u) : 0.0;
+        const double x2 = e + 64 < len ? lds64_at(w + (e + 64) * 8u) : 0.0;
+        const double x3 = e + 96 < len ? lds64_at(w + (e + 96) * 8u) : 0.0;
+        a0 = __dadd_rn(a0, x0);
+        a1 = __dadd_rn(a1, x1);
+        a2 = __dadd_rn(a2, x2);
+        a3 = __dadd_rn(a3, x3);
+      }
+      const double a = warp_sum(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)));
+      if (lane == 0) sm_st(SmArr{wt}, to.T + (q - h.q0), a);
+    }
+    bar_sync_n(kBarFold, kFoldThreads);
+  }
+  if (has_next) piece_request(to, next, fr.pc);
+  uint32_t cur = dummy;
+  double sum = 0.0;
+  uint32_t q0 = 0;
+  do {  // (runs once for an empty list: the first batch of the next tile still has to be requested)
+    uint32_t nxt[kPre];
+    if (q0 + kPre < h.L) {
+      block_fold_request(to, h, q0 + kPre, pad, nxt);
+    } else if (has_next) {
+      block_fold_request(to, next, 0, pad, nxt);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) nxt[q] = pad;
+    }
+    if (q0 < h.L) {
+      double val[kPre];
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {  // the whole batch's tile values first: independent loads
+        const long long x = __double_as_longlong(lds64_at(wt + (fr.ent[q] & 0x3fffu) * 8u)) ^ ((long long)(fr.ent[q] & 0x4000u) << 49);
+        val[q] = __longlong_as_double(x);
+      }
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        const uint32_t node = fr.ent[q] >> 15;
+        if (node != cur) {  // the previous node is complete: one read-modify-write of its accumulator
+          sm_st(s.acc, cur, __dadd_rn(sm_ld(s.acc, cur), sum));
+          cur = node;
+          sum = 0.0;
+        }
+        sum = __dadd_rn(sum, val[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPre; ++q) fr.ent[q] = nxt[q];
+    q0 += kPre;
+  } while (q0 < h.L);
+  sm_st(s.acc, cur, __dadd_rn(sm_ld(s.acc, cur), sum));
+}
+
 // ---------------------------------------------------------------------------- the folding sweep
 // One sweep over the CTA's cell that produces a new arc vector AND its node sums.  Compute warp w owns the stages
 // g = w, w + 8, w + 16, ... of the cell (a stage = 128 consecutive cell-order arcs) and a private ring of RING slots; lane 0
@@ -206,20 +296,23 @@ __device__ __forceinline__ double block_node_total(const BlockOp& bo, uint32_t p
 // the arcs pos + lane + 32 q (q < 4): it reads array a of the slot at slot + a * 1024 (+ 8 * index) (4-byte arrays behind
 // the 8-byte ones), stores its results to global memory and the new arc value of arc q to wt_addr + 8 * (lane + 32 q).
 // A tile (T arcs) is complete when all compute warps have arrived; the fold warps then add its node sums into s.acc while
-// the compute warps fill the other tile buffer (named barriers as in tile_loop).  `kbase` counts the stages this warp has
-// consumed since the kernel started: slot and mbarrier parity follow from it, the mbarriers are initialised once.
+// the compute warps fill the other tile buffer (named barriers as in tile_loop).  `rs` (ring slot and mbarrier phase of this
+// warp's next stage) lives across the sweeps of a kernel: the mbarriers are initialised once.
+struct RingState {
+  uint32_t slot, phase;
+};
 template <int N8, int N4, class CONSUME>
-__device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, int RING, uint32_t slot_bytes,
+__device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
                                            const double* const (&src8)[N8], const uint32_t* const (&src4)[N4 ? N4 : 1],
-                                           CONSUME consume, uint32_t& kbase) {
+                                           CONSUME consume, RingState& rs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t SPT = bo.tl.T / kBStage;  // stages per tile (a multiple of 8)
   if (warp < kBComputeWarps) {
     const uint32_t nk = c.nst > (uint32_t)warp ? (c.nst - warp + kBComputeWarps - 1) / kBComputeWarps : 0;  // my stages
     const uint32_t ring0 = s.ring + (uint32_t)warp * RING * slot_bytes, bar0 = s.mbar + (uint32_t)warp * kBMaxRing * 8u;
     constexpr uint32_t kTx = N8 * kBStage * 8 + N4 * kBStage * 4;
-    auto issue = [&](uint32_t k) __attribute__((always_inline)) {  // lane 0 only
-      const uint32_t sl = (kbase + k) % RING, bar = bar0 + sl * 8u, dst = ring0 + sl * slot_bytes;
+    auto issue = [&](uint32_t k, uint32_t sl) __attribute__((always_inline)) {  // lane 0 only: stage k of this warp into slot sl
+      const uint32_t bar = bar0 + sl * 8u, dst = ring0 + sl * slot_bytes;
       const size_t pos = (size_t)c.c0 + ((size_t)k * kBComputeWarps + warp) * kBStage;
       mbar_expect_tx(bar, kTx);
 #pragma unroll
@@ -227,43 +320,47 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
 #pragma unroll
       for (int a = 0; a < N4; ++a) bulk_g2s(dst + N8 * (kBStage * 8) + a * (kBStage * 4), src4[a] + pos, kBStage * 4, bar);
     };
-    if (lane == 0)
-      for (uint32_t k = 0; k < (uint32_t)RING && k < nk; ++k) issue(k);
+    if (lane == 0) {
+      uint32_t sl = rs.slot;
+      for (uint32_t k = 0; k < RING && k < nk; ++k) {
+        issue(k, sl);
+        sl = sl + 1 == RING ? 0 : sl + 1;
+      }
+    }
     uint32_t k = 0;
     for (uint32_t t = 0; t < c.ntiles; ++t) {
       if (t >= 2) bar_sync_n(kBarEmpty + (t & 1u), kBlock);  // the fold of tile t - 2 has left this buffer
       const uint32_t wt0 = s.wt.a + (t & 1u) * s.wt_stride;
-      for (uint32_t i = 0; i < SPT / kBComputeWarps; ++i) {
-        const uint32_t g = t * SPT + i * kBComputeWarps + warp;
-        if (g >= c.nst) break;
-        const uint32_t sl = (kbase + k) % RING;
-        mbar_wait(bar0 + sl * 8u, ((kbase + k) / RING) & 1u);
-        consume(c.c0 + g * kBStage, ring0 + sl * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), lane);
+      uint32_t g = t * SPT + warp;
+      for (uint32_t i = 0; i < SPT / kBComputeWarps && g < c.nst; ++i, g += kBComputeWarps) {
+        mbar_wait(bar0 + rs.slot * 8u, rs.phase);
+        consume(c.c0 + g * kBStage, ring0 + rs.slot * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), lane);
         __syncwarp();  // every lane has read its slot words
-        if (lane == 0 && k + RING < nk) issue(k + RING);
+        if (lane == 0 && k + RING < nk) issue(k + RING, rs.slot);
         ++k;
+        if (++rs.slot == RING) {
+          rs.slot = 0;
+          rs.phase ^= 1u;
+        }
       }
       bar_arrive_n(kBarFull + (t & 1u), kBlock);
     }
-    kbase += nk;
     // drain: every arrival of the fold warps is matched by a wait, so that the barriers are clean for the next sweep
     for (uint32_t u = c.ntiles > 2 ? c.ntiles - 2 : 0; u < c.ntiles; ++u) bar_sync_n(kBarEmpty + (u & 1u), kBlock);
     fence_proxy_async();  // the vector just written is bulk-copied by the next sweep (after the grid barrier in between)
   } else {
-    const uint32_t tile0 = blockIdx.x * bo.tl.ntile;
-    const TileSmem ts{s.node, s.acc, s.wt, s.wt_stride};
+    const uint32_t tile0 = blockIdx.x * bo.tl.ntile, dummy = bo.PT + bo.PH;
     TileHdr hdr = tile_hdr(bo.tl, tile0);
     FoldRegs fr;
     if (c.ntiles) {
-      fold_request(bo.tl, hdr, 0, fr.ent);
+      block_fold_request(bo.tl, hdr, 0, block_pad_entry(dummy, bo.tl.T), fr.ent);
       piece_request(bo.tl, hdr, fr.pc);
     }
     for (uint32_t t = 0; t < c.ntiles; ++t) {
       TileHdr next = hdr;
       if (t + 1 < c.ntiles) next = tile_hdr(bo.tl, tile0 + t + 1);
-      const SmArr wt{s.wt.a + (t & 1u) * s.wt_stride};
       bar_sync_n(kBarFull + (t & 1u), kBlock);
-      tile_node_sums(bo.tl, ts, wt, hdr, next, t + 1 < c.ntiles, fr);
+      block_fold_tile(bo.tl, s, s.wt.a + (t & 1u) * s.wt_stride, hdr, next, t + 1 < c.ntiles, fr, dummy);
       bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
       hdr = next;
     }
@@ -271,15 +368,17 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
   __syncthreads();
 }
 
-__device__ __forceinline__ void init_block_mbarriers(const BlockSmem& s) {
+// mbarriers of the rings, and the zero slot of both tile buffers that padding list entries read
+__device__ __forceinline__ void init_block_smem(const BlockOp& bo, const BlockSmem& s) {
   if (threadIdx.x < kBComputeWarps * kBMaxRing) mbar_init(s.mbar + threadIdx.x * 8u, 1);
+  if (threadIdx.x < 2) sm_st(SmArr{s.wt.a + threadIdx.x * s.wt_stride}, bo.tl.T + kMaxPieces - 1, 0.0);
   fence_mbar_init();
   __syncthreads();
 }
 
 // node partial sums of an arbitrary cell-order arc vector X over the CTA's cell (init: the un-normalised b)
-__device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, int RING, uint32_t slot_bytes,
-                                              const double* X, uint32_t& kbase) {
+__device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
+                                              const double* X, RingState& rs) {
   zero_block_acc(bo, s);
   __syncthreads();
   const double* const src8[1] = {X};
@@ -287,13 +386,14 @@ __device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem
   fold_sweep<1, 0>(
       bo, s, c, RING, slot_bytes, src8, src4,
       [&](uint32_t, uint32_t slot, uint32_t wt, int lane) __attribute__((always_inline)) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t e = (lane + 32 * q) * 8u;
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt + e), "d"(sm_ld_at(slot + e)) : "memory");
-        }
+        const uint32_t sl = slot + lane * 8u, w = wt + lane * 8u;
+        const double x0 = lds64<0>(sl), x1 = lds64<256>(sl), x2 = lds64<512>(sl), x3 = lds64<768>(sl);
+        sts64<0>(w, x0);
+        sts64<256>(w, x1);
+        sts64<512>(w, x2);
+        sts64<768>(w, x3);
       },
-      kbase);
+      rs);
 }
 
 // =============================================================================================
@@ -307,13 +407,13 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
   const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, false);
   const BlockCtx c = block_ctx(bo, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int RING = (int)bo.ring1;
+  const uint32_t RING = bo.ring1;
   const uint32_t slot_bytes = (uint32_t)block_slot_bytes(2, 0);
   const TileOp& to = bo.tl;
-  init_block_mbarriers(s);
+  init_block_smem(bo, s);
 
   unsigned int epoch = a.st->epoch;
-  uint32_t kbase = 0;
+  RingState rs{0u, 0u};
   int steps = 0, status = ST_RUNNING, rot = 0;
   double sc = 1.0, sp = 1.0, bp = 0.0, bnorm = 0.0;
   GridSync gs = a.gs;
@@ -342,7 +442,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
     }
     fence_proxy_async();
     __syncthreads();  // the cell's share of W_cur is written (and fenced towards the async proxy) before it is bulk-copied
-    block_sums_of(bo, s, c, RING, slot_bytes, Wc, kbase);
+    block_sums_of(bo, s, c, RING, slot_bytes, Wc, rs);
     publish_block_partials(bo, s, c, 0);
     bnorm = sqrt(tile_sync<true>(acc, to, a.gs, epoch, sh));
     if (bnorm <= a.tol) status = ST_ZERO_B;
@@ -422,16 +522,27 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
         fold_sweep<2, 0>(
             bo, s, c, RING, slot_bytes, src8, src4,
             [&](uint32_t pos, uint32_t slot, uint32_t wt, int ln) __attribute__((always_inline)) {
+              const uint32_t sl = slot + ln * 8u;
+              double wn[4], wc[4];
+              wn[0] = lds64<0>(sl), wn[1] = lds64<256>(sl), wn[2] = lds64<512>(sl), wn[3] = lds64<768>(sl);
+              wc[0] = lds64<1024>(sl), wc[1] = lds64<1280>(sl), wc[2] = lds64<1536>(sl), wc[3] = lds64<1792>(sl);
+              double w[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t e = (ln + 32 * q) * 8u;
-                const double w = rec_sub(sm_ld_at(slot + e), alpha, __dmul_rn(sm_ld_at(slot + kBStage * 8 + e), sc));
-                __stcg(Wn + pos + ln + 32 * q, w);
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt + e), "d"(w) : "memory");
-                acc = fma(w, w, acc);
-              }
+              for (int q = 0; q < 4; ++q) w[q] = rec_sub(wn[q], alpha, __dmul_rn(wc[q], sc));
+              double* out = Wn + pos + ln;
+              __stcg(out, w[0]);
+              __stcg(out + 32, w[1]);
+              __stcg(out + 64, w[2]);
+              __stcg(out + 96, w[3]);
+              const uint32_t ws = wt + ln * 8u;
+              sts64<0>(ws, w[0]);
+              sts64<256>(ws, w[1]);
+              sts64<512>(ws, w[2]);
+              sts64<768>(ws, w[3]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc = fma(w[q], w[q], acc);
             },
-            kbase);
+            rs);
       }
       publish_block_partials(bo, s, c, (j + 1) & 1);
       const double beta = sqrt(tile_sync<true>(acc, to, gs, epoch, sh));
@@ -476,14 +587,14 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
   const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, true);
   const BlockCtx c = block_ctx(bo, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int RING = (int)(WITH_V ? bo.ring2v : bo.ring2);
+  const uint32_t RING = WITH_V ? bo.ring2v : bo.ring2;
   const uint32_t slot_bytes = (uint32_t)block_slot_bytes(4, WITH_V ? 2 : 1);
   const TileOp& to = bo.tl;
-  init_block_mbarriers(s);
+  init_block_smem(bo, s);
   uint32_t vlo, vhi;  // share of the (replicated) node part of x / V this CTA writes
   cta_chunk(p, vlo, vhi);
   unsigned int epoch = a.st->epoch;
-  uint32_t kbase = 0;
+  RingState rs{0u, 0u};
   double* const buf0 = a.buf[0];
   double* const buf1 = a.buf[1];
   double* const buf2 = a.buf[2];
@@ -523,7 +634,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
     }
     fence_proxy_async();
     __syncthreads();
-    block_sums_of(bo, s, c, RING, slot_bytes, Braw, kbase);
+    block_sums_of(bo, s, c, RING, slot_bytes, Braw, rs);
     publish_block_partials(bo, s, c, 0);
     tile_sync<false>(0.0, to, a.gs, epoch, sh);
   }
@@ -566,31 +677,55 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
       const uint32_t* const src4[2] = {bo.th, bo.gidx};
       const uint32_t* const src4n[1] = {bo.th};
       auto body = [&](uint32_t pos, uint32_t slot, uint32_t wt, int ln) __attribute__((always_inline)) {
+        // all loads of the lane's four arcs first, then the node-value gathers, then the arithmetic, then the stores
+        const uint32_t sl = slot + ln * 8u, sl4 = slot + 4 * kBStage * 8 + ln * 4u;
+        double v[4], vp[4], xx[4], dd[4], xt[4], xh[4];
+        uint32_t th[4];
+        v[0] = lds64<0>(sl), v[1] = lds64<256>(sl), v[2] = lds64<512>(sl), v[3] = lds64<768>(sl);
+        th[0] = lds32<0>(sl4), th[1] = lds32<128>(sl4), th[2] = lds32<256>(sl4), th[3] = lds32<384>(sl4);
+        vp[0] = lds64<1024>(sl), vp[1] = lds64<1280>(sl), vp[2] = lds64<1536>(sl), vp[3] = lds64<1792>(sl);
+        dd[0] = lds64<3072>(sl), dd[1] = lds64<3328>(sl), dd[2] = lds64<3584>(sl), dd[3] = lds64<3840>(sl);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t e = (ln + 32 * q) * 8u, e4 = (ln + 32 * q) * 4u;
-          const double v = sm_ld_at(slot + e);
-          const double vp = sm_ld_at(slot + kBStage * 8 + e);
-          const double xx = sm_ld_at(slot + 2 * kBStage * 8 + e);
-          const double dd = sm_ld_at(slot + 3 * kBStage * 8 + e);
-          const uint32_t th = sm_ld_u32_at(slot + 4 * kBStage * 8 + e4);
-          const double xt = sm_ld(s.node, th & 0x7fffu), xh = sm_ld(s.node, bo.PT + ((th >> 15) & 0x7fffu));
-          const double w = rec_sub(rec_sub(arc_row_b(dd, v, th, xt, xh), bp, vp), alpha, v);
-          const double vn = __dmul_rn(w, sinv);
-          const uint32_t i = pos + ln + 32 * q;
-          __stcg(Vn + i, vn);
-          __stcg(xc + i, __dadd_rn(xx, __dmul_rn(yj, vn)));
-          if (WITH_V) {
-            const uint32_t g = sm_ld_u32_at(slot + 4 * kBStage * 8 + kBStage * 4 + e4);
-            if (g != kBPad) __stcs(Vcol + g, vn);
-          }
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt + e), "d"(w) : "memory");
+          xt[q] = lds64_at(s.node.a + (th[q] & 0x7fffu) * 8u);
+          xh[q] = lds64_at(s.node.a + (bo.PT + ((th[q] >> 15) & 0x7fffu)) * 8u);
+        }
+        xx[0] = lds64<2048>(sl), xx[1] = lds64<2304>(sl), xx[2] = lds64<2560>(sl), xx[3] = lds64<2816>(sl);
+        double w[4], vn[4], xo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          w[q] = rec_sub(rec_sub(arc_row_b(dd[q], v[q], th[q], xt[q], xh[q]), bp, vp[q]), alpha, v[q]);
+          vn[q] = __dmul_rn(w[q], sinv);
+          xo[q] = __dadd_rn(xx[q], __dmul_rn(yj, vn[q]));
+        }
+        double* o1 = Vn + pos + ln;
+        double* o2 = xc + pos + ln;
+        __stcg(o1, vn[0]);
+        __stcg(o1 + 32, vn[1]);
+        __stcg(o1 + 64, vn[2]);
+        __stcg(o1 + 96, vn[3]);
+        __stcg(o2, xo[0]);
+        __stcg(o2 + 32, xo[1]);
+        __stcg(o2 + 64, xo[2]);
+        __stcg(o2 + 96, xo[3]);
+        const uint32_t ws = wt + ln * 8u;
+        sts64<0>(ws, w[0]);
+        sts64<256>(ws, w[1]);
+        sts64<512>(ws, w[2]);
+        sts64<768>(ws, w[3]);
+        if (WITH_V) {
+          const uint32_t sg = sl4 + kBStage * 4;
+          const uint32_t g0 = lds32<0>(sg), g1 = lds32<128>(sg), g2 = lds32<256>(sg), g3 = lds32<384>(sg);
+          if (g0 != kBPad) __stcs(Vcol + g0, vn[0]);
+          if (g1 != kBPad) __stcs(Vcol + g1, vn[1]);
+          if (g2 != kBPad) __stcs(Vcol + g2, vn[2]);
+          if (g3 != kBPad) __stcs(Vcol + g3, vn[3]);
         }
       };
       if (WITH_V)
-        fold_sweep<4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, kbase);
+        fold_sweep<4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, rs);
       else
-        fold_sweep<4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, kbase);
+        fold_sweep<4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, rs);
     }
     publish_block_partials(bo, s, c, (j + 1) & 1);
     tile_sync<false>(0.0, to, a.gs, epoch, sh);

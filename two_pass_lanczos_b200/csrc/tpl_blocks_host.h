@@ -7,7 +7,8 @@
 //      ordered by tail node, then by arc index (two stable counting sorts), every cell is padded to a multiple of 128 slots;
 //   3. per position: d, the packed th word (local tail | local head << 15 | tail-first | loop-or-padding) and gidx;
 //   4. tile lists of every cell over LOCAL node ids (tails [0, PT), heads [PT, PT + PH)) by the builder of the tiled
-//      kernels (tpl_tiles_host.h): a cell is handed to it as a one-CTA instance.
+//      kernels (tpl_tiles_host.h): a cell is handed to it as a one-CTA instance; a fold thread's entries stay sorted by node
+//      and list padding becomes a harmless entry (the tile's zero slot into a dummy accumulator).
 // Cells are independent: they are built by a pool of host threads and concatenated in cell order (the result does not depend
 // on the number of threads).
 #pragma once
@@ -156,7 +157,10 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
         tl[i] = skip ? 0u : (w32 & 0x7fffu);
         hl[i] = skip ? 0u : PT + ((w32 >> 15) & 0x7fffu);
       }
-      build_cta_tiles(n, PT + PH, tl.data(), hl.data(), 1, h.T, h.ntile, 0, w, thdr[c], lent[c], piece[c]);
+      build_cta_tiles(n, PT + PH, tl.data(), hl.data(), 1, h.T, h.ntile, 0, w, thdr[c], lent[c], piece[c], false, kMaxPieces - 1);
+      const uint32_t pad = block_pad_entry(PT + PH, h.T);  // padding = zero slot of the tile into the dummy accumulator
+      for (uint32_t& e : lent[c])
+        if (e == kEntPad) e = pad;
     }
   };
   if (threads == 1) {
@@ -207,6 +211,25 @@ inline int check_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t
   one.ntile = h.ntile;
   one.lent = h.lent;
   one.piece = h.piece;
+  for (uint32_t& e : one.lent)
+    if (e == block_pad_entry(h.PT + h.PH, h.T)) e = kEntPad;
+  // a thread's entries are sorted by node (the fold adds a node's values in a register and flushes on a node change)
+  for (size_t t = 0; t < h.thdr.size(); ++t) {
+    const uint4 hd = h.thdr[t];
+    for (uint32_t i = 0; i < (uint32_t)kFoldThreads; ++i) {
+      uint32_t prev = 0;
+      bool padded = false;
+      for (uint32_t q = 0; q < hd.y; ++q) {
+        const uint32_t e = one.lent[hd.x + (size_t)q * kFoldThreads + i];
+        if (e == kEntPad) {
+          padded = true;
+          continue;
+        }
+        if (padded || (e >> 15) < prev) return 16;  // padding only at the end, nodes non-decreasing
+        prev = e >> 15;
+      }
+    }
+  }
   for (uint32_t c = 0; c < Gc; ++c) {
     const uint32_t r = c / h.GC, cc = c % h.GC, c0 = h.cell_off[c], c1 = h.cell_off[c + 1];
     if (c0 > c1 || c0 % kBStage || c1 % kBStage) return 5;

@@ -31,9 +31,11 @@ struct TileScratch {
 };
 
 // lists of CTA c, offsets relative to the CTA's own lent / piece arrays
+// bank_order = false keeps a thread's entries sorted by node (the blocked kernels add a node's values in a register);
+// max_pieces < kMaxPieces reserves the last piece slot of a tile buffer (their padding entries read a zero from it)
 inline void build_cta_tiles(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, int G, uint32_t T, uint32_t ntile,
                             int c, TileScratch& w, std::vector<uint4>& thdr, std::vector<uint32_t>& lent,
-                            std::vector<uint32_t>& piece) {
+                            std::vector<uint32_t>& piece, bool bank_order = true, uint32_t max_pieces = kMaxPieces) {
   const size_t A = (m + G - 1) / G;
   const int B = kFoldThreads;  // the fold warps walk the lists
   const size_t lo = std::min(m, A * (size_t)c), hi = std::min(m, lo + A);
@@ -58,7 +60,7 @@ inline void build_cta_tiles(size_t m, size_t p, const uint32_t* tail, const uint
       while (j < t1 && tail[j] == tail[i] && tail[j] != head[j]) ++j;
       const size_t len = j - i;
       const size_t need = (len + kPieceMax - 1) / kPieceMax;
-      if (len >= kPieceMin && npieces + need <= kMaxPieces) {
+      if (len >= kPieceMin && npieces + need <= max_pieces) {
         for (size_t q = i; q < j; q += kPieceMax) {
           const uint32_t l = (uint32_t)std::min<size_t>(kPieceMax, j - q);
           piece.push_back((uint32_t)(q - t0) | ((l - 1) << 16));
@@ -107,7 +109,12 @@ inline void build_cta_tiles(size_t m, size_t p, const uint32_t* tail, const uint
     // The order in which a thread folds its entries is free (any fixed order is deterministic).  It is chosen so that the
     // 16 threads of a half-warp, which execute fold step q together, read their tile values and their accumulators from
     // different shared-memory banks whenever they can: a random order costs ~3 wavefronts per 8-byte access.
-    for (int i0 = 0; i0 < B; i0 += 16) {
+    if (!bank_order) {
+      for (int i = 0; i < B; ++i)
+        for (uint32_t e = w.cut[i], q = 0; e < w.cut[i + 1]; ++e, ++q)
+          lent[base + (size_t)q * B + i] = (w.sorted_node[e] << 15) | w.sorted_code[e];
+    }
+    for (int i0 = 0; bank_order && i0 < B; i0 += 16) {
       for (int l = 0; l < 16; ++l) {
         w.rem[l].clear();
         if (i0 + l < B)
