@@ -1,8 +1,9 @@
 """Blocked streaming layout (tpl_blocks_host.h), built and checked on the host through tpl_blocks_plan: gidx is a bijection
 between the non-padding cell-order positions and the arcs, every packed tail/head word decodes to its arc inside the cell's
 node blocks (with the CSC-order and self-loop flags), cells are sorted by (tail, arc index) and padded to whole 128-arc stages,
-every non-loop arc is once on its local tail and once on its local head in the lists of its tile, and the layout does not depend
-on the number of host threads."""
+every non-loop arc is once on its local tail and once on its local head in the lists of its tile, the list slices have equal
+length with correct new-node flags and chain depths (check_cell_lists), and the layout does not depend on the number of host
+threads."""
 import ctypes as C
 
 import numpy as np
@@ -44,8 +45,8 @@ def test_layout_is_consistent_on_netgen_shaped_instances(m, flavour):
 
 def test_layout_at_the_largest_single_gpu_size_fits_with_a_deep_ring():
     """50M arcs: p = 11 547; the two node blocks of a cell hold ~2-3 k values (the last tail block also takes the sinks, which
-    have no out-arcs) -> tiles of >= 3072 arcs and three ring slots in pass 2 (the tiled kernels were left with 2048-arc tiles
-    by their two p-long arrays).  Only the sizing is checked here (no 50M-arc build on the CPU box): blocks_fit is exercised
+    have no out-arcs) -> three ring slots in pass 2 and double-buffered list blocks still fit (the tiled kernels kept two
+    p-long arrays, 184 KB, in shared memory).  Only the sizing is checked here (no 50M-arc build on the CPU box): blocks_fit is exercised
     through a 2M-arc instance with the node count of the 50M one."""
     rng = np.random.default_rng(5)
     m, p = 2_000_000, 11_547
@@ -53,7 +54,9 @@ def test_layout_at_the_largest_single_gpu_size_fits_with_a_deep_ring():
     head = rng.integers(100, p, m)
     st = plan(m, p, tail, head)
     assert st["fits"] == 1 and st["code"] == 0
-    assert st["T"] >= 3072 and ((st["rings"] >> 8) & 0xff) >= 3
+    # (this graph has no same-tail runs of 32 arcs inside a cell, so every arc costs two list entries: the worst case for the
+    # list buffers; a netgen-shaped 50M-arc instance gets 2048-arc tiles)
+    assert st["T"] >= 1024 and ((st["rings"] >> 8) & 0xff) >= 3
 
 
 @pytest.mark.parametrize("ctas", [13, 148])
@@ -83,7 +86,7 @@ def test_layout_does_not_depend_on_the_host_thread_count():
 
 def test_layout_degenerate_inputs():
     st = plan(40_000, 1, np.zeros(40_000), np.zeros(40_000))  # one node: every arc is a self-loop
-    assert st["fits"] == 1 and st["code"] == 0 and st["entries"] == 0
+    assert st["fits"] == 1 and st["code"] == 0 and st["pieces"] == 0
     rng = np.random.default_rng(1)
     st = plan(33_000, 40_000, rng.integers(0, 40_000, 33_000), rng.integers(0, 40_000, 33_000))  # more nodes than arcs
     assert st["fits"] == 1 and st["code"] == 0

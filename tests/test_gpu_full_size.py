@@ -40,13 +40,13 @@ def test_headline_two_pass_residual_and_variants(headline):
 
 def test_kernel_shapes_by_size(headline):
     """The headline instance runs on the cell kernels; 650k arcs (cells too large) on the chunk-resident or the tiled ones,
-    whichever fits; 2M arcs on the blocked streaming ones; every mode switch reports what it selects."""
+    whichever fits; 2M arcs on the blocked streaming ones (from ~1.5M arcs); every mode switch reports what it selects."""
     inst, gop, b = headline
     assert gop.kernel_shape() == "cells"
     for mode, shape in ((4, "chunks"), (5, "blocked"), (2, "tiled"), (3, "gather"), (1, "gather"), (0, "cells")):
         gop.set_mode(mode)
         assert gop.kernel_shape() == shape
-    for m, shapes in ((650_000, ("chunks", "blocked")), (2_000_000, ("blocked",))):
+    for m, shapes in ((650_000, ("chunks", "tiled")), (2_000_000, ("blocked",))):
         big = datagen.gen_kkt(m, 3, 2, "wc")
         op = tpl.LinOp.from_kkt(big.m, big.p, big.tail, big.head, big.d)
         assert op.kernel_shape() in shapes, op.kernel_shape()

@@ -30,6 +30,7 @@ namespace tpl {
 constexpr int kBStage = 128;                 // arcs of one warp-stage (4 per lane)
 constexpr int kBComputeWarps = kStreamWarps; // warps 0..7 compute, warps 8..15 fold (as in tpl_tiles.cuh)
 constexpr int kBMaxRing = 4;
+constexpr int kBMaxList = 8;
 constexpr uint32_t kBLoop = 0x80000000u;     // th word: self-loop or padding (no incidence entries)
 constexpr uint32_t kBTailFirst = 0x40000000u;  // th word: global tail index < global head index (CSC accumulation order)
 constexpr uint32_t kBPad = 0xffffffffu;      // gidx of a padding slot
@@ -39,7 +40,10 @@ struct BlockOp {
   uint32_t PT, PH;   // largest tail / head block: local node ids are tails [0, PT), heads [PT, PT + PH)
   uint32_t Mpad;     // arcs in cell order, padding included; the node part of a cell-order vector starts here
   uint32_t ring1, ring2, ring2v;  // ring slots per compute warp: pass 1, pass 2, pass 2 with a basis
+  uint32_t lblk;     // bytes of the largest tile list block ((L + 1) rows of kFoldThreads words): size of a list buffer
+  uint32_t nl;       // list buffers (2 .. kBMaxList): the list block of a tile is bulk-copied nl - 1 tiles ahead
   uint32_t m;        // arcs in natural order (node part of a natural-order vector starts here)
+  uint32_t dbg;      // timing experiments only (results are wrong): 1 = fold warps skip their work, 2 = compute warps skip theirs
   const uint32_t* cell_off;  // [G + 1] first cell-order position of every cell (multiples of kBStage)
   const uint32_t* tbs;       // [GR + 1] first node of every tail block
   const uint32_t* hbs;       // [GC + 1] first node of every head block
@@ -55,20 +59,35 @@ struct BlockSmem {
   SmArr node, acc, wt;
   uint32_t wt_stride;
   uint32_t ring;   // shared-window address of the slot area: [compute warp][slot][slot_bytes]
-  uint32_t mbar;   // [compute warp][kBMaxRing] mbarriers
+  uint32_t mbar;   // [compute warp][kBMaxRing] mbarriers of the rings, then kBMaxList mbarriers of the list buffers
+  uint32_t lst;    // [nl][lblk] list blocks of the tile being folded and of the next ones (bulk-copied nl - 1 tiles ahead)
+  uint32_t scr;    // [kFoldThreads] doubles: a fold thread's share of a node that earlier threads also hold
 };
-// List padding is a harmless entry instead of a branch: it adds the tile's ZERO slot (index T + kMaxPieces - 1, written once;
-// the host keeps at most kMaxPieces - 1 pieces per tile) into the DUMMY accumulator (local node id PL).
+// List format of the blocked kernels (host: build_cell_lists).  A tile's block is (L + 1) rows of kFoldThreads words,
+// thread-interleaved: row 0 = the thread's DEPTH, rows 1..L its entries
+//     minus << 31 | new_node << 30 | local node << 16 | 8 * index into the tile buffer (arcs, then pieces)
+// sorted by node and cut into slices of EQUAL length: a node may straddle threads.  A thread adds the values of one node in a
+// register and touches the shared accumulator once per node; the share of its FIRST node is added `depth` barrier phases
+// later when earlier threads hold entries of the same node (depth = position in that chain), so the order in which the
+// shares of a node are added is fixed and no two threads ever update one accumulator in the same phase.
+// Padding (only behind the last entry of a tile) is a harmless entry instead of a branch: it adds the tile's ZERO slot
+// (index T + kMaxPieces - 1, written once; at most kMaxPieces - 1 pieces per tile) into the DUMMY accumulator (node PL).
+constexpr uint32_t kBEntMinus = 0x80000000u, kBEntNew = 0x40000000u, kBEntNodeShift = 16, kBEntNodeMask = 0x3fffu, kBEntOffMask = 0xffffu;
+constexpr uint32_t kBMaxLocalNodes = kBEntNodeMask;  // PT + PH + dummy must fit the 14-bit node field
 constexpr uint32_t kBAccPad = 2;  // accumulator slots behind the PL real ones (dummy + alignment)
-__host__ __device__ inline uint32_t block_pad_entry(uint32_t PL, uint32_t T) { return (PL << 15) | (T + kMaxPieces - 1); }
+constexpr int kBPre = 8;          // list entries per fold thread requested together
+__host__ __device__ inline uint32_t block_pad_entry(uint32_t PL, uint32_t T) {
+  return kBEntNew | (PL << kBEntNodeShift) | ((T + kMaxPieces - 1) * 8u);
+}
 __host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4; }
 // pass 1 never needs node values and accumulators at the same time (they alias), pass 2 needs both
-__host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, bool pass2, bool with_v) {
+constexpr uint32_t kBMbarBytes = (kBComputeWarps * kBMaxRing + kBMaxList) * 8;
+__host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, uint32_t lblk, uint32_t nl, bool pass2, bool with_v) {
   const size_t slot = pass2 ? block_slot_bytes(4, with_v ? 2 : 1) : block_slot_bytes(2, 0);
   return ((pass2 ? 2 : 1) * ((size_t)PL + kBAccPad) + 2 * ((size_t)T + kMaxPieces)) * sizeof(double) + (size_t)kBComputeWarps * ring * slot +
-         (size_t)kBComputeWarps * kBMaxRing * 8 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
+         (size_t)nl * lblk + kBMbarBytes + kFoldThreads * 8 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
 }
-__device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, bool pass2) {
+__device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, uint32_t lblk, uint32_t nl, bool pass2) {
   // bulk copies need 16-byte aligned shared-memory addresses: PL and T + kMaxPieces are even (host), the base is rounded up
   const uint32_t b = ((uint32_t)__cvta_generic_to_shared(base) + 15u) & ~15u;
   BlockSmem s;
@@ -77,7 +96,9 @@ __device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uin
   s.wt.a = s.acc.a + (PL + kBAccPad) * 8u;
   s.wt_stride = (T + kMaxPieces) * 8u;
   s.mbar = s.wt.a + 2u * s.wt_stride;
-  s.ring = s.mbar + kBComputeWarps * kBMaxRing * 8u;
+  s.scr = s.mbar + kBMbarBytes;
+  s.lst = s.scr + kFoldThreads * 8u;
+  s.ring = s.lst + nl * lblk;
   return s;
 }
 
@@ -138,6 +159,11 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v) {
 __device__ __forceinline__ double lds64_at(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32_at(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 
@@ -214,24 +240,33 @@ __device__ __forceinline__ double block_node_total(const BlockOp& bo, uint32_t p
 }
 
 // ---------------------------------------------------------------------------- node sums of a tile (fold warps)
-// The lists of the blocked kernels keep a fold thread's entries SORTED BY NODE (tpl_blocks_host.h): the thread loads the tile
-// values of a whole batch first (independent ld.shared), adds the values of one node in a register and touches the shared
-// accumulator once per node and tile -- a dependent ld / add / st chain per ENTRY (the fold of tpl_tiles.cuh) was
-// latency-bound at ~45 instructions and ~70 cycles per entry.  Padding entries add the tile's zero slot into the dummy
-// accumulator: no branch.  `fr` holds the tile's first list batch and its piece words on entry, those of tile `next` on return.
-__device__ __forceinline__ void block_fold_request(const TileOp& to, const TileHdr& h, uint32_t q0, uint32_t pad, uint32_t (&ent)[kPre]) {
-  const uint32_t* mine = to.lent + h.e0 + (threadIdx.x - kStreamThreads);
-#pragma unroll
-  for (int q = 0; q < kPre; ++q) ent[q] = q0 + q < h.L ? __ldg(mine + (size_t)(q0 + q) * kFoldThreads) : pad;
+struct BlockTileHdr {
+  uint32_t e0, L, D;  // first word of the tile's block, entries per thread, deepest chain
+  uint32_t q0, q1;    // the tile's pieces
+};
+__device__ __forceinline__ BlockTileHdr block_tile_hdr(const TileOp& to, uint32_t tile_id) {
+  const TileHdr h = tile_hdr(to, tile_id);
+  return BlockTileHdr{h.e0, h.L & 0xffffffu, h.L >> 24, h.q0, h.q1};
 }
-__device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSmem& s, uint32_t wt, const TileHdr& h, const TileHdr& next,
-                                                bool has_next, FoldRegs& fr, uint32_t dummy) {
-  const uint32_t pad = block_pad_entry(dummy, to.T);
+__device__ __forceinline__ void block_piece_request(const TileOp& to, const BlockTileHdr& h, uint32_t (&pc)[2]) {
+  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t q = h.q0 + fwarp + kFoldWarps * (lane + 32 * i);
+    pc[i] = q < h.q1 ? __ldg(to.piece + q) : 0u;
+  }
+}
+// Adds the node sums of the tile held in buffer `wt` into s.acc; `lst` is the shared-memory copy of the tile's list block
+// (bulk-copied one tile ahead: a global load per batch of entries made the fold latency-bound -- 2.2 cycles per arc with
+// nothing else running, against 1.2 available in phase B of pass 1).  `pc` holds the tile's piece words on entry, those of
+// tile `next` (if there is one) on return.
+__device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSmem& s, uint32_t wt, uint32_t lst, const BlockTileHdr& h,
+                                                const BlockTileHdr& next, bool has_next, uint32_t (&pcw)[2], uint32_t dummy) {
   const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
   if (h.q1 > h.q0) {  // same-tail runs of the tile, one warp per piece: four lane-strided chains, xor tree
     uint32_t i = 0;
     for (uint32_t q = h.q0 + fwarp; q < h.q1; q += kFoldWarps, ++i) {
-      const uint32_t pc = __shfl_sync(0xffffffffu, i < 32 ? fr.pc[0] : fr.pc[1], i & 31);
+      const uint32_t pc = __shfl_sync(0xffffffffu, i < 32 ? pcw[0] : pcw[1], i & 31);
       const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
       const uint32_t w = wt + first * 8u;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -250,43 +285,53 @@ __device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSme
     }
     bar_sync_n(kBarFold, kFoldThreads);
   }
-  if (has_next) piece_request(to, next, fr.pc);
-  uint32_t cur = dummy;
+  if (has_next) block_piece_request(to, next, pcw);
+  // Walk of my slice: straight-line code per entry (value load, sign, add; a node change is a predicated read-modify-write of
+  // the previous node's accumulator).  The share of my first node goes to my scratch word instead when earlier threads hold
+  // entries of the same node (depth > 0) and is added chain position by chain position afterwards.
+  const uint32_t mine = lst + (uint32_t)ftid * 4u;  // row q of my slice at mine + (q + 1) * 4 * kFoldThreads
+  const uint32_t depth = lds32<0>(mine);
+  const uint32_t my_scr = s.scr + (uint32_t)ftid * 8u;
+  if (depth) asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_scr), "d"(0.0));
+  uint32_t tgt = s.acc.a + dummy * 8u;       // accumulator of the node being added
+  uint32_t first_tgt = depth ? my_scr : 0u;  // non-zero until my first node has taken it
   double sum = 0.0;
+  auto entry = [&](uint32_t ent, double x) __attribute__((always_inline)) {
+    const double val = __hiloint2double(__double2hiint(x) ^ (int)(ent & kBEntMinus), __double2loint(x));
+    if (ent & kBEntNew) {  // the previous node of this slice is complete
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(tgt), "d"(__dadd_rn(lds64_at(tgt), sum)));
+      const uint32_t own = s.acc.a + ((ent >> kBEntNodeShift) & kBEntNodeMask) * 8u;
+      tgt = first_tgt ? first_tgt : own;
+      first_tgt = 0u;
+      sum = 0.0;
+    }
+    sum = __dadd_rn(sum, val);
+  };
+  uint32_t row = mine + 4u * kFoldThreads;
   uint32_t q0 = 0;
-  do {  // (runs once for an empty list: the first batch of the next tile still has to be requested)
-    uint32_t nxt[kPre];
-    if (q0 + kPre < h.L) {
-      block_fold_request(to, h, q0 + kPre, pad, nxt);
-    } else if (has_next) {
-      block_fold_request(to, next, 0, pad, nxt);
-    } else {
+  for (; q0 + kBPre <= h.L; q0 += kBPre, row += kBPre * 4u * kFoldThreads) {  // whole batches: no bounds checks
+    uint32_t ent[kBPre];
+    double x[kBPre];
 #pragma unroll
-      for (int q = 0; q < kPre; ++q) nxt[q] = pad;
+    for (int q = 0; q < kBPre; ++q) ent[q] = lds32_at(row + q * (4u * kFoldThreads));
+#pragma unroll
+    for (int q = 0; q < kBPre; ++q) x[q] = lds64_at(wt + (ent[q] & kBEntOffMask));  // the batch's tile values: independent loads
+#pragma unroll
+    for (int q = 0; q < kBPre; ++q) entry(ent[q], x[q]);
+  }
+  for (; q0 < h.L; ++q0, row += 4u * kFoldThreads) {  // the rest, one by one (L is the same for every thread)
+    const uint32_t ent = lds32_at(row);
+    entry(ent, lds64_at(wt + (ent & kBEntOffMask)));
+  }
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(tgt), "d"(__dadd_rn(lds64_at(tgt), sum)));
+  if (h.D) {
+    const uint32_t e1 = h.L ? lds32_at(mine + 4u * kFoldThreads) : 0u;  // my first entry names the node my scratch word belongs to
+    const uint32_t dn = s.acc.a + ((e1 >> kBEntNodeShift) & kBEntNodeMask) * 8u;
+    for (uint32_t d = 1; d <= h.D; ++d) {  // shares of straddling nodes, chain position by chain position
+      bar_sync_n(kBarFold, kFoldThreads);
+      if (depth == d) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dn), "d"(__dadd_rn(lds64_at(dn), lds64_at(my_scr))));
     }
-    if (q0 < h.L) {
-      double val[kPre];
-#pragma unroll
-      for (int q = 0; q < kPre; ++q) {  // the whole batch's tile values first: independent loads
-        const long long x = __double_as_longlong(lds64_at(wt + (fr.ent[q] & 0x3fffu) * 8u)) ^ ((long long)(fr.ent[q] & 0x4000u) << 49);
-        val[q] = __longlong_as_double(x);
-      }
-#pragma unroll
-      for (int q = 0; q < kPre; ++q) {
-        const uint32_t node = fr.ent[q] >> 15;
-        if (node != cur) {  // the previous node is complete: one read-modify-write of its accumulator
-          sm_st(s.acc, cur, __dadd_rn(sm_ld(s.acc, cur), sum));
-          cur = node;
-          sum = 0.0;
-        }
-        sum = __dadd_rn(sum, val[q]);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < kPre; ++q) fr.ent[q] = nxt[q];
-    q0 += kPre;
-  } while (q0 < h.L);
-  sm_st(s.acc, cur, __dadd_rn(sm_ld(s.acc, cur), sum));
+  }
 }
 
 // ---------------------------------------------------------------------------- the folding sweep
@@ -299,14 +344,18 @@ __device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSme
 // the compute warps fill the other tile buffer (named barriers as in tile_loop).  `rs` (ring slot and mbarrier phase of this
 // warp's next stage) lives across the sweeps of a kernel: the mbarriers are initialised once.
 struct RingState {
-  uint32_t slot, phase;
+  uint32_t slot, phase;  // compute warps: ring slot and mbarrier phase of the next stage
+  uint32_t lphase;       // fold warps: bit b = phase of list buffer b's mbarrier
 };
 template <int N8, int N4, class CONSUME>
 __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
                                            const double* const (&src8)[N8], const uint32_t* const (&src4)[N4 ? N4 : 1],
-                                           CONSUME consume, RingState& rs) {
+                                           CONSUME consume, RingState& rs, const Trace* tr = nullptr, int tr_step = -1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t SPT = bo.tl.T / kBStage;  // stages per tile (a multiple of 8)
+  const bool timed = tr != nullptr && tr->buf != nullptr && tr_step >= 0 && tr_step < tr->max_steps;
+  long long c_a = 0, c_b = 0, c_tot = 0, t_x = 0;  // diagnostics: cycles waiting for data / for the other role, total
+  if (timed) c_tot = -clock64();
   if (warp < kBComputeWarps) {
     const uint32_t nk = c.nst > (uint32_t)warp ? (c.nst - warp + kBComputeWarps - 1) / kBComputeWarps : 0;  // my stages
     const uint32_t ring0 = s.ring + (uint32_t)warp * RING * slot_bytes, bar0 = s.mbar + (uint32_t)warp * kBMaxRing * 8u;
@@ -329,12 +378,16 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
     }
     uint32_t k = 0;
     for (uint32_t t = 0; t < c.ntiles; ++t) {
+      if (timed) t_x = clock64();
       if (t >= 2) bar_sync_n(kBarEmpty + (t & 1u), kBlock);  // the fold of tile t - 2 has left this buffer
+      if (timed) c_b += clock64() - t_x;
       const uint32_t wt0 = s.wt.a + (t & 1u) * s.wt_stride;
       uint32_t g = t * SPT + warp;
       for (uint32_t i = 0; i < SPT / kBComputeWarps && g < c.nst; ++i, g += kBComputeWarps) {
+        if (timed) t_x = clock64();
         mbar_wait(bar0 + rs.slot * 8u, rs.phase);
-        consume(c.c0 + g * kBStage, ring0 + rs.slot * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), lane);
+        if (timed) c_a += clock64() - t_x;
+        if (!(bo.dbg & 2u)) consume(c.c0 + g * kBStage, ring0 + rs.slot * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), lane);
         __syncwarp();  // every lane has read its slot words
         if (lane == 0 && k + RING < nk) issue(k + RING, rs.slot);
         ++k;
@@ -348,21 +401,58 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
     // drain: every arrival of the fold warps is matched by a wait, so that the barriers are clean for the next sweep
     for (uint32_t u = c.ntiles > 2 ? c.ntiles - 2 : 0; u < c.ntiles; ++u) bar_sync_n(kBarEmpty + (u & 1u), kBlock);
     fence_proxy_async();  // the vector just written is bulk-copied by the next sweep (after the grid barrier in between)
-  } else {
-    const uint32_t tile0 = blockIdx.x * bo.tl.ntile, dummy = bo.PT + bo.PH;
-    TileHdr hdr = tile_hdr(bo.tl, tile0);
-    FoldRegs fr;
-    if (c.ntiles) {
-      block_fold_request(bo.tl, hdr, 0, block_pad_entry(dummy, bo.tl.T), fr.ent);
-      piece_request(bo.tl, hdr, fr.pc);
+    if (timed && threadIdx.x == 0) {
+      unsigned long long* q = tr->buf + ((size_t)blockIdx.x * tr->max_steps + tr_step) * kTraceMarks;
+      q[16] = (unsigned long long)c_a;                 // compute warp 0: waiting for bulk copies
+      q[17] = (unsigned long long)c_b;                 // ... for the fold to release a tile buffer
+      q[18] = (unsigned long long)(c_tot + clock64()); // ... whole sweep
     }
+  } else {
+    // Fold warps.  The list block of tile t is bulk-copied into list buffer t % nl by fold thread 0: tiles 0 .. nl - 1 at the
+    // start of the sweep, tile t - 1 + nl as soon as every fold thread has left tile t - 1 (= has passed the full-barrier of
+    // tile t).  Short sweeps (small cells) thus have their whole list in flight from the start.
+    const uint32_t tile0 = blockIdx.x * bo.tl.ntile, dummy = bo.PT + bo.PH, nl = bo.nl;
+    const uint32_t lbar = s.mbar + kBComputeWarps * kBMaxRing * 8u;
+    const bool issuer = threadIdx.x == kStreamThreads;
+    auto fetch = [&](const BlockTileHdr& h, uint32_t b) __attribute__((always_inline)) {  // issuer only
+      const uint32_t bytes = (h.L + 1u) * (4u * kFoldThreads);
+      mbar_expect_tx(lbar + b * 8u, bytes);
+      bulk_g2s(s.lst + b * bo.lblk, bo.tl.lent + h.e0, bytes, lbar + b * 8u);
+    };
+    BlockTileHdr h0 = block_tile_hdr(bo.tl, tile0), h1 = h0, hf = h0;
+    if (c.ntiles > 1) h1 = block_tile_hdr(bo.tl, tile0 + 1);
+    uint32_t pcw[2] = {0u, 0u};
+    if (c.ntiles) {
+      if (issuer) {
+        for (uint32_t u = 0; u < nl && u < c.ntiles; ++u) fetch(block_tile_hdr(bo.tl, tile0 + u), u);
+        if (nl < c.ntiles) hf = block_tile_hdr(bo.tl, tile0 + nl);  // the next block to fetch
+      }
+      block_piece_request(bo.tl, h0, pcw);
+    }
+    uint32_t b = 0;  // list buffer of tile t
     for (uint32_t t = 0; t < c.ntiles; ++t) {
-      TileHdr next = hdr;
-      if (t + 1 < c.ntiles) next = tile_hdr(bo.tl, tile0 + t + 1);
+      BlockTileHdr h2 = h1;
+      if (t + 2 < c.ntiles) h2 = block_tile_hdr(bo.tl, tile0 + t + 2);
+      if (timed) t_x = clock64();
       bar_sync_n(kBarFull + (t & 1u), kBlock);
-      block_fold_tile(bo.tl, s, s.wt.a + (t & 1u) * s.wt_stride, hdr, next, t + 1 < c.ntiles, fr, dummy);
+      if (timed) c_a += clock64() - t_x;
+      if (issuer && t >= 1 && t - 1 + nl < c.ntiles) {  // every fold thread has left tile t - 1: its buffer is free
+        fetch(hf, b == 0 ? nl - 1 : b - 1);
+        if (t + nl < c.ntiles) hf = block_tile_hdr(bo.tl, tile0 + t + nl);
+      }
+      mbar_wait(lbar + b * 8u, (rs.lphase >> b) & 1u);
+      rs.lphase ^= 1u << b;
+      if (!(bo.dbg & 1u))
+        block_fold_tile(bo.tl, s, s.wt.a + (t & 1u) * s.wt_stride, s.lst + b * bo.lblk, h0, h1, t + 1 < c.ntiles, pcw, dummy);
       bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
-      hdr = next;
+      h0 = h1;
+      h1 = h2;
+      b = b + 1 == nl ? 0 : b + 1;
+    }
+    if (timed && threadIdx.x == kStreamThreads) {
+      unsigned long long* q = tr->buf + ((size_t)blockIdx.x * tr->max_steps + tr_step) * kTraceMarks;
+      q[19] = (unsigned long long)c_a;                 // fold warp 0: waiting for a full tile
+      q[20] = (unsigned long long)(c_tot + clock64()); // ... whole sweep
     }
   }
   __syncthreads();
@@ -370,7 +460,7 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
 
 // mbarriers of the rings, and the zero slot of both tile buffers that padding list entries read
 __device__ __forceinline__ void init_block_smem(const BlockOp& bo, const BlockSmem& s) {
-  if (threadIdx.x < kBComputeWarps * kBMaxRing) mbar_init(s.mbar + threadIdx.x * 8u, 1);
+  if (threadIdx.x < kBComputeWarps * kBMaxRing + kBMaxList) mbar_init(s.mbar + threadIdx.x * 8u, 1);
   if (threadIdx.x < 2) sm_st(SmArr{s.wt.a + threadIdx.x * s.wt_stride}, bo.tl.T + kMaxPieces - 1, 0.0);
   fence_mbar_init();
   __syncthreads();
@@ -404,7 +494,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
   extern __shared__ double smem[];
   __shared__ CtaShared sh;
   const uint32_t PL = bo.PT + bo.PH, p = op.p, m = bo.m, M = bo.Mpad;
-  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, false);
+  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, bo.lblk, bo.nl, false);
   const BlockCtx c = block_ctx(bo, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t RING = bo.ring1;
@@ -413,7 +503,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
   init_block_smem(bo, s);
 
   unsigned int epoch = a.st->epoch;
-  RingState rs{0u, 0u};
+  RingState rs{0u, 0u, 0u};
   int steps = 0, status = ST_RUNNING, rot = 0;
   double sc = 1.0, sp = 1.0, bp = 0.0, bnorm = 0.0;
   GridSync gs = a.gs;
@@ -457,8 +547,11 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
       double* Vcol = WITH_V ? a.V + (size_t)j * a.ldv : nullptr;
 
       // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
+      gs.trace_step = j;
+      trace_mark(gs.trace, j, 0);
       stage_block_nodes(bo, s, c, Xnode, sc);
       __syncthreads();
+      trace_mark(gs.trace, j, 1);
       if (WITH_V) {  // node part of the basis column: replicated on every rank, each CTA writes its share
         uint32_t vlo, vhi;
         cta_chunk(p, vlo, vhi);
@@ -475,6 +568,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
           __stcg(Wn + M + u, wt);
         }
       }
+      trace_mark(gs.trace, j, 2);
       for (uint32_t base = c.c0; base < c.c1; base += kUnroll * kBlock) {
         double wc[kUnroll], wp[kUnroll], dd[kUnroll];
         uint32_t th[kUnroll], gi[kUnroll];
@@ -503,6 +597,8 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
         }
       }
       fence_proxy_async();  // w~ is bulk-copied by phase B
+      trace_mark(gs.trace, j, 3);
+      gs.trace_base = 4;
       const double alpha = tile_sync<true, false>(acc, to, gs, epoch, sh);
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
@@ -516,6 +612,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
         acc = fma(w, w, acc);
       }
       __syncthreads();  // accumulators are zero before the first fold
+      trace_mark(gs.trace, j, 8);
       {
         const double* const src8[2] = {Wn, Wc};
         const uint32_t* const src4[1] = {nullptr};
@@ -542,9 +639,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc = fma(w[q], w[q], acc);
             },
-            rs);
+            rs, &gs.trace, j);
       }
+      trace_mark(gs.trace, j, 9);
       publish_block_partials(bo, s, c, (j + 1) & 1);
+      trace_mark(gs.trace, j, 10);
+      gs.trace_base = 11;
       const double beta = sqrt(tile_sync<true>(acc, to, gs, epoch, sh));
 
       if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -584,7 +684,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
   extern __shared__ double smem[];
   __shared__ CtaShared sh;
   const uint32_t PL = bo.PT + bo.PH, p = op.p, m = bo.m, M = bo.Mpad;
-  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, true);
+  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, bo.lblk, bo.nl, true);
   const BlockCtx c = block_ctx(bo, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t RING = WITH_V ? bo.ring2v : bo.ring2;
@@ -594,7 +694,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
   uint32_t vlo, vhi;  // share of the (replicated) node part of x / V this CTA writes
   cta_chunk(p, vlo, vhi);
   unsigned int epoch = a.st->epoch;
-  RingState rs{0u, 0u};
+  RingState rs{0u, 0u, 0u};
   double* const buf0 = a.buf[0];
   double* const buf1 = a.buf[1];
   double* const buf2 = a.buf[2];
@@ -649,6 +749,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
     const double bp = j == 0 ? 0.0 : __ldg(a.betas + j - 1);
     const double sinv = 1.0 / beta;
     const double yj = __ldg(a.y + j + 1);
+    GridSync gs = a.gs;
+    gs.trace_step = j;
+    trace_mark(gs.trace, j, 0);
 
     stage_block_nodes(bo, s, c, Xnode, 1.0);
     zero_block_acc(bo, s);
@@ -672,6 +775,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
       }
     }
     __syncthreads();  // node values are staged, accumulators are zero
+    trace_mark(gs.trace, j, 1);
     {
       const double* const src8[4] = {Vc, Vp, xc, bo.d};
       const uint32_t* const src4[2] = {bo.th, bo.gidx};
@@ -723,12 +827,15 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
         }
       };
       if (WITH_V)
-        fold_sweep<4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, rs);
+        fold_sweep<4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, rs, &gs.trace, j);
       else
-        fold_sweep<4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, rs);
+        fold_sweep<4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, rs, &gs.trace, j);
     }
+    trace_mark(gs.trace, j, 2);
     publish_block_partials(bo, s, c, (j + 1) & 1);
-    tile_sync<false>(0.0, to, a.gs, epoch, sh);
+    trace_mark(gs.trace, j, 3);
+    gs.trace_base = 4;
+    tile_sync<false>(0.0, to, gs, epoch, sh);
     rot = (rot + 1) % 3;
     sc_cur = sinv;
   }

@@ -6,9 +6,7 @@
 //   2. cell order: arc j belongs to cell (tail block of tail_j) * GC + (head block of head_j); inside a cell the arcs are
 //      ordered by tail node, then by arc index (two stable counting sorts), every cell is padded to a multiple of 128 slots;
 //   3. per position: d, the packed th word (local tail | local head << 15 | tail-first | loop-or-padding) and gidx;
-//   4. tile lists of every cell over LOCAL node ids (tails [0, PT), heads [PT, PT + PH)) by the builder of the tiled
-//      kernels (tpl_tiles_host.h): a cell is handed to it as a one-CTA instance; a fold thread's entries stay sorted by node
-//      and list padding becomes a harmless entry (the tile's zero slot into a dummy accumulator).
+//   4. tile lists of every cell over LOCAL node ids (tails [0, PT), heads [PT, PT + PH)): build_cell_lists below.
 // Cells are independent: they are built by a pool of host threads and concatenated in cell order (the result does not depend
 // on the number of threads).
 #pragma once
@@ -27,7 +25,7 @@ namespace tpl {
 struct HostBlocks {
   bool ok = false;
   uint32_t GR = 0, GC = 0, PT = 0, PH = 0, Mpad = 0, T = 0, ntile = 0;
-  uint32_t ring1 = 0, ring2 = 0, ring2v = 0;
+  uint32_t ring1 = 0, ring2 = 0, ring2v = 0, lblk = 0, nl = 2;
   std::vector<uint32_t> cell_off, tbs, hbs, th, gidx;
   std::vector<double> d;
   std::vector<uint4> thdr;
@@ -53,23 +51,104 @@ inline std::vector<uint32_t> weight_blocks(const std::vector<uint64_t>& weight, 
   return bnd;
 }
 
-// Tile size (multiple of 1024 arcs, at most 4096) and ring depths for which the kernels fit in `smem_limit` bytes: the largest
-// tile that still leaves three ring slots to pass 2 (bytes in flight matter more than hand-offs per sweep), else the largest
-// tile that fits with two.
-inline bool blocks_fit(uint32_t PL, size_t smem_limit, size_t max_cell, uint32_t& T, uint32_t& ring1, uint32_t& ring2, uint32_t& ring2v) {
+// Ring depths for which the kernels fit in `smem_limit` bytes with tiles of T arcs and list buffers of lblk bytes; `need` = the
+// least number of ring slots pass 2 must get.
+inline bool blocks_fit(uint32_t PL, size_t smem_limit, uint32_t T, uint32_t lblk, int need, uint32_t& ring1, uint32_t& ring2, uint32_t& ring2v) {
   const size_t budget = smem_limit > 3072 ? smem_limit - 3072 : 0;  // static shared memory of the kernels + margin
-  const uint32_t want = (uint32_t)std::min<size_t>(4096, std::max<size_t>(1024, (max_cell + 1023) / 1024 * 1024));
-  for (int need = 3; need >= 2; --need)
-    for (uint32_t t = want; t >= 1024; t -= 1024) {
-      auto fits = [&](int ring, bool pass2, bool v) { return block_smem_bytes(PL, t, ring, pass2, v) <= budget; };
-      if (!fits(need, true, false) || !fits(2, true, true) || !fits(2, false, false)) continue;
-      T = t;
-      ring2 = fits(4, true, false) ? 4 : fits(3, true, false) ? 3 : 2;
-      ring2v = fits(3, true, true) ? 3 : 2;
-      ring1 = fits(4, false, false) ? 4 : fits(3, false, false) ? 3 : 2;
-      return true;
+  auto fits = [&](int ring, bool pass2, bool v) { return block_smem_bytes(PL, T, ring, lblk, 2, pass2, v) <= budget; };
+  if (!fits(need, true, false) || !fits(2, true, true) || !fits(2, false, false)) return false;
+  ring2 = fits(4, true, false) ? 4 : fits(3, true, false) ? 3 : 2;
+  ring2v = fits(3, true, true) ? 3 : 2;
+  ring1 = fits(4, false, false) ? 4 : fits(3, false, false) ? 3 : 2;
+  return true;
+}
+
+// Tile lists of ONE cell in the blocked format (entries over local node ids; see tpl_blocks.cuh "list format"):
+// per tile the same-tail runs become pieces, every remaining tail entry, every piece and every head entry is one list entry;
+// the entries are sorted by node (stable: a node's tail side in arc order, then its head side) and cut into kFoldThreads
+// slices of EQUAL length L -- a node may straddle threads: thread i then adds its share of the node `depth_i` barrier phases
+// after the thread that holds the node's first entry (depth = position in the chain of threads that share the node), which
+// keeps the summation order fixed.  Row 0 of a tile's block holds the per-thread depth, rows 1..L the entries,
+// thread-interleaved.  thdr = {first word, L | max depth << 24, first piece, end piece}.
+struct BlockListScratch {
+  std::vector<uint32_t> cnt, e_node, e_code, s_node, s_code, order;
+};
+inline bool build_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const uint32_t* hl, uint32_t T, uint32_t ntile,
+                             BlockListScratch& w, std::vector<uint4>& thdr, std::vector<uint32_t>& lent, std::vector<uint32_t>& piece) {
+  const uint32_t B = kFoldThreads, pad = block_pad_entry(PL, T);
+  w.cnt.resize((size_t)PL + 1);
+  thdr.assign(ntile, make_uint4(0, 0, 0, 0));
+  lent.clear();
+  piece.clear();
+  for (uint32_t t = 0; t < ntile; ++t) {
+    const uint32_t t0 = std::min(n, t * T), t1 = std::min(n, t0 + T);
+    const uint32_t q0 = (uint32_t)piece.size();
+    w.e_node.clear();
+    w.e_code.clear();
+    uint32_t npieces = 0;
+    for (uint32_t i = t0; i < t1;) {  // tail side: maximal runs of equal tail (loops / padding contribute nothing)
+      if (tl[i] == hl[i]) {
+        ++i;
+        continue;
+      }
+      uint32_t j = i;
+      while (j < t1 && tl[j] == tl[i] && tl[j] != hl[j]) ++j;
+      const uint32_t len = j - i, need = (len + kPieceMax - 1) / kPieceMax;
+      if (len >= kPieceMin && npieces + need <= kMaxPieces - 1) {
+        for (uint32_t q = i; q < j; q += kPieceMax) {
+          const uint32_t l = std::min<uint32_t>(kPieceMax, j - q);
+          piece.push_back((q - t0) | ((l - 1) << 16));
+          w.e_node.push_back(tl[i]);
+          w.e_code.push_back((T + npieces) * 8u);
+          ++npieces;
+        }
+      } else {
+        for (uint32_t q = i; q < j; ++q) {
+          w.e_node.push_back(tl[i]);
+          w.e_code.push_back((q - t0) * 8u);
+        }
+      }
+      i = j;
     }
-  return false;
+    for (uint32_t i = t0; i < t1; ++i)  // head side
+      if (tl[i] != hl[i]) {
+        w.e_node.push_back(hl[i]);
+        w.e_code.push_back(((i - t0) * 8u) | kBEntMinus);
+      }
+    const uint32_t ne = (uint32_t)w.e_node.size();
+    std::fill(w.cnt.begin(), w.cnt.end(), 0u);
+    for (uint32_t e = 0; e < ne; ++e) ++w.cnt[w.e_node[e] + 1];
+    for (uint32_t u = 0; u < PL; ++u) w.cnt[u + 1] += w.cnt[u];
+    w.s_node.resize(ne);
+    w.s_code.resize(ne);
+    w.order.assign(w.cnt.begin(), w.cnt.end() - 1);
+    for (uint32_t e = 0; e < ne; ++e) {
+      const uint32_t dst = w.order[w.e_node[e]]++;
+      w.s_node[dst] = w.e_node[e];
+      w.s_code[dst] = w.e_code[e];
+    }
+    const uint32_t L = (ne + B - 1) / B;
+    const size_t base = lent.size();
+    if (base + (size_t)(L + 1) * B >= 0xffffffffull) return false;
+    lent.resize(base + (size_t)(L + 1) * B, pad);
+    uint32_t maxdepth = 0, prev_depth = 0;
+    for (uint32_t i = 0; i < B; ++i) {
+      const uint32_t s0 = std::min(ne, i * L), s1 = std::min(ne, s0 + L);
+      uint32_t depth = 0;
+      if (s0 < s1 && i > 0 && s0 > 0 && w.s_node[s0] == w.s_node[s0 - 1])
+        depth = (w.s_node[s0 - L] == w.s_node[s0 - 1]) ? prev_depth + 1 : 1;  // thread i-1 holds only that node: one deeper
+      prev_depth = depth;
+      maxdepth = std::max(maxdepth, depth);
+      lent[base + i] = depth;
+      for (uint32_t e = s0; e < s1; ++e) {
+        const bool first = e == s0 || w.s_node[e] != w.s_node[e - 1];
+        lent[base + (size_t)(e - s0 + 1) * B + i] = w.s_code[e] | (w.s_node[e] << kBEntNodeShift) | (first ? kBEntNew : 0u);
+      }
+    }
+    if (maxdepth > 255) return false;
+    thdr[t] = make_uint4((uint32_t)base, L | (maxdepth << 24), q0, (uint32_t)piece.size());
+  }
+  return true;
 }
 
 inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len, int G,
@@ -91,7 +170,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   for (uint32_t b = 0; b < h.GC; ++b) PH = std::max(PH, h.hbs[b + 1] - h.hbs[b]);
   PT = (PT + 1u) & ~1u;  // even: 16-byte aligned shared-memory arrays
   PH = (PH + 1u) & ~1u;
-  if (PT > 0x8000u || PH > 0x8000u || PT + PH >= (1u << 17)) return;  // 15-bit local ids, 17-bit list nodes
+  if (PT > 0x8000u || PH > 0x8000u || PT + PH + kBAccPad > kBMaxLocalNodes) return;  // 15-bit local ids, 14-bit list nodes
   h.PT = PT;
   h.PH = PH;
   std::vector<uint32_t> node_tb(p), node_hb(p);
@@ -121,8 +200,6 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   }
   h.cell_off[Gc] = (uint32_t)off;
   h.Mpad = (uint32_t)off;
-  if (!blocks_fit(PT + PH, smem_limit, (size_t)max_cell, h.T, h.ring1, h.ring2, h.ring2v)) return;
-  h.ntile = (uint32_t)std::max<uint64_t>(1, ((max_cell + kBStage - 1) / kBStage * kBStage + h.T - 1) / h.T);
 
   h.d.assign(h.Mpad, 0.0);
   h.th.assign(h.Mpad, kBLoop);
@@ -139,36 +216,68 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   }
   std::vector<uint32_t>().swap(by_tail);
 
-  // tile lists per cell, over local node ids; a loop / padding slot gets tail == head (the list builder skips those)
+  // tile lists per cell, over local node ids; a loop / padding slot gets tail == head (the list builder skips those).
+  // Tile size: the largest multiple of 1024 arcs (at most 4096) whose kernels fit with three ring slots in pass 2 (bytes in
+  // flight matter more than hand-offs per sweep), else the largest that fits with two.  The list buffers depend on the lists
+  // themselves ((L + 1) KB per tile), so a size that does not fit is rebuilt one step smaller.
   if (threads <= 0) threads = m < (1u << 20) ? 1 : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
   threads = std::min<int>(threads, (int)Gc);
   std::vector<std::vector<uint4>> thdr(Gc);
   std::vector<std::vector<uint32_t>> lent(Gc), piece(Gc);
-  auto run = [&](int first) {
-    TileScratch w;
-    std::vector<uint32_t> tl, hl;
-    for (uint32_t c = (uint32_t)first; c < Gc; c += (uint32_t)threads) {
-      const uint32_t c0 = h.cell_off[c], n = h.cell_off[c + 1] - c0;
-      tl.resize(n);
-      hl.resize(n);
-      for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t w32 = h.th[c0 + i];
-        const bool skip = (w32 & kBLoop) != 0;
-        tl[i] = skip ? 0u : (w32 & 0x7fffu);
-        hl[i] = skip ? 0u : PT + ((w32 >> 15) & 0x7fffu);
+  const uint32_t padded_max = (uint32_t)((max_cell + kBStage - 1) / kBStage * kBStage);
+  // at least ~8 tiles per cell, so that the fold of one tile overlaps the stream of the next also on small instances
+  const uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max / 8 + 1023) / 1024 * 1024));
+  bool done = false;
+  for (int need = 3; need >= 2 && !done; --need)
+    for (uint32_t T = want; T >= 1024 && !done; T -= 1024) {
+      // cheap bound first: L >= entries / threads >= (arcs of a full tile) / threads
+      if (!blocks_fit(PT + PH, smem_limit, T, (std::min(T, padded_max) / kFoldThreads + 1) * 4u * kFoldThreads, need, h.ring1, h.ring2, h.ring2v))
+        continue;
+      h.T = T;
+      h.ntile = std::max<uint32_t>(1, (padded_max + T - 1) / T);
+      std::vector<uint8_t> failed(Gc, 0);
+      auto run = [&](int first) {
+        BlockListScratch w;
+        std::vector<uint32_t> tl, hl;
+        for (uint32_t c = (uint32_t)first; c < Gc; c += (uint32_t)threads) {
+          const uint32_t c0 = h.cell_off[c], n = h.cell_off[c + 1] - c0;
+          tl.resize(n);
+          hl.resize(n);
+          for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t w32 = h.th[c0 + i];
+            const bool skip = (w32 & kBLoop) != 0;
+            tl[i] = skip ? 0u : (w32 & 0x7fffu);
+            hl[i] = skip ? 0u : PT + ((w32 >> 15) & 0x7fffu);
+          }
+          failed[c] = !build_cell_lists(n, PT + PH, tl.data(), hl.data(), h.T, h.ntile, w, thdr[c], lent[c], piece[c]);
+        }
+      };
+      if (threads == 1) {
+        run(0);
+      } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(run, t);
+        for (std::thread& t : pool) t.join();
       }
-      build_cta_tiles(n, PT + PH, tl.data(), hl.data(), 1, h.T, h.ntile, 0, w, thdr[c], lent[c], piece[c], false, kMaxPieces - 1);
-      const uint32_t pad = block_pad_entry(PT + PH, h.T);  // padding = zero slot of the tile into the dummy accumulator
-      for (uint32_t& e : lent[c])
-        if (e == kEntPad) e = pad;
+      uint32_t Lmax = 0;
+      bool bad = false;
+      for (uint32_t c = 0; c < Gc; ++c) {
+        bad = bad || failed[c];
+        for (const uint4& x : thdr[c]) Lmax = std::max(Lmax, x.y & 0xffffffu);
+      }
+      if (bad) return;
+      h.lblk = (Lmax + 1) * 4u * kFoldThreads;
+      done = blocks_fit(PT + PH, smem_limit, T, h.lblk, need, h.ring1, h.ring2, h.ring2v);
     }
-  };
-  if (threads == 1) {
-    run(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t) pool.emplace_back(run, t);
-    for (std::thread& t : pool) t.join();
+  if (!done) return;
+  {  // as many list buffers as still fit next to the rings (deeper list prefetch; a short sweep then starts with its whole list in flight)
+    const size_t budget = smem_limit > 3072 ? smem_limit - 3072 : 0;
+    h.nl = 2;
+    while (h.nl < (uint32_t)kBMaxList && h.nl < h.ntile &&
+           block_smem_bytes(PT + PH, h.T, (int)h.ring2v, h.lblk, h.nl + 1, true, true) <= budget &&
+           block_smem_bytes(PT + PH, h.T, (int)h.ring2, h.lblk, h.nl + 1, true, false) <= budget &&
+           block_smem_bytes(PT + PH, h.T, (int)h.ring1, h.lblk, h.nl + 1, false, false) <= budget)
+      ++h.nl;
   }
   size_t nl = 0, np = 0;
   for (uint32_t c = 0; c < Gc; ++c) {
@@ -193,6 +302,86 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   h.ok = true;
 }
 
+// 0 when the lists of a cell hold, for every tile, each non-loop arc exactly once on its local head (minus) and once on its
+// local tail (directly or inside one piece), slices have equal length with padding only behind the last entry, the new-node
+// flags mark exactly the node changes inside a slice, entries are sorted by node across the slices, and every thread's depth
+// is its position in the chain of threads that share its first node.
+inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const uint32_t* hl, uint32_t T, uint32_t ntile,
+                            const uint4* thdr, const std::vector<uint32_t>& lent, const std::vector<uint32_t>& piece) {
+  const uint32_t B = kFoldThreads, pad = block_pad_entry(PL, T);
+  std::vector<uint8_t> seen_t(T), seen_h(T);
+  for (uint32_t t = 0; t < ntile; ++t) {
+    const uint4 hd = thdr[t];
+    const uint32_t L = hd.y & 0xffffffu, D = hd.y >> 24;
+    const uint32_t t0 = std::min(n, t * T), t1 = std::min(n, t0 + T), na = t1 - t0;
+    if ((size_t)hd.x + (size_t)(L + 1) * B > lent.size() || hd.z > hd.w || hd.w > piece.size()) return 2;
+    if (hd.w - hd.z > kMaxPieces - 1) return 3;
+    std::fill(seen_t.begin(), seen_t.end(), 0);
+    std::fill(seen_h.begin(), seen_h.end(), 0);
+    uint32_t prev_node = 0, prev_depth = 0, maxdepth = 0;
+    bool prev_single = false, any = false, ended = false;
+    for (uint32_t i = 0; i < B; ++i) {
+      const uint32_t depth = lent[hd.x + i];
+      uint32_t first_node = 0, last_node = 0, cnt = 0;
+      bool single = true;
+      for (uint32_t q = 0; q < L; ++q) {
+        const uint32_t e = lent[hd.x + (size_t)(q + 1) * B + i];
+        if (e == pad) {
+          ended = true;  // padding only behind the very last entry of the tile
+          continue;
+        }
+        if (ended) return 4;
+        const uint32_t node = (e >> kBEntNodeShift) & kBEntNodeMask, idx = (e & kBEntOffMask) / 8u;
+        if ((e & kBEntOffMask) % 8u) return 17;
+        if (node >= PL) return 5;
+        const bool isnew = (e & kBEntNew) != 0;
+        if (cnt == 0) {
+          if (!isnew) return 6;
+          first_node = node;
+        } else {
+          if (isnew != (node != last_node) || node < last_node) return 7;
+          if (node != last_node) single = false;
+        }
+        if (any && cnt == 0 && node < prev_node) return 8;  // sorted across slices
+        last_node = node;
+        ++cnt;
+        if (e & kBEntMinus) {  // head side
+          if (idx >= na || hl[t0 + idx] != node || seen_h[idx]) return 9;
+          seen_h[idx] = 1;
+        } else if (idx >= T) {  // a piece
+          const uint32_t q1 = hd.z + (idx - T);
+          if (q1 >= hd.w) return 10;
+          const uint32_t start = piece[q1] & 0xffffu, len = (piece[q1] >> 16) + 1;
+          if (len > kPieceMax || start + len > na) return 11;
+          for (uint32_t a = start; a < start + len; ++a) {
+            if (tl[t0 + a] != node || seen_t[a]) return 12;
+            seen_t[a] = 1;
+          }
+        } else {
+          if (idx >= na || tl[t0 + idx] != node || seen_t[idx]) return 13;
+          seen_t[idx] = 1;
+        }
+      }
+      uint32_t want = 0;
+      if (cnt && any && first_node == prev_node) want = prev_single ? prev_depth + 1 : 1;
+      if (depth != want) return 14;
+      maxdepth = std::max(maxdepth, depth);
+      if (cnt) {
+        prev_node = last_node;
+        prev_single = single;
+        prev_depth = depth;
+        any = true;
+      }
+    }
+    if (maxdepth != D) return 15;
+    for (uint32_t a = 0; a < na; ++a) {
+      const bool loop = tl[t0 + a] == hl[t0 + a];
+      if (seen_t[a] != (loop ? 0 : 1) || seen_h[a] != (loop ? 0 : 1)) return 16;
+    }
+  }
+  return 0;
+}
+
 // 0 when the layout is consistent: gidx is a bijection between the non-padding positions and the arcs; every position's
 // th word decodes to its arc's tail / head inside the cell's blocks, with the right order / loop flags; d is carried over;
 // cells are padded to stage multiples; inside a cell the arcs are sorted by (tail, arc index); the tile lists of every cell
@@ -206,30 +395,6 @@ inline int check_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t
   if (h.T % 1024 != 0 || h.T == 0 || (h.PT & 1u) || (h.PH & 1u)) return 4;
   std::vector<uint8_t> seen(m, 0);
   std::vector<uint32_t> tl, hl;
-  HostTiles one;  // a cell's lists as a one-CTA instance: thdr offsets are global, so lent / piece stay whole
-  one.T = h.T;
-  one.ntile = h.ntile;
-  one.lent = h.lent;
-  one.piece = h.piece;
-  for (uint32_t& e : one.lent)
-    if (e == block_pad_entry(h.PT + h.PH, h.T)) e = kEntPad;
-  // a thread's entries are sorted by node (the fold adds a node's values in a register and flushes on a node change)
-  for (size_t t = 0; t < h.thdr.size(); ++t) {
-    const uint4 hd = h.thdr[t];
-    for (uint32_t i = 0; i < (uint32_t)kFoldThreads; ++i) {
-      uint32_t prev = 0;
-      bool padded = false;
-      for (uint32_t q = 0; q < hd.y; ++q) {
-        const uint32_t e = one.lent[hd.x + (size_t)q * kFoldThreads + i];
-        if (e == kEntPad) {
-          padded = true;
-          continue;
-        }
-        if (padded || (e >> 15) < prev) return 16;  // padding only at the end, nodes non-decreasing
-        prev = e >> 15;
-      }
-    }
-  }
   for (uint32_t c = 0; c < Gc; ++c) {
     const uint32_t r = c / h.GC, cc = c % h.GC, c0 = h.cell_off[c], c1 = h.cell_off[c + 1];
     if (c0 > c1 || c0 % kBStage || c1 % kBStage) return 5;
@@ -261,8 +426,8 @@ inline int check_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t
         hl[pos - c0] = h.PT + ((w >> 15) & 0x7fffu);
       }
     }
-    one.thdr.assign(h.thdr.begin() + (size_t)c * h.ntile, h.thdr.begin() + (size_t)(c + 1) * h.ntile);
-    const int rc = check_tiles(c1 - c0, h.PT + h.PH, tl.data(), hl.data(), 1, one);
+    const int rc = check_cell_lists(c1 - c0, h.PT + h.PH, tl.data(), hl.data(), h.T, h.ntile, h.thdr.data() + (size_t)c * h.ntile,
+                                    h.lent, h.piece);
     if (rc) return 100 + rc;
   }
   for (size_t j = 0; j < m; ++j)

@@ -182,6 +182,7 @@ struct tpl_op {
   bool blocked_ok = false;     // blocked streaming kernels (tpl_blocks.cuh): 2-D node-block partition, cell-order vectors
   tpl::BlockOp blk{};
   size_t smem_blk1 = 0, smem_blk2 = 0, smem_blk2v = 0;
+  uint32_t blk_max_cell = 0;   // arcs of the largest cell
   double* bbuf[3] = {nullptr, nullptr, nullptr};  // the three rotating vectors in cell order: [Mpad arcs | p nodes]
   double* h_pin = nullptr;  // pinned mirror of coef_d
   double* V_int = nullptr;
@@ -764,7 +765,8 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       tpl::BlockOp& bo = op->blk;
       bo = tpl::BlockOp{};
       bo.GR = hb.GR; bo.GC = hb.GC; bo.PT = hb.PT; bo.PH = hb.PH; bo.Mpad = hb.Mpad; bo.m = (uint32_t)m;
-      bo.ring1 = hb.ring1; bo.ring2 = hb.ring2; bo.ring2v = hb.ring2v;
+      bo.ring1 = hb.ring1; bo.ring2 = hb.ring2; bo.ring2v = hb.ring2v; bo.lblk = hb.lblk; bo.nl = hb.nl;
+      if (const char* e = std::getenv("TPL_BLOCK_DBG")) bo.dbg = (uint32_t)std::atoi(e);  // timing experiments (tpl_blocks.cuh)
       bo.tl.T = hb.T;
       bo.tl.ntile = hb.ntile;
       rc = dev_upload(op, &bo.cell_off, hb.cell_off);
@@ -780,10 +782,11 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       for (auto& bb : op->bbuf)
         if (!rc) rc = dev_alloc(op, &bb, (size_t)hb.Mpad + p);
       const uint32_t PL = hb.PT + hb.PH;
-      op->smem_blk1 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring1, false, false);
-      op->smem_blk2 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2, true, false);
-      op->smem_blk2v = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2v, true, true);
+      op->smem_blk1 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring1, hb.lblk, hb.nl, false, false);
+      op->smem_blk2 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2, hb.lblk, hb.nl, true, false);
+      op->smem_blk2v = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2v, hb.lblk, hb.nl, true, true);
       op->blocked_ok = !rc;
+      for (size_t q = 0; q + 1 < hb.cell_off.size(); ++q) op->blk_max_cell = std::max(op->blk_max_cell, hb.cell_off[q + 1] - hb.cell_off[q]);
       if (!rc) rc = setup_local_fabric(op, true);
     }
   }
@@ -971,7 +974,8 @@ int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   for (uint32_t e : hb.gidx) hsh = (hsh ^ e) * 1099511628211ull;
   stats[13] = hsh;
   stats[14] = (uint64_t)tpl::check_blocks(m, p, tail, head, d, d_len, hb);
-  stats[15] = tpl::block_smem_bytes(hb.PT + hb.PH, hb.T, (int)hb.ring2, true, false);
+  stats[15] = tpl::block_smem_bytes(hb.PT + hb.PH, hb.T, (int)hb.ring2, hb.lblk, hb.nl, true, false);
+  stats[8] |= (uint64_t)hb.nl << 24;
   return TPL_OK;
 }
 
@@ -1079,8 +1083,14 @@ int launch_cells(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
   op->launches += 1;
   return TPL_OK;
 }
-// mode 0: blocked streaming kernels before the tiled ones (mode 5 forces them, mode 2 forces the tiled ones)
-bool use_blocked(const tpl_op* op) { return op->format == 2 && op->blocked_ok && (op->mode == 0 || op->mode == 5); }
+// mode 0: the blocked streaming kernels from ~1.5M arcs on one GPU (cells of >= 10k arcs; measured: 0.61 vs 0.56 of the HBM
+// roofline at 2M arcs, 0.92 vs 0.74 at 20M, but 0.40 vs 0.48 at 1M, where a sweep is only a few tiles long), the tiled ones
+// below; mode 5 forces the blocked kernels, mode 2 the tiled ones.  A sharded handle runs the family that owns its exchange block.
+bool use_blocked(const tpl_op* op) {
+  if (op->format != 2 || !op->blocked_ok) return false;
+  if (op->mode == 5 || (op->comm && op->mode == 0)) return true;
+  return op->mode == 0 && (op->blk_max_cell >= 10240 || !op->tiled_ok);
+}
 bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op->mode == 0 || op->mode == 2); }
 
 }  // namespace
