@@ -92,3 +92,16 @@ def test_layout_degenerate_inputs():
     assert st["fits"] == 1 and st["code"] == 0
     st = plan(100_000, 300_000, rng.integers(0, 300_000, 100_000), rng.integers(0, 300_000, 100_000), smem=60_000)
     assert st["fits"] == 0  # two node blocks + tile buffers + ring do not fit: the caller keeps the other shapes
+
+
+def test_layout_of_a_shard_ignores_nodes_without_local_arcs():
+    """A rank of a sharded operator holds a contiguous slice of the arcs but all p nodes: the tails of the other ranks' arcs (and
+    sinks / sources) have no arcs on that side and must not take shared memory -- blocks are cut over the ACTIVE nodes only."""
+    inst = datagen.gen_kkt(1_600_000, 3, 4, "wc")
+    lo, hi = inst.m // 4, inst.m // 2  # rank 1 of 4
+    st = plan(hi - lo, inst.p, inst.tail[lo:hi], inst.head[lo:hi], inst.d[lo:hi])
+    assert st["fits"] == 1 and st["code"] == 0
+    active_tails = len(np.unique(inst.tail[lo:hi]))
+    assert active_tails < 0.4 * inst.p
+    assert st["PT"] <= active_tails / 12 + 8          # not p / 12 + (nodes without out-arcs)
+    assert st["PH"] <= inst.p / 12 + 8

@@ -45,8 +45,13 @@ struct BlockOp {
   uint32_t m;        // arcs in natural order (node part of a natural-order vector starts here)
   uint32_t dbg;      // timing experiments only (results are wrong): 1 = fold warps skip their work, 2 = compute warps skip theirs
   const uint32_t* cell_off;  // [G + 1] first cell-order position of every cell (multiples of kBStage)
-  const uint32_t* tbs;       // [GR + 1] first node of every tail block
-  const uint32_t* hbs;       // [GC + 1] first node of every head block
+  // A block is a run of the ACTIVE nodes of its side (nodes with at least one out-arc / in-arc among this handle's arcs, in
+  // ascending order): nodes without arcs on a side -- sinks, sources, and on a sharded handle the tails of other ranks'
+  // arcs -- take no shared memory and no partial sums.
+  const uint32_t* tbs;       // [GR + 1] first position in tbn of every tail block
+  const uint32_t* hbs;       // [GC + 1] first position in hbn of every head block
+  const uint32_t* tbn;       // [active tails] node ids, ascending
+  const uint32_t* hbn;       // [active heads] node ids, ascending
   const double* d;           // [Mpad] quadratic costs in cell order (0 in padding and beyond the loader's short D)
   const uint32_t* th;        // [Mpad] tail_local | head_local << 15 | kBTailFirst | kBLoop
   const uint32_t* gidx;      // [Mpad] natural arc index of a cell-order position (kBPad in padding)
@@ -181,8 +186,8 @@ __device__ __forceinline__ double arc_row_b(double dj, double xj, uint32_t th, d
 struct BlockCtx {
   uint32_t r, cc;     // this CTA's tail / head block
   uint32_t c0, c1;    // its cell-order range (c1 - c0 is a multiple of kBStage)
-  uint32_t t0, nt;    // first node and size of its tail block
-  uint32_t h0, nh;    // first node and size of its head block
+  uint32_t t0, nt;    // first position (in tbn) and size of its tail block
+  uint32_t h0, nh;    // first position (in hbn) and size of its head block
   uint32_t ulo, uhi;  // node rows it owns
   uint32_t nst;       // stages of the cell
   uint32_t ntiles;    // tiles of the cell
@@ -206,8 +211,8 @@ __device__ __forceinline__ BlockCtx block_ctx(const BlockOp& bo, uint32_t p) {
 
 // node values of the CTA's two blocks -> s.node (local ids), scaled by `sc` (one rounding, the reference's in-place scaling)
 __device__ __forceinline__ void stage_block_nodes(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, const double* Xnode, double sc) {
-  for (uint32_t i = threadIdx.x; i < c.nt; i += kBlock) sm_st(s.node, i, __dmul_rn(__ldcg(Xnode + c.t0 + i), sc));
-  for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) sm_st(s.node, bo.PT + i, __dmul_rn(__ldcg(Xnode + c.h0 + i), sc));
+  for (uint32_t i = threadIdx.x; i < c.nt; i += kBlock) sm_st(s.node, i, __dmul_rn(__ldcg(Xnode + __ldg(bo.tbn + c.t0 + i)), sc));
+  for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) sm_st(s.node, bo.PT + i, __dmul_rn(__ldcg(Xnode + __ldg(bo.hbn + c.h0 + i)), sc));
 }
 __device__ __forceinline__ void zero_block_acc(const BlockOp& bo, const BlockSmem& s) {
   for (uint32_t i = threadIdx.x; i < bo.PT + bo.PH + kBAccPad; i += kBlock) sm_st(s.acc, i, 0.0);
@@ -215,17 +220,18 @@ __device__ __forceinline__ void zero_block_acc(const BlockOp& bo, const BlockSme
 
 // This CTA's partial sums (s.acc) -> the owners' buffers, parity `par`.  Destination-indexed: node u of rank rk keeps
 // world * (GC + GR) consecutive words; rank s, cell (r, cc) writes the tail side of its nodes to word s * (GC + GR) + cc and
-// the head side to word s * (GC + GR) + GC + r.  Every word is written exactly once per step (a cell writes all nodes of
-// its two blocks, zeros included), so nothing has to be cleared.  Caller synchronised before.
+// the head side to word s * (GC + GR) + GC + r.  Every word of an active node is written exactly once per step (a cell writes
+// all nodes of its two blocks, zeros included); the words of a node that is not active on a side are never written and keep
+// the zero they were allocated with.  Nothing has to be cleared.  Caller synchronised before.
 __device__ __forceinline__ void publish_block_partials(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t par) {
   const Fabric& f = bo.tl.fab;
   const uint32_t per = bo.GC + bo.GR, SL = f.world * per;
   for (uint32_t i = threadIdx.x; i < c.nt; i += kBlock) {
-    const uint32_t u = c.t0 + i, rk = u / f.Bp;
+    const uint32_t u = __ldg(bo.tbn + c.t0 + i), rk = u / f.Bp;
     __stcg(f.partials[rk] + ((size_t)par * f.Bp + (u - rk * f.Bp)) * SL + f.rank * per + c.cc, sm_ld(s.acc, i));
   }
   for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) {
-    const uint32_t u = c.h0 + i, rk = u / f.Bp;
+    const uint32_t u = __ldg(bo.hbn + c.h0 + i), rk = u / f.Bp;
     __stcg(f.partials[rk] + ((size_t)par * f.Bp + (u - rk * f.Bp)) * SL + f.rank * per + bo.GC + c.r, sm_ld(s.acc, bo.PT + i));
   }
 }

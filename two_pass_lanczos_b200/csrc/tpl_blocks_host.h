@@ -26,7 +26,7 @@ struct HostBlocks {
   bool ok = false;
   uint32_t GR = 0, GC = 0, PT = 0, PH = 0, Mpad = 0, T = 0, ntile = 0;
   uint32_t ring1 = 0, ring2 = 0, ring2v = 0, lblk = 0, nl = 2;
-  std::vector<uint32_t> cell_off, tbs, hbs, th, gidx;
+  std::vector<uint32_t> cell_off, tbs, hbs, tbn, hbn, th, gidx;
   std::vector<double> d;
   std::vector<uint4> thdr;
   std::vector<uint32_t> lent, piece;
@@ -163,21 +163,36 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
     ++outdeg[tail[j]];
     ++indeg[head[j]];
   }
-  h.tbs = weight_blocks(outdeg, h.GR);
-  h.hbs = weight_blocks(indeg, h.GC);
+  // blocks over the ACTIVE nodes of each side only (ascending node id): tbn / hbn list them, tbs / hbs cut the lists
+  std::vector<uint64_t> wt_t, wt_h;
+  std::vector<uint32_t> tpos(p, 0), hpos(p, 0);  // position of a node in tbn / hbn
+  for (size_t u = 0; u < p; ++u) {
+    if (outdeg[u]) {
+      tpos[u] = (uint32_t)h.tbn.size();
+      h.tbn.push_back((uint32_t)u);
+      wt_t.push_back(outdeg[u]);
+    }
+    if (indeg[u]) {
+      hpos[u] = (uint32_t)h.hbn.size();
+      h.hbn.push_back((uint32_t)u);
+      wt_h.push_back(indeg[u]);
+    }
+  }
+  h.tbs = weight_blocks(wt_t, h.GR);
+  h.hbs = weight_blocks(wt_h, h.GC);
   uint32_t PT = 0, PH = 0;
   for (uint32_t a = 0; a < h.GR; ++a) PT = std::max(PT, h.tbs[a + 1] - h.tbs[a]);
   for (uint32_t b = 0; b < h.GC; ++b) PH = std::max(PH, h.hbs[b + 1] - h.hbs[b]);
-  PT = (PT + 1u) & ~1u;  // even: 16-byte aligned shared-memory arrays
-  PH = (PH + 1u) & ~1u;
+  PT = std::max(2u, (PT + 1u) & ~1u);  // even: 16-byte aligned shared-memory arrays
+  PH = std::max(2u, (PH + 1u) & ~1u);
   if (PT > 0x8000u || PH > 0x8000u || PT + PH + kBAccPad > kBMaxLocalNodes) return;  // 15-bit local ids, 14-bit list nodes
   h.PT = PT;
   h.PH = PH;
-  std::vector<uint32_t> node_tb(p), node_hb(p);
+  std::vector<uint32_t> node_tb(p, 0), node_hb(p, 0);
   for (uint32_t a = 0; a < h.GR; ++a)
-    for (uint32_t u = h.tbs[a]; u < h.tbs[a + 1]; ++u) node_tb[u] = a;
+    for (uint32_t q = h.tbs[a]; q < h.tbs[a + 1]; ++q) node_tb[h.tbn[q]] = a;
   for (uint32_t b = 0; b < h.GC; ++b)
-    for (uint32_t u = h.hbs[b]; u < h.hbs[b + 1]; ++u) node_hb[u] = b;
+    for (uint32_t q = h.hbs[b]; q < h.hbs[b + 1]; ++q) node_hb[h.hbn[q]] = b;
 
   // arcs by tail node, then by arc index (identity for a tail-grouped arc list) ...
   std::vector<uint32_t> by_tail(m);
@@ -211,7 +226,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
       const uint32_t t = tail[j], hd = head[j];
       h.gidx[pos] = j;
       h.d[pos] = j < d_len ? d[j] : 0.0;
-      h.th[pos] = (t - h.tbs[node_tb[t]]) | ((hd - h.hbs[node_hb[hd]]) << 15) | (t < hd ? kBTailFirst : 0u) | (t == hd ? kBLoop : 0u);
+      h.th[pos] = (tpos[t] - h.tbs[node_tb[t]]) | ((hpos[hd] - h.hbs[node_hb[hd]]) << 15) | (t < hd ? kBTailFirst : 0u) | (t == hd ? kBLoop : 0u);
     }
   }
   std::vector<uint32_t>().swap(by_tail);
@@ -390,7 +405,11 @@ inline int check_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t
                         const HostBlocks& h) {
   const uint32_t Gc = h.GR * h.GC;
   if (!h.ok || h.cell_off.size() != Gc + 1 || h.tbs.size() != h.GR + 1 || h.hbs.size() != h.GC + 1) return 1;
-  if (h.tbs[0] != 0 || h.tbs[h.GR] != p || h.hbs[0] != 0 || h.hbs[h.GC] != p) return 2;
+  if (h.tbs[0] != 0 || h.tbs[h.GR] != h.tbn.size() || h.hbs[0] != 0 || h.hbs[h.GC] != h.hbn.size()) return 2;
+  for (size_t q = 0; q < h.tbn.size(); ++q)
+    if (h.tbn[q] >= p || (q && h.tbn[q] <= h.tbn[q - 1])) return 2;
+  for (size_t q = 0; q < h.hbn.size(); ++q)
+    if (h.hbn[q] >= p || (q && h.hbn[q] <= h.hbn[q - 1])) return 2;
   if (h.th.size() != h.Mpad || h.gidx.size() != h.Mpad || h.d.size() != h.Mpad || h.cell_off[Gc] != h.Mpad) return 3;
   if (h.T % 1024 != 0 || h.T == 0 || (h.PT & 1u) || (h.PH & 1u)) return 4;
   std::vector<uint8_t> seen(m, 0);
@@ -414,8 +433,9 @@ inline int check_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t
       if (g >= m || seen[g]) return 9;
       seen[g] = 1;
       const uint32_t t = tail[g], hd = head[g];
-      if (t < h.tbs[r] || t >= h.tbs[r + 1] || hd < h.hbs[cc] || hd >= h.hbs[cc + 1]) return 10;
-      if ((w & 0x7fffu) != t - h.tbs[r] || ((w >> 15) & 0x7fffu) != hd - h.hbs[cc]) return 11;
+      const uint32_t lt = w & 0x7fffu, lh = (w >> 15) & 0x7fffu;
+      if (lt >= h.tbs[r + 1] - h.tbs[r] || lh >= h.hbs[cc + 1] - h.hbs[cc]) return 10;
+      if (h.tbn[h.tbs[r] + lt] != t || h.hbn[h.hbs[cc] + lh] != hd) return 11;
       if (((w & kBLoop) != 0) != (t == hd) || ((w & kBTailFirst) != 0) != (t < hd)) return 12;
       if (h.d[pos] != (g < d_len ? d[g] : 0.0)) return 13;
       const uint64_t key = ((uint64_t)t << 32) | g;

@@ -772,6 +772,8 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       rc = dev_upload(op, &bo.cell_off, hb.cell_off);
       if (!rc) rc = dev_upload(op, &bo.tbs, hb.tbs);
       if (!rc) rc = dev_upload(op, &bo.hbs, hb.hbs);
+      if (!rc) rc = dev_upload(op, &bo.tbn, hb.tbn);
+      if (!rc) rc = dev_upload(op, &bo.hbn, hb.hbn);
       if (!rc) rc = dev_upload(op, &bo.d, hb.d);
       if (!rc) rc = dev_upload(op, &bo.th, hb.th);
       if (!rc) rc = dev_upload(op, &bo.gidx, hb.gidx);
