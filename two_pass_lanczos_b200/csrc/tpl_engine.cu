@@ -19,6 +19,7 @@
 #include "tpl_blocks.cuh"
 #include "tpl_blocks_host.h"
 #include "tpl_cells_host.h"
+#include "tpl_csr.cuh"
 #include "tpl_dense.cuh"
 #include "tpl_kernels.cuh"
 #include "tpl_sharded.cuh"
@@ -149,7 +150,7 @@ struct tpl_op {
   uint32_t n = 0;
   int G = 0;  // CTAs of the persistent grid (= SM count)
   tpl::IncidenceOp inc{};
-  tpl::CsrOp csr{};
+  tpl::SellOp sell{};  // generic sparse operator: SELL-32 slices + long-row segments (tpl_csr.cuh)
   tpl::DenseOp dense{};
   std::vector<std::pair<void*, size_t>> allocs;
   size_t device_bytes = 0;
@@ -494,13 +495,12 @@ int finish_setup(tpl_op* op) {
     if (int rc = set_smem(tpl::apply_dense_kernel, smem)) return rc;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_dense_kernel<true>, tpl::kBlock, smem));
   } else {
-    if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, false>, smem)) return rc;
-    if (int rc = set_smem(tpl::pass1_kernel<tpl::CsrOp, true>, smem)) return rc;
-    if (int rc = set_smem(tpl::pass2_kernel<tpl::CsrOp, false>, smem)) return rc;
-    if (int rc = set_smem(tpl::pass2_kernel<tpl::CsrOp, true>, smem)) return rc;
-    if (int rc = set_smem(tpl::apply_kernel<tpl::CsrOp>, smem)) return rc;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_kernel<tpl::CsrOp, true>,
-                                                           tpl::kBlock, smem));
+    if (int rc = set_smem(tpl::pass1_csr_kernel<false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass1_csr_kernel<true>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_csr_kernel<false>, smem)) return rc;
+    if (int rc = set_smem(tpl::pass2_csr_kernel<true>, smem)) return rc;
+    if (int rc = set_smem(tpl::apply_csr_kernel, smem)) return rc;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpl::pass1_csr_kernel<true>, tpl::kBlock, smem));
   }
   if (per_sm < 1) return fail(TPL_ERR_CUDA, "CUDA error: persistent kernel does not fit on an SM (smem %zu B)", smem);
   return TPL_OK;
@@ -575,12 +575,43 @@ int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, co
     }
   }
   build_segments(h, row_ent, op->G);
-  op->csr.n = (uint32_t)n;
-  op->csr.long_thresh = long_thresh;
-  rc = dev_upload(op, &op->csr.row_ptr, row_ptr);
-  if (!rc) rc = dev_upload(op, &op->csr.col, col);
-  if (!rc) rc = dev_upload(op, &op->csr.val, v);
-  if (!rc) rc = upload_long_rows(op, h, op->csr.lr);
+  // SELL-32 slices of the short rows (tpl_csr.cuh): entry e of row r at sptr[r / 32] + 32 e + r % 32
+  {
+    const size_t nslice = (n + 31) / 32;
+    std::vector<uint32_t> sptr(nslice + 1, 0);
+    std::vector<uint8_t> rlen(n);
+    static_assert(96 < 0xff, "row lengths of short rows fit a byte");
+    for (size_t sl = 0; sl < nslice; ++sl) {
+      uint32_t width = 0;
+      for (size_t i = sl * 32; i < std::min(n, sl * 32 + 32); ++i) {
+        const uint32_t len = row_ptr[i + 1] - row_ptr[i];
+        rlen[i] = len > long_thresh ? 0xff : (uint8_t)len;
+        if (len <= long_thresh) width = std::max(width, len);
+      }
+      sptr[sl + 1] = sptr[sl] + 32 * width;
+    }
+    std::vector<uint32_t> scol(sptr[nslice]);
+    std::vector<double> sval(sptr[nslice], 0.0);
+    for (size_t sl = 0; sl < nslice; ++sl) {
+      const uint32_t width = (sptr[sl + 1] - sptr[sl]) / 32;
+      for (uint32_t ln = 0; ln < 32; ++ln) {
+        const size_t i = sl * 32 + ln;
+        const uint32_t len = i < n && rlen[i] != 0xff ? rlen[i] : 0;
+        for (uint32_t e = 0; e < width; ++e) {
+          const size_t w = (size_t)sptr[sl] + 32 * e + ln;
+          scol[w] = e < len ? col[row_ptr[i] + e] : (uint32_t)std::min(i, n - 1);
+          if (e < len) sval[w] = v[row_ptr[i] + e];
+        }
+      }
+    }
+    op->sell.n = (uint32_t)n;
+    op->sell.nslice = (uint32_t)nslice;
+    rc = dev_upload(op, &op->sell.sptr, sptr);
+    if (!rc) rc = dev_upload(op, &op->sell.scol, scol);
+    if (!rc) rc = dev_upload(op, &op->sell.sval, sval);
+    if (!rc) rc = dev_upload(op, &op->sell.rlen, rlen);
+  }
+  if (!rc) rc = upload_long_rows(op, h, op->sell.lr);
   op->matrix_bytes = 12ull * nnz + 4ull * (n + 1);
   op->smem_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
   if (!rc) rc = finish_setup(op);
@@ -794,7 +825,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   }
   // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of the stream batch, at most
   // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
-  if (!rc && p >= 1 && p < (1u << 17)) {
+  if (!rc && p >= 1 && p < (1u << 17) && !(op->blocked_ok && op->blk_max_cell >= 4 * 10240)) {
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
     const long budget = (long)max_optin - 2048 - (long)(2 * p + 2 * tpl::kMaxPieces) * 8;
@@ -1147,8 +1178,7 @@ int launch_pass1(tpl_op* op, const tpl::Pass1Args& a, bool whole_pass) {
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass1_kernel<tpl::IncidenceOp, false>, op->inc, a);
-  return with_v ? launch_coop(op, tpl::pass1_kernel<tpl::CsrOp, true>, op->csr, a)
-                : launch_coop(op, tpl::pass1_kernel<tpl::CsrOp, false>, op->csr, a);
+  return with_v ? launch_coop(op, tpl::pass1_csr_kernel<true>, op->sell, a) : launch_coop(op, tpl::pass1_csr_kernel<false>, op->sell, a);
 }
 int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   const bool with_v = a.V != nullptr;
@@ -1169,8 +1199,7 @@ int launch_pass2(tpl_op* op, const tpl::Pass2Args& a) {
   if (op->format == 2)
     return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, true>, op->inc, a)
                   : launch_coop(op, tpl::pass2_kernel<tpl::IncidenceOp, false>, op->inc, a);
-  return with_v ? launch_coop(op, tpl::pass2_kernel<tpl::CsrOp, true>, op->csr, a)
-                : launch_coop(op, tpl::pass2_kernel<tpl::CsrOp, false>, op->csr, a);
+  return with_v ? launch_coop(op, tpl::pass2_csr_kernel<true>, op->sell, a) : launch_coop(op, tpl::pass2_csr_kernel<false>, op->sell, a);
 }
 
 // Brings b to the device (no copy when it already lives there).
@@ -1398,16 +1427,17 @@ int run_pass_two(tpl_op* op, const double* b_dev, const double* alphas, const do
   } else if (int rc = launch_pass2(op, a)) {
     return rc;
   }
+  CUDA_TRY(cudaEventRecord(op->ev[3], op->stream));
+  op->timed[1] = true;
   if (op->fab_connected && op->mode == 0) {
-    // the next fused pass continues from the epoch this one ended with (the kernel stored it in the state block)
+    // the next fused pass continues from the epoch this one ended with (the kernel stored it in the state block); the
+    // read-back is bookkeeping between passes, outside the pass-2 event pair
     CUDA_TRY(cudaMemcpyAsync(op->h_pin, op->coef_d, sizeof(tpl::State), cudaMemcpyDeviceToHost, op->stream));
     CUDA_TRY(cudaStreamSynchronize(op->stream));
     tpl::State st;
     std::memcpy(&st, op->h_pin, sizeof st);
     op->fab_epoch = st.epoch;
   }
-  CUDA_TRY(cudaEventRecord(op->ev[3], op->stream));
-  op->timed[1] = true;
   return TPL_OK;
 }
 
@@ -1487,7 +1517,7 @@ int tpl_op_apply(tpl_op* op, const double* x, double* y) {
   else if (op->format == 2)
     tpl::apply_kernel<tpl::IncidenceOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->inc, x_dev, y_dev);
   else
-    tpl::apply_kernel<tpl::CsrOp><<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->csr, x_dev, y_dev);
+    tpl::apply_csr_kernel<<<op->G, tpl::kBlock, op->smem_bytes, op->stream>>>(op->sell, x_dev, y_dev);
   CUDA_TRY(cudaGetLastError());
   op->launches += 1;
   if (op->comm)  // node rows of the local operator are partial sums over this rank's arcs
