@@ -239,6 +239,17 @@ int tpl_ftk_exp(const double* alphas, size_t na, const double* betas, size_t nb,
 int tpl_ftk_square(const double* alphas, size_t na, const double* betas, size_t nb, double* y,
                    size_t* y_len, void* user);
 
+/* k-sweeps (the reference's benches re-solve for every k, src/bin/tradeoff.rs:262-290, src/bin/stability.rs:259-312):
+ * x_q = f(A) b with ks[q] Lanczos steps for q < nk from ONE basis generation (tpl_lanczos_sweep: one-pass, the n x max(ks)
+ * basis stays in HBM and every x_q comes out of one streaming pass over it, 16 at a time) or ONE pass 1 (tpl_lanczos_two_pass_sweep:
+ * O(n) memory, one pass 2 per k).  X: n x nk column-major, leading dimension ldx >= n, host or device.  f_tk is called once per
+ * k with the leading ks[q] coefficients.  Every x_q is bit-identical to the corresponding tpl_lanczos / tpl_lanczos_two_pass
+ * solve (step j of the recurrence does not depend on k).  ks[q] == 0 -> TPL_ERR_PANIC. */
+int tpl_lanczos_sweep(tpl_op* op, const double* b, const size_t* ks, size_t nk, tpl_ftk_solver f_tk, void* user, double* X,
+                      size_t ldx);
+int tpl_lanczos_two_pass_sweep(tpl_op* op, const double* b, const size_t* ks, size_t nk, tpl_ftk_solver f_tk, void* user,
+                               double* X, size_t ldx);
+
 /* SURVEY 8f N1 (no reference counterpart; the reference's benches re-solve for every k, src/bin/tradeoff.rs:262-290):
  * residual norms ||b - A x_j||, j = 1..na, of the iterates x_j = ||b|| V_j T_j^{-1} e_1 from the coefficients of ONE
  * pass 1 (progressive Givens QR of T, O(na), host).  betas[j-1] = beta_j must be given for every j that is wanted

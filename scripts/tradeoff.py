@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--k-end", type=int, default=1000)
     ap.add_argument("--k-step", type=int, default=50)
     ap.add_argument("--output", default="")
+    ap.add_argument("--sweep", action="store_true",
+                    help="also time the batched sweeps (lanczos_sweep / lanczos_two_pass_sweep: one basis generation / one pass 1 for all k)")
     args = ap.parse_args()
     inst = datagen.gen_kkt(args.arcs, args.rho, 1, "aa")
     rows = ["variant,k,time_s,rss_kb,kernel_shape,pass1_ms,pass2_or_gemv_ms,rel_diff_vs_two_pass"]
@@ -48,6 +50,22 @@ def main():
             rows.append(f"{variant},{k},{dt:.9f},{op.device_bytes() // 1024},{op.kernel_shape()},{tm['pass_one_ms']:.3f},"
                         f"{second:.3f},{diff:.2e}")
             print(rows[-1], flush=True)
+            op.close()
+    if args.sweep:
+        ks = list(range(args.k_start, args.k_end + 1, args.k_step))
+        per_k = {v: sum(float(r.split(",")[2]) for r in rows[1:] if r.startswith(v + ",")) for v in ("two-pass", "standard")}
+        for variant, fn in (("two-pass-sweep", tpl.lanczos_two_pass_sweep), ("standard-sweep", tpl.lanczos_sweep)):
+            op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d)
+            b = op.apply(np.full(inst.n, 1.0 / np.sqrt(inst.n)))
+            fn(op, b, ks, "inv")
+            t = time.perf_counter()
+            X = fn(op, b, ks, "inv")
+            dt = time.perf_counter() - t
+            ref = per_k["two-pass" if variant.startswith("two") else "standard"]
+            rows.append(f"{variant},{ks[0]}..{ks[-1]},{dt:.9f},{op.device_bytes() // 1024},{op.kernel_shape()},,,"
+                        f"{len(ks)} solutions in one call; the per-k solves above take {ref:.6f} s in total ({ref / dt:.1f}x)")
+            print(rows[-1], flush=True)
+            del X
             op.close()
     if args.output:
         with open(args.output, "w") as f:

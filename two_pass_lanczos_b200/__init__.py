@@ -10,7 +10,7 @@ All compute goes through the C ABI of libtplanczos.so (include/tplanczos.h); the
 from . import algorithms, data_loader, datagen, error, operators, sharding, solvers  # noqa: F401
 from .error import CudaError, DataLoaderError, LanczosError  # noqa: F401
 from .operators import LinOp  # noqa: F401
-from .solvers import lanczos, lanczos_two_pass  # noqa: F401
+from .solvers import lanczos, lanczos_sweep, lanczos_two_pass, lanczos_two_pass_sweep  # noqa: F401
 
 __all__ = ["lanczos", "lanczos_two_pass", "algorithms", "solvers", "data_loader", "datagen", "operators", "LinOp",
            "LanczosError", "DataLoaderError", "CudaError"]

@@ -67,6 +67,8 @@ SIGNATURES = {
                                STEP_CB, C.c_void_p]),
     "tpl_lanczos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, FTK_FN, C.c_void_p, C.c_void_p]),
     "tpl_lanczos_two_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, FTK_FN, C.c_void_p, C.c_void_p]),
+    "tpl_lanczos_sweep": (C.c_int, [C.c_void_p, C.c_void_p, c_szp, C.c_size_t, FTK_FN, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "tpl_lanczos_two_pass_sweep": (C.c_int, [C.c_void_p, C.c_void_p, c_szp, C.c_size_t, FTK_FN, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tpl_ftk_inv": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, c_dp, c_szp, C.c_void_p]),
     "tpl_ftk_exp": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, c_dp, c_szp, C.c_void_p]),
     "tpl_ftk_inv_residuals": (C.c_int, [c_dp, C.c_size_t, c_dp, C.c_size_t, C.c_double, c_dp]),

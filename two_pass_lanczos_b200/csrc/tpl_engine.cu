@@ -188,6 +188,10 @@ struct tpl_op {
   double* h_pin = nullptr;  // pinned mirror of coef_d
   double* V_int = nullptr;
   size_t V_int_elems = 0;
+  double* sweep_d = nullptr;    // k-sweep: staging block for up to kSweepChunk solutions when the caller's X is on the host
+  size_t sweep_elems = 0;
+  double* sweep_y_d = nullptr;  // k-sweep: coefficient matrix Y (kmax x chunk)
+  size_t sweep_y_elems = 0;
   cudaEvent_t ev[6] = {};
   bool timed[3] = {false, false, false};
   uint64_t launches = 0;
@@ -1459,6 +1463,29 @@ int gemv_vy(tpl_op* op, const double* V_dev, size_t ldv, size_t steps, const dou
   return TPL_OK;
 }
 
+int ensure_sweep_buffer(tpl_op* op, size_t elems) {
+  if (elems <= op->sweep_elems) return TPL_OK;
+  if (op->sweep_d) {
+    if (int rc = dev_free(op, op->sweep_d)) return rc;
+    op->sweep_d = nullptr;
+    op->sweep_elems = 0;
+  }
+  if (int rc = dev_alloc(op, &op->sweep_d, elems)) return rc;
+  op->sweep_elems = elems;
+  return TPL_OK;
+}
+int ensure_sweep_coef(tpl_op* op, size_t elems) {
+  if (elems <= op->sweep_y_elems) return TPL_OK;
+  if (op->sweep_y_d) {
+    if (int rc = dev_free(op, op->sweep_y_d)) return rc;
+    op->sweep_y_d = nullptr;
+    op->sweep_y_elems = 0;
+  }
+  if (int rc = dev_alloc(op, &op->sweep_y_d, elems)) return rc;
+  op->sweep_y_elems = elems;
+  return TPL_OK;
+}
+
 int ensure_internal_basis(tpl_op* op, size_t elems) {
   if (elems <= op->V_int_elems) return TPL_OK;
   if (op->V_int) {
@@ -1641,6 +1668,120 @@ int tpl_lanczos_two_pass(tpl_op* op, const double* b, size_t k, tpl_ftk_solver f
                             nullptr, 0))
     return rc;
   return finish_x(op, x_dev, x);
+}
+
+// the k-sweep of the reference's benches (src/bin/tradeoff.rs:262-290 re-solves for every k) from ONE basis
+// generation / ONE pass 1 to max(ks).  Step j of the recurrence does not depend on k, so alphas[:k], betas[:k-1] of the long
+// run are those of a k-step run, and every x_q below is bit-identical to the corresponding single solve.
+static int sweep_prepare(tpl_op* op, const size_t* ks, size_t nk, size_t& kmax) {
+  if (!ks || nk == 0) return fail(TPL_ERR_PANIC, "null argument");
+  kmax = 0;
+  for (size_t q = 0; q < nk; ++q) {
+    if (ks[q] == 0) return fail(TPL_ERR_PANIC, "capacity overflow (k == 0; the reference panics in Vec::with_capacity(k - 1))");
+    kmax = std::max(kmax, ks[q]);
+  }
+  (void)op;
+  return TPL_OK;
+}
+// y'_q = f(T_{steps_q}) e1 with steps_q = min(ks[q], steps_taken), through the caller's closure
+static int sweep_ftk(tpl_ftk_solver f_tk, void* user, const Decomp& d, size_t k, std::vector<double>& y, size_t& steps_q) {
+  Decomp dq;
+  steps_q = std::min(k, d.steps);
+  dq.steps = steps_q;
+  dq.b_norm = d.b_norm;
+  dq.alphas.assign(d.alphas.begin(), d.alphas.begin() + steps_q);
+  dq.betas.assign(d.betas.begin(), d.betas.begin() + (steps_q ? steps_q - 1 : 0));
+  return call_ftk(f_tk, user, dq, y);
+}
+
+int tpl_lanczos_sweep(tpl_op* op, const double* b, const size_t* ks, size_t nk, tpl_ftk_solver f_tk, void* user, double* X,
+                      size_t ldx) {
+  tpl::clear_error();
+  if (!op || !b || !X || !f_tk) return fail(TPL_ERR_PANIC, "null argument");
+  if (ldx < op->n) return tpl::fail_parameter_mismatch("ldx", op->n, ldx);
+  size_t kmax = 0;
+  if (int rc = sweep_prepare(op, ks, nk, kmax)) return rc;
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  if (int rc = ensure_internal_basis(op, (size_t)op->n * kmax)) return rc;
+  Decomp d;
+  if (int rc = run_pass_one(op, b_dev, kmax, op->V_int, op->n, nullptr, nullptr, d)) return rc;
+  const bool x_dev_out = is_device_ptr(X);
+  double* Xd = X;
+  size_t ldd = ldx;
+  if (!x_dev_out) {
+    if (int rc = ensure_sweep_buffer(op, (size_t)op->n * std::min<size_t>(nk, tpl::kSweepChunk))) return rc;
+    Xd = op->sweep_d;
+    ldd = op->n;
+  }
+  std::vector<double> y, Y;
+  CUDA_TRY(cudaEventRecord(op->ev[4], op->stream));
+  for (size_t q0 = 0; q0 < nk; q0 += tpl::kSweepChunk) {
+    const size_t nq = std::min<size_t>(tpl::kSweepChunk, nk - q0);
+    size_t kc = 0;
+    Y.assign((std::max<size_t>(d.steps, 1)) * nq, 0.0);
+    for (size_t q = 0; q < nq; ++q) {
+      size_t steps_q = 0;
+      if (d.steps) {
+        if (int rc = sweep_ftk(f_tk, user, d, ks[q0 + q], y, steps_q)) return rc;
+        for (size_t j = 0; j < steps_q; ++j) Y[j * nq + q] = y[j];
+      }
+      kc = std::max(kc, steps_q);
+    }
+    double* out = x_dev_out ? X + q0 * ldx : Xd;
+    if (kc == 0) {  // solvers.rs:65-67: no step was taken
+      CUDA_TRY(cudaMemset2DAsync(out, ldd * sizeof(double), 0, (size_t)op->n * sizeof(double), nq, op->stream));
+    } else {
+      if (int rc = ensure_sweep_coef(op, Y.size())) return rc;
+      CUDA_TRY(cudaMemcpyAsync(op->sweep_y_d, Y.data(), Y.size() * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+      const int block = 256;
+      const int grid = (int)std::min<size_t>((op->n + block - 1) / block, (size_t)op->G * 16);
+      tpl::gemv_vy_sweep_kernel<<<grid, block, 0, op->stream>>>(op->V_int, op->n, op->n, (int)kc, op->sweep_y_d, (int)nq, d.b_norm,
+                                                                out, ldd);
+      CUDA_TRY(cudaGetLastError());
+      op->launches += 1;
+      CUDA_TRY(cudaStreamSynchronize(op->stream));  // Y (pageable host memory) is rewritten by the next chunk
+    }
+    if (!x_dev_out)
+      CUDA_TRY(cudaMemcpy2DAsync(X + q0 * ldx, ldx * sizeof(double), Xd, ldd * sizeof(double), (size_t)op->n * sizeof(double), nq,
+                                 cudaMemcpyDeviceToHost, op->stream));
+  }
+  CUDA_TRY(cudaEventRecord(op->ev[5], op->stream));
+  op->timed[2] = true;
+  CUDA_TRY(cudaStreamSynchronize(op->stream));
+  return TPL_OK;
+}
+
+int tpl_lanczos_two_pass_sweep(tpl_op* op, const double* b, const size_t* ks, size_t nk, tpl_ftk_solver f_tk, void* user, double* X,
+                               size_t ldx) {
+  tpl::clear_error();
+  if (!op || !b || !X || !f_tk) return fail(TPL_ERR_PANIC, "null argument");
+  if (ldx < op->n) return tpl::fail_parameter_mismatch("ldx", op->n, ldx);
+  size_t kmax = 0;
+  if (int rc = sweep_prepare(op, ks, nk, kmax)) return rc;
+  DeviceGuard g(op->device);
+  const double* b_dev = nullptr;
+  if (int rc = stage_b(op, b, &b_dev)) return rc;
+  Decomp d;
+  if (int rc = run_pass_one(op, b_dev, kmax, nullptr, 0, nullptr, nullptr, d)) return rc;
+  const bool x_dev_out = is_device_ptr(X);
+  std::vector<double> y;
+  for (size_t q = 0; q < nk; ++q) {
+    double* xq = X + q * ldx;
+    double* x_dev = x_dev_out ? xq : op->x_d;
+    if (d.steps == 0) {  // solvers.rs:150-152
+      CUDA_TRY(cudaMemsetAsync(x_dev, 0, sizeof(double) * op->n, op->stream));
+    } else {
+      size_t steps_q = 0;
+      if (int rc = sweep_ftk(f_tk, user, d, ks[q], y, steps_q)) return rc;
+      for (double& yi : y) yi = yi * d.b_norm;  // solvers.rs:169
+      if (int rc = run_pass_two(op, b_dev, d.alphas.data(), d.betas.data(), steps_q, d.b_norm, y.data(), y.size(), x_dev, nullptr, 0))
+        return rc;
+    }
+    if (int rc = finish_x(op, x_dev, xq)) return rc;
+  }
+  return TPL_OK;
 }
 
 // k chosen from the residual estimates of one pass 1

@@ -1021,4 +1021,43 @@ __global__ void __launch_bounds__(256) gemv_vy_kernel(const double* __restrict__
   }
 }
 
+// k-sweep reconstruction: x_q = b_norm * (V[:, :steps_q] y'_q) for up to kSweepChunk right-hand coefficient vectors in ONE
+// streaming pass over the basis (the reference's sweep re-solves for every k, src/bin/tradeoff.rs:262-290).  Y is kmax x nq
+// row-major, zero beyond steps_q: adding 0 * v leaves an accumulator unchanged, and every x_q sees exactly the sequence of
+// roundings of gemv_vy_kernel -- bit-identical to the per-k solves.
+constexpr int kSweepChunk = 16;
+__global__ void __launch_bounds__(256) gemv_vy_sweep_kernel(const double* __restrict__ V, size_t ldv, uint32_t n, int kmax,
+                                                             const double* __restrict__ Y, int nq, double b_norm,
+                                                             double* __restrict__ X, size_t ldx) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double* col = V + i;
+    double acc[kSweepChunk];
+#pragma unroll
+    for (int q = 0; q < kSweepChunk; ++q) acc[q] = 0.0;
+    int j = 0;
+    for (; j + 4 <= kmax; j += 4) {
+      double t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldcs(col + (size_t)(j + u) * ldv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double* yrow = Y + (size_t)(j + u) * nq;  // the same words for every thread: one broadcast load each
+#pragma unroll
+        for (int q = 0; q < kSweepChunk; ++q)
+          if (q < nq) acc[q] = __dadd_rn(acc[q], __dmul_rn(t[u], __ldg(yrow + q)));
+      }
+    }
+    for (; j < kmax; ++j) {
+      const double t = __ldcs(col + (size_t)j * ldv);
+      const double* yrow = Y + (size_t)j * nq;
+#pragma unroll
+      for (int q = 0; q < kSweepChunk; ++q)
+        if (q < nq) acc[q] = __dadd_rn(acc[q], __dmul_rn(t, __ldg(yrow + q)));
+    }
+#pragma unroll
+    for (int q = 0; q < kSweepChunk; ++q)
+      if (q < nq) X[(size_t)q * ldx + i] = __dmul_rn(b_norm, acc[q]);
+  }
+}
+
 }  // namespace tpl

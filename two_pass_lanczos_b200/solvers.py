@@ -78,6 +78,40 @@ def lanczos_two_pass(operator: LinOp, b, k: int, f_tk_solver):
     return _solve("tpl_lanczos_two_pass", operator, b, k, f_tk_solver)
 
 
+def _sweep(entry: str, operator: LinOp, b, ks, f_tk_solver):
+    bp, keep, is_torch = operator._vec(b)
+    n = operator.nrows()
+    ks_arr = (C.c_size_t * len(ks))(*[int(k) for k in ks])
+    if is_torch and keep.is_cuda:
+        X = keep.new_empty((len(ks), n))          # row q = x_q (column-major n x nk for the library)
+        xptr = C.c_void_p(X.data_ptr())
+    else:
+        X = np.empty((len(ks), n))
+        xptr = C.c_void_p(X.ctypes.data)
+    errors: list = []
+    cb = _native_ftk(f_tk_solver) if isinstance(f_tk_solver, str) else _wrap_closure(f_tk_solver, errors)
+    rc = getattr(_lib.load(), entry)(operator._h, bp, ks_arr, len(ks), cb, None, xptr, n)
+    if rc == 6 and errors:
+        from .error import LanczosError
+
+        raise LanczosError(6, f"The user-provided f(T_k) solver failed: {errors[0]}")
+    _lib.check(rc)
+    return X
+
+
+def lanczos_sweep(operator: LinOp, b, ks, f_tk_solver):
+    """One-pass k-sweep: x_q = f(A) b with ks[q] steps for every q from ONE basis generation to max(ks) and one streaming pass
+    over the basis (the reference re-solves per k, src/bin/tradeoff.rs:262-290).  Returns an array whose row q is bit-identical
+    to `lanczos(operator, b, ks[q], f_tk_solver)`."""
+    return _sweep("tpl_lanczos_sweep", operator, b, ks, f_tk_solver)
+
+
+def lanczos_two_pass_sweep(operator: LinOp, b, ks, f_tk_solver):
+    """Two-pass k-sweep with O(n) memory: ONE pass 1 to max(ks), one pass 2 per k.  Row q is bit-identical to
+    `lanczos_two_pass(operator, b, ks[q], f_tk_solver)`."""
+    return _sweep("tpl_lanczos_two_pass_sweep", operator, b, ks, f_tk_solver)
+
+
 def inv_residual_estimates(alphas, betas, b_norm: float = 1.0):
     """||b - A x_j||, j = 1..len(alphas), of the iterates x_j = ||b|| V_j T_j^{-1} e_1, from the coefficients of one pass 1
     (`tpl_ftk_inv_residuals`).  `betas[j-1]` = beta_j; entries whose beta is not given come back NaN (a
