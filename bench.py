@@ -70,6 +70,17 @@ def recorded_traffic():
     return None
 
 
+def recorded_large_traffic(shape, arcs):
+    """dram bytes per Lanczos step of the streaming kernels on the large instance, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if shape == "blocked" and arcs == 50_000_000 and os.path.exists(path):
+        try:
+            return json.load(open(path)).get("blocked_50M_arcs")
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -221,7 +232,7 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def large_instance_leg(args, rank, world, local_rank, dist, dev):
+def large_instance_leg(args, rank, world, local_rank, dist, dev, shuffled=False):
     """BASELINE.json config 4 / north_star: the large synthetic instance (default 50M arcs, rho = 3, k = 500) on the same
     N GPUs, after the headline workload -- a reported extra (`large_instance` in the JSON line), not the headline value.
     One GPU: tiled streaming kernels; N > 1: arc-partitioned, the same kernels spanning all ranks."""
@@ -231,12 +242,19 @@ def large_instance_leg(args, rank, world, local_rank, dist, dev):
     from two_pass_lanczos_b200 import datagen, sharding
 
     inst = datagen.gen_kkt(args.large_arcs, args.rho, args.seed, "aa")
+    if shuffled:  # the same graph with its arcs in random order (netgen emits them grouped by tail)
+        perm = np.random.default_rng(args.seed).permutation(inst.m)
+        inst.tail, inst.head, inst.d = inst.tail[perm], inst.head[perm], inst.d[perm]
+    torch.cuda.synchronize()
+    t_build = time.perf_counter()
     if world > 1:
         ident = sharding.broadcast_unique_id(dist, rank)
         op = sharding.sharded_linop(inst.m, inst.p, inst.tail, inst.head, inst.d, rank, world, ident, device=local_rank,
                                    dist=None if os.environ.get("TPL_SHARDED_NCCL") else dist)
     else:
         op = tpl.LinOp.from_kkt(inst.m, inst.p, inst.tail, inst.head, inst.d, device=local_rank)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
     stream = torch.cuda.current_stream()
     op.set_stream(stream.cuda_stream)
     nloc = op.nrows()
@@ -269,7 +287,10 @@ def large_instance_leg(args, rank, world, local_rank, dist, dev):
     out = {"workload": f"netgen-shaped KKT {inst.m} arcs rho={args.rho} n={inst.n}, lanczos_two_pass f=inv k={args.k}",
            "n_gpus": world, "time_s": best[0] * 1e-3, "pass1_ms": best[1], "pass2_ms": best[2],
            "algorithmic_gb": (a1 + a2) / 1e9, "gbs": gbs, "frac_of_hbm_peak": gbs / (peak * world),
-           "kernel_shape": op.kernel_shape(), "residual": res,
+           "pass1_frac": a1 / (best[1] * 1e-3) / 1e9 / (peak * world), "pass2_frac": a2 / (best[2] * 1e-3) / 1e9 / (peak * world),
+           "arc_order": "random permutation" if shuffled else "grouped by tail (netgen order)",
+           "operator_build_s": round(build_s, 3),
+           "kernel_shape": op.kernel_shape(), "residual": res, "traffic": recorded_large_traffic(op.kernel_shape(), inst.m),
            "timing": "CUDA events on the launching stream, max over ranks, best of 2 solves"}
     op.close()
     return out
@@ -394,6 +415,8 @@ def run_b200(args, rank, world, local_rank):
     if args.large_arcs > 0:
         try:
             large = large_instance_leg(args, rank, world, local_rank, dist, dev)
+            if world == 1:  # the same instance with its arcs in random order: the kernels must not depend on netgen's grouping
+                large["shuffled_arcs"] = large_instance_leg(args, rank, world, local_rank, dist, dev, shuffled=True)
         except Exception as e:  # noqa: BLE001 - the extra leg must never take the headline line down
             large = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
@@ -410,7 +433,12 @@ def run_b200(args, rank, world, local_rank):
             "chunks": "pass1_resident_kernel<false> (contiguous chunks in shared memory; one persistent launch per pass)",
             "tiled": "pass1_tiled_kernel<false> (streaming, tiled node sums; one persistent launch per pass)",
             "gather": "pass1_kernel<IncidenceOp,false> (streaming, gathered node rows; one persistent launch per pass)",
+            "blocked": "pass1_blocked_kernel<false> (streaming, 2-D node-block partition, cell-order vectors, bulk-copy input ring; "
+                       "one persistent launch per pass)",
             "sharded": "shard_phase_a_kernel + shard_phase_b_kernel (2 launches + 2 NCCL all-reduces per step)",
+            "sharded-blocked": "pass1_blocked_kernel<false> spanning all ranks (destination-indexed node-sum exchange, node-value "
+                               "all-gather and alpha / beta all-reduce as peer-memory stores over NVLink inside one persistent "
+                               "launch per pass)",
             "sharded-fused": "pass1_tiled_kernel<false> spanning all ranks (node-sum reduce-scatter, node-value all-gather and "
                              "alpha / beta all-reduce as peer-memory stores over NVLink inside one persistent launch per pass)",
         }.get(shape, shape)
