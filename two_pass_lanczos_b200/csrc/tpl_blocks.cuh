@@ -34,6 +34,8 @@ constexpr int kBMaxList = 8;
 constexpr uint32_t kBLoop = 0x80000000u;     // th word: self-loop or padding (no incidence entries)
 constexpr uint32_t kBTailFirst = 0x40000000u;  // th word: global tail index < global head index (CSC accumulation order)
 constexpr uint32_t kBPad = 0xffffffffu;      // gidx of a padding slot
+constexpr uint32_t kBNoPiece = 0xffffffffu;  // unused run descriptor of a stage
+constexpr uint32_t kBPieceMin = 24;          // shortest same-tail run (inside one stage) summed by the compute warp
 
 struct BlockOp {
   uint32_t GR, GC;   // tail blocks x head blocks; the grid has GR * GC CTAs, CTA c = r * GC + cc
@@ -55,6 +57,7 @@ struct BlockOp {
   const double* d;           // [Mpad] quadratic costs in cell order (0 in padding and beyond the loader's short D)
   const uint32_t* th;        // [Mpad] tail_local | head_local << 15 | kBTailFirst | kBLoop
   const uint32_t* gidx;      // [Mpad] natural arc index of a cell-order position (kBPad in padding)
+  const uint4* pdesc;        // [Mpad / 128] per stage up to four same-tail runs: start | (len - 1) << 8 | tile slot << 16 (kBNoPiece: none)
   double* xc;                // [Mpad] arc part of x in cell order (pass 2 workspace)
   TileOp tl;                 // tile lists over local node ids (T, ntile, thdr, lent, piece), R, and the exchange buffers:
                              // tl.fab.partials[rank] is [2][Bp][world * (GC + GR)], destination-indexed
@@ -84,7 +87,7 @@ constexpr int kBPre = 8;          // list entries per fold thread requested toge
 __host__ __device__ inline uint32_t block_pad_entry(uint32_t PL, uint32_t T) {
   return kBEntNew | (PL << kBEntNodeShift) | ((T + kMaxPieces - 1) * 8u);
 }
-__host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4; }
+__host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4 + 16; }  // + the stage's run descriptors
 // pass 1 never needs node values and accumulators at the same time (they alias), pass 2 needs both
 constexpr uint32_t kBMbarBytes = (kBComputeWarps * kBMaxRing + kBMaxList) * 8;
 __host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, uint32_t lblk, uint32_t nl, bool pass2, bool with_v) {
@@ -245,6 +248,29 @@ __device__ __forceinline__ double block_node_total(const BlockOp& bo, uint32_t p
   return warp_sum(a);
 }
 
+// Same-tail runs of a stage, summed by the compute warp that has just produced the values (they are still in its registers):
+// lane l holds arcs l, l + 32, l + 64, l + 96 of the stage.  A run [start, start + len) adds its arcs per lane in that order,
+// then the xor tree; lane 0 stores the sum into the tile buffer behind the T arc values, where the list walk finds it like
+// any other value.  Both passes run this code: the tail-side sums are bit-identical.  (Round-2 measurement: summed by the
+// fold warps from shared memory, these runs were 45 % of the fold's time, and the fold bounds phase B of pass 1.)
+__device__ __forceinline__ void stage_pieces(const double (&w)[4], uint32_t slot_desc, uint32_t wt_tile, uint32_t T, int lane) {
+  uint4 pd;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pd.x), "=r"(pd.y), "=r"(pd.z), "=r"(pd.w) : "r"(slot_desc));
+  const uint32_t d[4] = {pd.x, pd.y, pd.z, pd.w};
+  // (running the xor trees of the runs side by side instead of one after the other was measured 14 % SLOWER: 299 vs 263 us
+  // per pass-1 step at 20M arcs)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (d[i] == kBNoPiece) continue;  // the same for every lane
+    const uint32_t start = d[i] & 0xffu, len = ((d[i] >> 8) & 0xffu) + 1u;
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a = __dadd_rn(a, (uint32_t)(lane + 32 * q) - start < len ? w[q] : 0.0);
+    a = warp_sum(a);
+    if (lane == 0) asm volatile("st.shared.f64 [%0], %1;" ::"r"(wt_tile + (T + (d[i] >> 16)) * 8u), "d"(a));
+  }
+}
+
 // ---------------------------------------------------------------------------- node sums of a tile (fold warps)
 struct BlockTileHdr {
   uint32_t e0, L, D;  // first word of the tile's block, entries per thread, deepest chain
@@ -254,44 +280,13 @@ __device__ __forceinline__ BlockTileHdr block_tile_hdr(const TileOp& to, uint32_
   const TileHdr h = tile_hdr(to, tile_id);
   return BlockTileHdr{h.e0, h.L & 0xffffffu, h.L >> 24, h.q0, h.q1};
 }
-__device__ __forceinline__ void block_piece_request(const TileOp& to, const BlockTileHdr& h, uint32_t (&pc)[2]) {
-  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const uint32_t q = h.q0 + fwarp + kFoldWarps * (lane + 32 * i);
-    pc[i] = q < h.q1 ? __ldg(to.piece + q) : 0u;
-  }
-}
-// Adds the node sums of the tile held in buffer `wt` into s.acc; `lst` is the shared-memory copy of the tile's list block
-// (bulk-copied one tile ahead: a global load per batch of entries made the fold latency-bound -- 2.2 cycles per arc with
-// nothing else running, against 1.2 available in phase B of pass 1).  `pc` holds the tile's piece words on entry, those of
-// tile `next` (if there is one) on return.
+// Adds the node sums of the tile held in buffer `wt` (arc values + run sums) into s.acc; `lst` is the shared-memory copy of
+// the tile's list block (bulk-copied ahead: a global load per batch of entries made the fold latency-bound -- 2.2 cycles
+// per arc with nothing else running, against 1.2 available in phase B of pass 1).
 __device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSmem& s, uint32_t wt, uint32_t lst, const BlockTileHdr& h,
-                                                const BlockTileHdr& next, bool has_next, uint32_t (&pcw)[2], uint32_t dummy) {
-  const int ftid = threadIdx.x - kStreamThreads, lane = ftid & 31, fwarp = ftid >> 5;
-  if (h.q1 > h.q0) {  // same-tail runs of the tile, one warp per piece: four lane-strided chains, xor tree
-    uint32_t i = 0;
-    for (uint32_t q = h.q0 + fwarp; q < h.q1; q += kFoldWarps, ++i) {
-      const uint32_t pc = __shfl_sync(0xffffffffu, i < 32 ? pcw[0] : pcw[1], i & 31);
-      const uint32_t first = pc & 0xffffu, len = (pc >> 16) + 1;
-      const uint32_t w = wt + first * 8u;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      for (uint32_t e = lane; e < len; e += 128) {
-        const double x0 = lds64_at(w + e * 8u);
-        const double x1 = e + 32 < len ? lds64_at(w + (e + 32) * 8u) : 0.0;
-        const double x2 = e + 64 < len ? lds64_at(w + (e + 64) * 8u) : 0.0;
-        const double x3 = e + 96 < len ? lds64_at(w + (e + 96) * 8u) : 0.0;
-        a0 = __dadd_rn(a0, x0);
-        a1 = __dadd_rn(a1, x1);
-        a2 = __dadd_rn(a2, x2);
-        a3 = __dadd_rn(a3, x3);
-      }
-      const double a = warp_sum(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)));
-      if (lane == 0) sm_st(SmArr{wt}, to.T + (q - h.q0), a);
-    }
-    bar_sync_n(kBarFold, kFoldThreads);
-  }
-  if (has_next) block_piece_request(to, next, pcw);
+                                                uint32_t dummy) {
+  (void)to;
+  const int ftid = threadIdx.x - kStreamThreads;
   // Walk of my slice: straight-line code per entry (value load, sign, add; a node change is a predicated read-modify-write of
   // the previous node's accumulator).  The share of my first node goes to my scratch word instead when earlier threads hold
   // entries of the same node (depth > 0) and is added chain position by chain position afterwards.
@@ -343,9 +338,10 @@ __device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSme
 // ---------------------------------------------------------------------------- the folding sweep
 // One sweep over the CTA's cell that produces a new arc vector AND its node sums.  Compute warp w owns the stages
 // g = w, w + 8, w + 16, ... of the cell (a stage = 128 consecutive cell-order arcs) and a private ring of RING slots; lane 0
-// issues the bulk copies of N8 8-byte arrays and N4 4-byte arrays per stage.  `consume(pos, slot, wt_addr, lane)` handles
-// the arcs pos + lane + 32 q (q < 4): it reads array a of the slot at slot + a * 1024 (+ 8 * index) (4-byte arrays behind
-// the 8-byte ones), stores its results to global memory and the new arc value of arc q to wt_addr + 8 * (lane + 32 q).
+// issues the bulk copies of N8 8-byte arrays, N4 4-byte arrays and the stage's run descriptors.  `consume(pos, slot, wt_stage,
+// wt_tile, desc, lane)` handles the arcs pos + lane + 32 q (q < 4): it reads array a of the slot at slot + a * 1024 (+ 8 *
+// index) (4-byte arrays behind the 8-byte ones), stores its results to global memory, the new arc value of arc q to
+// wt_stage + 8 * (lane + 32 q), and the sums of the stage's same-tail runs behind the tile's arc values (stage_pieces).
 // A tile (T arcs) is complete when all compute warps have arrived; the fold warps then add its node sums into s.acc while
 // the compute warps fill the other tile buffer (named barriers as in tile_loop).  `rs` (ring slot and mbarrier phase of this
 // warp's next stage) lives across the sweeps of a kernel: the mbarriers are initialised once.
@@ -365,7 +361,8 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
   if (warp < kBComputeWarps) {
     const uint32_t nk = c.nst > (uint32_t)warp ? (c.nst - warp + kBComputeWarps - 1) / kBComputeWarps : 0;  // my stages
     const uint32_t ring0 = s.ring + (uint32_t)warp * RING * slot_bytes, bar0 = s.mbar + (uint32_t)warp * kBMaxRing * 8u;
-    constexpr uint32_t kTx = N8 * kBStage * 8 + N4 * kBStage * 4;
+    constexpr uint32_t kTx = N8 * kBStage * 8 + N4 * kBStage * 4 + 16;
+    constexpr uint32_t kDescOff = N8 * kBStage * 8 + N4 * kBStage * 4;  // the stage's run descriptors sit behind the arrays
     auto issue = [&](uint32_t k, uint32_t sl) __attribute__((always_inline)) {  // lane 0 only: stage k of this warp into slot sl
       const uint32_t bar = bar0 + sl * 8u, dst = ring0 + sl * slot_bytes;
       const size_t pos = (size_t)c.c0 + ((size_t)k * kBComputeWarps + warp) * kBStage;
@@ -374,6 +371,7 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
       for (int a = 0; a < N8; ++a) bulk_g2s(dst + a * (kBStage * 8), src8[a] + pos, kBStage * 8, bar);
 #pragma unroll
       for (int a = 0; a < N4; ++a) bulk_g2s(dst + N8 * (kBStage * 8) + a * (kBStage * 4), src4[a] + pos, kBStage * 4, bar);
+      bulk_g2s(dst + kDescOff, bo.pdesc + pos / kBStage, 16, bar);
     };
     if (lane == 0) {
       uint32_t sl = rs.slot;
@@ -393,7 +391,8 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
         if (timed) t_x = clock64();
         mbar_wait(bar0 + rs.slot * 8u, rs.phase);
         if (timed) c_a += clock64() - t_x;
-        if (!(bo.dbg & 2u)) consume(c.c0 + g * kBStage, ring0 + rs.slot * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), lane);
+        if (!(bo.dbg & 2u))
+          consume(c.c0 + g * kBStage, ring0 + rs.slot * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), wt0, ring0 + rs.slot * slot_bytes + kDescOff, lane);
         __syncwarp();  // every lane has read its slot words
         if (lane == 0 && k + RING < nk) issue(k + RING, rs.slot);
         ++k;
@@ -427,13 +426,11 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
     };
     BlockTileHdr h0 = block_tile_hdr(bo.tl, tile0), h1 = h0, hf = h0;
     if (c.ntiles > 1) h1 = block_tile_hdr(bo.tl, tile0 + 1);
-    uint32_t pcw[2] = {0u, 0u};
     if (c.ntiles) {
       if (issuer) {
         for (uint32_t u = 0; u < nl && u < c.ntiles; ++u) fetch(block_tile_hdr(bo.tl, tile0 + u), u);
         if (nl < c.ntiles) hf = block_tile_hdr(bo.tl, tile0 + nl);  // the next block to fetch
       }
-      block_piece_request(bo.tl, h0, pcw);
     }
     uint32_t b = 0;  // list buffer of tile t
     for (uint32_t t = 0; t < c.ntiles; ++t) {
@@ -449,7 +446,7 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
       mbar_wait(lbar + b * 8u, (rs.lphase >> b) & 1u);
       rs.lphase ^= 1u << b;
       if (!(bo.dbg & 1u))
-        block_fold_tile(bo.tl, s, s.wt.a + (t & 1u) * s.wt_stride, s.lst + b * bo.lblk, h0, h1, t + 1 < c.ntiles, pcw, dummy);
+        block_fold_tile(bo.tl, s, s.wt.a + (t & 1u) * s.wt_stride, s.lst + b * bo.lblk, h0, dummy);
       bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
       h0 = h1;
       h1 = h2;
@@ -481,13 +478,14 @@ __device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem
   const uint32_t* const src4[1] = {nullptr};
   fold_sweep<1, 0>(
       bo, s, c, RING, slot_bytes, src8, src4,
-      [&](uint32_t, uint32_t slot, uint32_t wt, int lane) __attribute__((always_inline)) {
+      [&](uint32_t, uint32_t slot, uint32_t wt, uint32_t wt_tile, uint32_t desc, int lane) __attribute__((always_inline)) {
         const uint32_t sl = slot + lane * 8u, w = wt + lane * 8u;
-        const double x0 = lds64<0>(sl), x1 = lds64<256>(sl), x2 = lds64<512>(sl), x3 = lds64<768>(sl);
-        sts64<0>(w, x0);
-        sts64<256>(w, x1);
-        sts64<512>(w, x2);
-        sts64<768>(w, x3);
+        const double x[4] = {lds64<0>(sl), lds64<256>(sl), lds64<512>(sl), lds64<768>(sl)};
+        sts64<0>(w, x[0]);
+        sts64<256>(w, x[1]);
+        sts64<512>(w, x[2]);
+        sts64<768>(w, x[3]);
+        stage_pieces(x, desc, wt_tile, bo.tl.T, lane);
       },
       rs);
 }
@@ -624,7 +622,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
         const uint32_t* const src4[1] = {nullptr};
         fold_sweep<2, 0>(
             bo, s, c, RING, slot_bytes, src8, src4,
-            [&](uint32_t pos, uint32_t slot, uint32_t wt, int ln) __attribute__((always_inline)) {
+            [&](uint32_t pos, uint32_t slot, uint32_t wt, uint32_t wt_tile, uint32_t desc, int ln) __attribute__((always_inline)) {
               const uint32_t sl = slot + ln * 8u;
               double wn[4], wc[4];
               wn[0] = lds64<0>(sl), wn[1] = lds64<256>(sl), wn[2] = lds64<512>(sl), wn[3] = lds64<768>(sl);
@@ -642,6 +640,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
               sts64<256>(ws, w[1]);
               sts64<512>(ws, w[2]);
               sts64<768>(ws, w[3]);
+              stage_pieces(w, desc, wt_tile, bo.tl.T, ln);
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc = fma(w[q], w[q], acc);
             },
@@ -786,7 +785,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
       const double* const src8[4] = {Vc, Vp, xc, bo.d};
       const uint32_t* const src4[2] = {bo.th, bo.gidx};
       const uint32_t* const src4n[1] = {bo.th};
-      auto body = [&](uint32_t pos, uint32_t slot, uint32_t wt, int ln) __attribute__((always_inline)) {
+      auto body = [&](uint32_t pos, uint32_t slot, uint32_t wt, uint32_t wt_tile, uint32_t desc, int ln) __attribute__((always_inline)) {
         // all loads of the lane's four arcs first, then the node-value gathers, then the arithmetic, then the stores
         const uint32_t sl = slot + ln * 8u, sl4 = slot + 4 * kBStage * 8 + ln * 4u;
         double v[4], vp[4], xx[4], dd[4], xt[4], xh[4];
@@ -823,6 +822,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
         sts64<256>(ws, w[1]);
         sts64<512>(ws, w[2]);
         sts64<768>(ws, w[3]);
+        stage_pieces(w, desc, wt_tile, bo.tl.T, ln);
         if (WITH_V) {
           const uint32_t sg = sl4 + kBStage * 4;
           const uint32_t g0 = lds32<0>(sg), g1 = lds32<128>(sg), g2 = lds32<256>(sg), g3 = lds32<384>(sg);

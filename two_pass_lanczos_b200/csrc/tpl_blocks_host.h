@@ -28,7 +28,7 @@ struct HostBlocks {
   uint32_t ring1 = 0, ring2 = 0, ring2v = 0, lblk = 0, nl = 2;
   std::vector<uint32_t> cell_off, tbs, hbs, tbn, hbn, th, gidx;
   std::vector<double> d;
-  std::vector<uint4> thdr;
+  std::vector<uint4> thdr, pdesc;  // pdesc: per 128-arc stage up to four same-tail runs (start | (len - 1) << 8 | tile slot << 16)
   std::vector<uint32_t> lent, piece;
 };
 
@@ -74,7 +74,8 @@ struct BlockListScratch {
   std::vector<uint32_t> cnt, e_node, e_code, s_node, s_code, order;
 };
 inline bool build_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const uint32_t* hl, uint32_t T, uint32_t ntile,
-                             BlockListScratch& w, std::vector<uint4>& thdr, std::vector<uint32_t>& lent, std::vector<uint32_t>& piece) {
+                             BlockListScratch& w, std::vector<uint4>& thdr, std::vector<uint32_t>& lent, std::vector<uint32_t>& piece,
+                             uint4* pdesc) {
   const uint32_t B = kFoldThreads, pad = block_pad_entry(PL, T);
   w.cnt.resize((size_t)PL + 1);
   thdr.assign(ntile, make_uint4(0, 0, 0, 0));
@@ -86,29 +87,35 @@ inline bool build_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const 
     w.e_node.clear();
     w.e_code.clear();
     uint32_t npieces = 0;
-    for (uint32_t i = t0; i < t1;) {  // tail side: maximal runs of equal tail (loops / padding contribute nothing)
-      if (tl[i] == hl[i]) {
-        ++i;
-        continue;
-      }
-      uint32_t j = i;
-      while (j < t1 && tl[j] == tl[i] && tl[j] != hl[j]) ++j;
-      const uint32_t len = j - i, need = (len + kPieceMax - 1) / kPieceMax;
-      if (len >= kPieceMin && npieces + need <= kMaxPieces - 1) {
-        for (uint32_t q = i; q < j; q += kPieceMax) {
-          const uint32_t l = std::min<uint32_t>(kPieceMax, j - q);
-          piece.push_back((q - t0) | ((l - 1) << 16));
+    // tail side: maximal runs of equal tail INSIDE a stage of 128 arcs (loops / padding contribute nothing).  Runs of at
+    // least kBPieceMin arcs, up to four per stage, are summed by the compute warp that produces the stage (stage_pieces)
+    // and enter the list as one entry that reads the sum from slot T + npieces of the tile buffer.
+    for (uint32_t s0 = t0; s0 < t1; s0 += kBStage) {
+      const uint32_t s1 = std::min(t1, s0 + kBStage);
+      uint32_t used = 0;
+      uint32_t d4[4] = {kBNoPiece, kBNoPiece, kBNoPiece, kBNoPiece};
+      for (uint32_t i = s0; i < s1;) {
+        if (tl[i] == hl[i]) {
+          ++i;
+          continue;
+        }
+        uint32_t j = i;
+        while (j < s1 && tl[j] == tl[i] && tl[j] != hl[j]) ++j;
+        const uint32_t len = j - i;
+        if (len >= kBPieceMin && used < 4 && npieces < kMaxPieces - 1) {
+          d4[used++] = (i - s0) | ((len - 1) << 8) | (npieces << 16);
           w.e_node.push_back(tl[i]);
           w.e_code.push_back((T + npieces) * 8u);
           ++npieces;
+        } else {
+          for (uint32_t q = i; q < j; ++q) {
+            w.e_node.push_back(tl[i]);
+            w.e_code.push_back((q - t0) * 8u);
+          }
         }
-      } else {
-        for (uint32_t q = i; q < j; ++q) {
-          w.e_node.push_back(tl[i]);
-          w.e_code.push_back((q - t0) * 8u);
-        }
+        i = j;
       }
-      i = j;
+      pdesc[s0 / kBStage] = make_uint4(d4[0], d4[1], d4[2], d4[3]);
     }
     for (uint32_t i = t0; i < t1; ++i)  // head side
       if (tl[i] != hl[i]) {
@@ -251,6 +258,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
       h.T = T;
       h.ntile = std::max<uint32_t>(1, (padded_max + T - 1) / T);
       std::vector<uint8_t> failed(Gc, 0);
+      h.pdesc.assign(h.Mpad / kBStage, make_uint4(kBNoPiece, kBNoPiece, kBNoPiece, kBNoPiece));
       auto run = [&](int first) {
         BlockListScratch w;
         std::vector<uint32_t> tl, hl;
@@ -264,7 +272,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
             tl[i] = skip ? 0u : (w32 & 0x7fffu);
             hl[i] = skip ? 0u : PT + ((w32 >> 15) & 0x7fffu);
           }
-          failed[c] = !build_cell_lists(n, PT + PH, tl.data(), hl.data(), h.T, h.ntile, w, thdr[c], lent[c], piece[c]);
+          failed[c] = !build_cell_lists(n, PT + PH, tl.data(), hl.data(), h.T, h.ntile, w, thdr[c], lent[c], piece[c], h.pdesc.data() + c0 / kBStage);
         }
       };
       if (threads == 1) {
@@ -322,15 +330,26 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
 // flags mark exactly the node changes inside a slice, entries are sorted by node across the slices, and every thread's depth
 // is its position in the chain of threads that share its first node.
 inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const uint32_t* hl, uint32_t T, uint32_t ntile,
-                            const uint4* thdr, const std::vector<uint32_t>& lent, const std::vector<uint32_t>& piece) {
+                            const uint4* thdr, const std::vector<uint32_t>& lent, const uint4* pdesc) {
   const uint32_t B = kFoldThreads, pad = block_pad_entry(PL, T);
   std::vector<uint8_t> seen_t(T), seen_h(T);
   for (uint32_t t = 0; t < ntile; ++t) {
     const uint4 hd = thdr[t];
     const uint32_t L = hd.y & 0xffffffu, D = hd.y >> 24;
     const uint32_t t0 = std::min(n, t * T), t1 = std::min(n, t0 + T), na = t1 - t0;
-    if ((size_t)hd.x + (size_t)(L + 1) * B > lent.size() || hd.z > hd.w || hd.w > piece.size()) return 2;
-    if (hd.w - hd.z > kMaxPieces - 1) return 3;
+    if ((size_t)hd.x + (size_t)(L + 1) * B > lent.size()) return 2;
+    // the tile's runs: slot -> (first arc, length), from the stage descriptors
+    std::vector<std::pair<uint32_t, uint32_t>> runs;
+    for (uint32_t s0 = t0; s0 < t1; s0 += kBStage) {
+      const uint4 d = pdesc[s0 / kBStage];
+      for (uint32_t dd : {d.x, d.y, d.z, d.w}) {
+        if (dd == kBNoPiece) continue;
+        const uint32_t slot = dd >> 16, start = dd & 0xffu, len = ((dd >> 8) & 0xffu) + 1;
+        if (slot != runs.size() || start + len > std::min<uint32_t>(kBStage, t1 - s0) || len < kBPieceMin) return 3;
+        runs.emplace_back(s0 - t0 + start, len);
+      }
+    }
+    if (runs.size() > kMaxPieces - 1) return 3;
     std::fill(seen_t.begin(), seen_t.end(), 0);
     std::fill(seen_h.begin(), seen_h.end(), 0);
     uint32_t prev_node = 0, prev_depth = 0, maxdepth = 0;
@@ -363,11 +382,10 @@ inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const u
         if (e & kBEntMinus) {  // head side
           if (idx >= na || hl[t0 + idx] != node || seen_h[idx]) return 9;
           seen_h[idx] = 1;
-        } else if (idx >= T) {  // a piece
-          const uint32_t q1 = hd.z + (idx - T);
-          if (q1 >= hd.w) return 10;
-          const uint32_t start = piece[q1] & 0xffffu, len = (piece[q1] >> 16) + 1;
-          if (len > kPieceMax || start + len > na) return 11;
+        } else if (idx >= T) {  // a same-tail run summed by the compute warp
+          if (idx - T >= runs.size()) return 10;
+          const uint32_t start = runs[idx - T].first, len = runs[idx - T].second;
+          if (start + len > na) return 11;
           for (uint32_t a = start; a < start + len; ++a) {
             if (tl[t0 + a] != node || seen_t[a]) return 12;
             seen_t[a] = 1;
@@ -447,7 +465,7 @@ inline int check_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_t
       }
     }
     const int rc = check_cell_lists(c1 - c0, h.PT + h.PH, tl.data(), hl.data(), h.T, h.ntile, h.thdr.data() + (size_t)c * h.ntile,
-                                    h.lent, h.piece);
+                                    h.lent, h.pdesc.data() + c0 / kBStage);
     if (rc) return 100 + rc;
   }
   for (size_t j = 0; j < m; ++j)

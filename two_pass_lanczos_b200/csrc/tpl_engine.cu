@@ -812,6 +812,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       if (!rc) rc = dev_upload(op, &bo.d, hb.d);
       if (!rc) rc = dev_upload(op, &bo.th, hb.th);
       if (!rc) rc = dev_upload(op, &bo.gidx, hb.gidx);
+      if (!rc) rc = dev_upload(op, &bo.pdesc, hb.pdesc);
       if (!rc) rc = dev_upload(op, &bo.tl.thdr, hb.thdr);
       if (!rc) rc = dev_upload(op, &bo.tl.lent, hb.lent);
       if (!rc) rc = dev_upload(op, &bo.tl.piece, hb.piece);
@@ -1004,7 +1005,8 @@ int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   stats[9] = cmax;
   stats[10] = cmin;
   stats[11] = hb.lent.size();
-  stats[12] = hb.piece.size();
+  stats[12] = 0;
+  for (const uint4& d : hb.pdesc) stats[12] += (d.x != tpl::kBNoPiece) + (d.y != tpl::kBNoPiece) + (d.z != tpl::kBNoPiece) + (d.w != tpl::kBNoPiece);
   for (uint32_t e : hb.lent) hsh = (hsh ^ e) * 1099511628211ull;
   for (uint32_t e : hb.piece) hsh = (hsh ^ e) * 1099511628211ull;
   for (uint32_t e : hb.th) hsh = (hsh ^ e) * 1099511628211ull;
