@@ -11,7 +11,10 @@
 // on the number of threads).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <numeric>
 #include <thread>
@@ -162,6 +165,14 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
                          size_t smem_limit, HostBlocks& h, int threads = 0) {
   h = HostBlocks{};
   if (m == 0 || p == 0 || G < 1) return;
+  const bool timing = std::getenv("TPL_BUILD_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "build_blocks %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
   h.GR = std::max<uint32_t>(1, (uint32_t)std::floor(std::sqrt((double)G)));
   h.GC = std::max<uint32_t>(1, (uint32_t)G / h.GR);
   const uint32_t Gc = h.GR * h.GC;
@@ -170,6 +181,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
     ++outdeg[tail[j]];
     ++indeg[head[j]];
   }
+  lap("degrees");
   // blocks over the ACTIVE nodes of each side only (ascending node id): tbn / hbn list them, tbs / hbs cut the lists
   std::vector<uint64_t> wt_t, wt_h;
   std::vector<uint32_t> tpos(p, 0), hpos(p, 0);  // position of a node in tbn / hbn
@@ -201,6 +213,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   for (uint32_t b = 0; b < h.GC; ++b)
     for (uint32_t q = h.hbs[b]; q < h.hbs[b + 1]; ++q) node_hb[h.hbn[q]] = b;
 
+  lap("blocks");
   // arcs by tail node, then by arc index (identity for a tail-grouped arc list) ...
   std::vector<uint32_t> by_tail(m);
   {
@@ -208,6 +221,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
     for (size_t u = 0; u < p; ++u) ptr[u + 1] = ptr[u] + outdeg[u];
     for (size_t j = 0; j < m; ++j) by_tail[ptr[tail[j]]++] = (uint32_t)j;
   }
+  lap("sort by tail");
   // ... then stably by cell
   std::vector<uint64_t> cnt(Gc + 1, 0);
   auto cell_of = [&](uint32_t j) { return node_tb[tail[j]] * h.GC + node_hb[head[j]]; };
@@ -223,6 +237,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   h.cell_off[Gc] = (uint32_t)off;
   h.Mpad = (uint32_t)off;
 
+  lap("cell counts");
   h.d.assign(h.Mpad, 0.0);
   h.th.assign(h.Mpad, kBLoop);
   h.gidx.assign(h.Mpad, kBPad);
@@ -237,6 +252,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
     }
   }
   std::vector<uint32_t>().swap(by_tail);
+  lap("cell order (d, th, gidx)");
 
   // tile lists per cell, over local node ids; a loop / padding slot gets tail == head (the list builder skips those).
   // Tile size: the largest multiple of 1024 arcs (at most 4096) whose kernels fit with three ring slots in pass 2 (bytes in
@@ -292,6 +308,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
       h.lblk = (Lmax + 1) * 4u * kFoldThreads;
       done = blocks_fit(PT + PH, smem_limit, T, h.lblk, need, h.ring1, h.ring2, h.ring2v);
     }
+  lap("tile lists");
   if (!done) return;
   {  // as many list buffers as still fit next to the rings (deeper list prefetch; a short sweep then starts with its whole list in flight)
     const size_t budget = smem_limit > 3072 ? smem_limit - 3072 : 0;
@@ -322,6 +339,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
     std::vector<uint32_t>().swap(lent[c]);
     std::vector<uint32_t>().swap(piece[c]);
   }
+  lap("concatenate");
   h.ok = true;
 }
 
