@@ -141,8 +141,10 @@ def config_dict(args, inst):
     return {"workload": workload_string(args, inst),
             "l2": "GPU arm: L2 flushed between solves (256 MiB write); CPU arm: 28 MB working set, cold first run discarded",
             "parallelism": "1 GPU" if world == 1 else
-            f"{world} GPUs, arc-partitioned rows + replicated node segment; per Lanczos step a reduction of the p={inst.p} "
-            f"node sums and two scalar all-reduces (pass 2: the node sums only); the CPU arm runs on rank 0's host cores"}
+            f"{world} GPUs behind the arc-partitioned rank-local API (rank r owns an arc block + a replica of the p={inst.p} node "
+            f"entries); the library shards the solve when that pays (per step a reduction of the node sums and two scalar "
+            f"all-reduces, fused into the kernels) and solves replicated when the whole job fits one GPU's on-chip kernels "
+            f"(`arm.kernel_shape`); the CPU arm runs on rank 0's host cores"}
 
 
 def workload_string(args, inst):
@@ -435,6 +437,8 @@ def run_b200(args, rank, world, local_rank):
             "gather": "pass1_kernel<IncidenceOp,false> (streaming, gathered node rows; one persistent launch per pass)",
             "blocked": "pass1_blocked_kernel<false> (streaming, 2-D node-block partition, cell-order vectors, bulk-copy input ring; "
                        "one persistent launch per pass)",
+            "replicated": "pass1_cell_kernel<false> on every rank (the whole operator fits the on-chip cell kernels: the ranks "
+                          "all-reduce their slices of b once and solve redundantly, no per-step communication)",
             "sharded": "shard_phase_a_kernel + shard_phase_b_kernel (2 launches + 2 NCCL all-reduces per step)",
             "sharded-blocked": "pass1_blocked_kernel<false> spanning all ranks (destination-indexed node-sum exchange, node-value "
                                "all-gather and alpha / beta all-reduce as peer-memory stores over NVLink inside one persistent "
@@ -442,7 +446,7 @@ def run_b200(args, rank, world, local_rank):
             "sharded-fused": "pass1_tiled_kernel<false> spanning all ranks (node-sum reduce-scatter, node-value all-gather and "
                              "alpha / beta all-reduce as peer-memory stores over NVLink inside one persistent launch per pass)",
         }.get(shape, shape)
-        on_chip = shape in ("cells", "chunks")
+        on_chip = shape in ("cells", "chunks", "replicated")
         line = {
             "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",

@@ -153,8 +153,9 @@ uint64_t tpl_op_device_bytes(const tpl_op* op);
  * they differ in the (fixed) order in which a node row is summed, i.e. by rounding only. */
 int tpl_op_set_mode(tpl_op* op, int mode);
 /* Name of the kernel family a whole-pass solve through this handle runs: "cells", "chunks", "blocked", "tiled", "gather",
- * "csr", "dense", "sharded" (NCCL phase kernels), "sharded-fused" (tiled kernels spanning all ranks) or "sharded-blocked"
- * (blocked kernels spanning all ranks) (static string). */
+ * "csr", "dense", "sharded" (NCCL phase kernels), "sharded-fused" (tiled kernels spanning all ranks), "sharded-blocked"
+ * (blocked kernels spanning all ranks) or "replicated" (sharded handle whose whole operator fits one GPU's on-chip kernels)
+ * (static string). */
 const char* tpl_op_kernel_shape(const tpl_op* op);
 /* Host-only: builds the tile entry lists of the tiled streaming kernels for `ctas` CTAs and tiles of `tile_arcs` arcs on
  * `threads` host threads (0 = automatic) and checks them (every non-loop arc once on its head and once on its tail node
@@ -267,6 +268,12 @@ int tpl_lanczos_two_pass_inv_adaptive(tpl_op* op, const double* b, size_t k_max,
  * supplies the 128-byte ncclUniqueId made by rank 0 (tpl_comm_unique_id) through its own
  * rendezvous (any out-of-band channel; bench.py broadcasts it between its ranks).
  * ------------------------------------------------------------------------------------ */
+/* REPLICATED execution: when the WHOLE operator fits the on-chip cell kernels of one GPU (about 600 k arcs), a sharded handle
+ * with world > 1 solves the full problem on every rank -- one all-reduce assembles b from the ranks' slices, the passes run
+ * without any per-step communication, every rank returns its slice (kernel shape "replicated").  Same rank-local API and
+ * results; sharding such a job costs two cross-GPU barriers per Lanczos step and is several times slower than one GPU.
+ * tpl_op_set_mode(op, != 0) or the environment variable TPL_NO_REPLICATE=1 (read at construction) keep the arc-partitioned
+ * paths; a replicated handle has no exchange block (tpl_op_fabric_export fails, the ranks stay unconnected). */
 int tpl_comm_unique_id(uint8_t id_out[128]);
 int tpl_op_from_kkt_sharded(size_t m, size_t p, size_t arc_begin, size_t arc_end, const uint32_t* tail,
                             const uint32_t* head, const double* d, size_t d_len, int device, int rank,

@@ -21,6 +21,7 @@ def main():
 
     out_path, m, k = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     fused = len(sys.argv) > 4 and sys.argv[4] == "fused"
+    replicated = len(sys.argv) > 4 and sys.argv[4] == "replicated"  # else TPL_NO_REPLICATE=1 is set by the launcher
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
@@ -29,7 +30,10 @@ def main():
     ident = sharding.broadcast_unique_id(dist, rank)
     op = sharding.sharded_linop(m, p, inst.tail, inst.head, inst.d, rank, world, ident, device=local,
                                dist=dist if fused else None)
-    assert op.kernel_shape() in (("sharded-blocked", "sharded-fused") if fused and world > 1 else ("sharded",))
+    if replicated and world > 1:
+        assert op.kernel_shape() == "replicated"
+    else:
+        assert op.kernel_shape() in (("sharded-blocked", "sharded-fused") if fused and world > 1 else ("sharded",))
     lo, hi = op.arc_lo, op.arc_hi
     info = op.shard_info()
     assert info == {"rank": rank, "world": world, "local_arcs": hi - lo, "nodes": p}

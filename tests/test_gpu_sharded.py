@@ -18,12 +18,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_world(world, m, k, tmp_path, fused=False):
+def _run_world(world, m, k, tmp_path, fused=False, replicated=False):
     out = str(tmp_path / f"sharded_w{world}.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(29400 + world + (10 if fused else 0)), os.path.join(ROOT, "tests", "sharded_worker.py"),
-           out, str(m), str(k), "fused" if fused else "nccl"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "127.0.0.1", "--master-port", str(29400 + world + (10 if fused else 0) + (20 if replicated else 0)),
+           os.path.join(ROOT, "tests", "sharded_worker.py"), out, str(m), str(k),
+           "replicated" if replicated else ("fused" if fused else "nccl")]
+    env = dict(os.environ)
+    if not replicated:  # keep the arc-partitioned paths under test at sizes that would otherwise run replicated
+        env["TPL_NO_REPLICATE"] = "1"
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     return np.load(out)
 
@@ -81,3 +85,16 @@ def test_sharded_world2_fused(tmp_path, m, k):
         pytest.skip("needs 2 GPUs")
     inst, r = _check(_run_world(2, m, k, tmp_path, fused=True), m, k)
     assert int(r["launches"]) < 40  # a handful of launches per solve, not two per Lanczos step
+
+
+def test_sharded_world2_replicated(tmp_path):
+    """An operator that fits the on-chip cell kernels as a whole runs REPLICATED on a sharded handle: every rank solves the full
+    problem (one all-reduce assembles b, no per-step communication) and returns its slice -- same rank-local API, same parity,
+    bit-identical node replicas, bit-identical regenerated basis."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    m, k = 50_000, 80
+    inst, r = _check(_run_world(2, m, k, tmp_path, replicated=True), m, k)
+    assert int(r["launches"]) < 40
