@@ -45,6 +45,9 @@ def main():
     p2 = alg.lanczos_pass_two_with_basis(op, b_loc, dec, yk)
     x_exp = tpl.lanczos_two_pass(op, b_loc, k, "exp")
     x_one = tpl.lanczos(op, b_loc, k, "exp")
+    # device tensors on torch's current stream (the handle, and the inner handle of a replicated operator, adopt it)
+    x_dev = tpl.lanczos_two_pass(op, torch.from_numpy(b_loc).cuda(), k, "exp")
+    assert x_dev.is_cuda and np.array_equal(x_dev.cpu().numpy(), x_exp)
     res = {"b": b_loc, "alphas": dec.alphas, "betas": dec.betas, "b_norm": dec.b_norm, "steps": dec.steps_taken,
            "drift": float(np.abs(std.v_k - p2.v_k).max()), "std_alphas": std.decomposition.alphas, "x_p2": p2.x_k,
            "x_exp": x_exp, "x_one": x_one, "launches": op.kernel_launches()}

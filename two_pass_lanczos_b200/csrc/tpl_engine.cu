@@ -912,11 +912,13 @@ uint64_t tpl_op_device_bytes(const tpl_op* op) { return op ? op->device_bytes : 
 int tpl_op_set_stream(tpl_op* op, void* cuda_stream) {
   if (!op) return fail(TPL_ERR_PANIC, "null argument");
   DeviceGuard g(op->device);
+  // (the inner handle of a replicated operator shares this handle's stream: it moves first, while the old stream still exists)
+  if (op->inner)
+    if (int rc = tpl_op_set_stream(op->inner, cuda_stream)) return rc;
   CUDA_TRY(cudaStreamSynchronize(op->stream));
   if (op->own_stream) CUDA_TRY(cudaStreamDestroy(op->stream));
   op->stream = static_cast<cudaStream_t>(cuda_stream);
   op->own_stream = false;
-  if (op->inner) return tpl_op_set_stream(op->inner, cuda_stream);
   return TPL_OK;
 }
 
