@@ -28,9 +28,16 @@
 namespace tpl {
 
 constexpr int kBStage = 128;                 // arcs of one warp-stage (4 per lane)
-constexpr int kBComputeWarps = kStreamWarps; // warps 0..7 compute, warps 8..15 fold (as in tpl_tiles.cuh)
+// Warp roles of the folding sweeps: warps [0, NCW) compute, the rest fold.  Pass 2 (8 / 8): its compute side is the heavy one
+// per arc but HBM-bound; pass 1 (12 / 4): phase B moves only 28 B per arc, its compute warps were latency-bound on their
+// dependent chains (ring wait -> loads -> run sums through five shuffle rounds) with two warps per scheduler, while the list
+// walk alone costs 8 us of a 250-us step at 20M arcs -- so the fold gets 4 warps, each thread walking two of the 256 slices.
+constexpr int kBComputeWarps1 = 12, kBComputeWarps2 = 8;
+constexpr int kBSlices = kFoldThreads;        // list slices per tile (host format; independent of how many threads walk them)
 constexpr int kBMaxRing = 4;
 constexpr int kBMaxList = 8;
+constexpr int kBMaxTileBufs = 4;
+constexpr int kBBarFull = 6, kBBarEmpty = 10;  // named barriers of the tile buffers (tpl_tiles.cuh uses 1..5)
 constexpr uint32_t kBLoop = 0x80000000u;     // th word: self-loop or padding (no incidence entries)
 constexpr uint32_t kBTailFirst = 0x40000000u;  // th word: global tail index < global head index (CSC accumulation order)
 constexpr uint32_t kBPad = 0xffffffffu;      // gidx of a padding slot
@@ -44,6 +51,7 @@ struct BlockOp {
   uint32_t ring1, ring2, ring2v;  // ring slots per compute warp: pass 1, pass 2, pass 2 with a basis
   uint32_t lblk;     // bytes of the largest tile list block ((L + 1) rows of kFoldThreads words): size of a list buffer
   uint32_t nl;       // list buffers (2 .. kBMaxList): the list block of a tile is bulk-copied nl - 1 tiles ahead
+  uint32_t ntb;      // tile buffers (2 .. kBMaxTileBufs): the compute warps run at most ntb tiles ahead of the fold
   uint32_t m;        // arcs in natural order (node part of a natural-order vector starts here)
   uint32_t dbg;      // timing experiments only (results are wrong): 1 = fold warps skip their work, 2 = compute warps skip theirs
   const uint32_t* cell_off;  // [G + 1] first cell-order position of every cell (multiples of kBStage)
@@ -69,43 +77,52 @@ struct BlockSmem {
   uint32_t ring;   // shared-window address of the slot area: [compute warp][slot][slot_bytes]
   uint32_t mbar;   // [compute warp][kBMaxRing] mbarriers of the rings, then kBMaxList mbarriers of the list buffers
   uint32_t lst;    // [nl][lblk] list blocks of the tile being folded and of the next ones (bulk-copied nl - 1 tiles ahead)
-  uint32_t scr;    // [kFoldThreads] doubles: a fold thread's share of a node that earlier threads also hold
+  uint32_t scr;    // [kBSlices] doubles: a slice's share of a node that earlier slices also hold
+  uint32_t hdr;    // [ntile] uint4: the headers of the cell's tiles (copied once per launch: a global load per tile sat on the
+                   // fold's critical path with the latency of a saturated memory system)
 };
-// List format of the blocked kernels (host: build_cell_lists).  A tile's block is (L + 1) rows of kFoldThreads words,
-// thread-interleaved: row 0 = the thread's DEPTH, rows 1..L its entries
-//     minus << 31 | new_node << 30 | local node << 16 | 8 * index into the tile buffer (arcs, then pieces)
-// sorted by node and cut into slices of EQUAL length: a node may straddle threads.  A thread adds the values of one node in a
-// register and touches the shared accumulator once per node; the share of its FIRST node is added `depth` barrier phases
-// later when earlier threads hold entries of the same node (depth = position in that chain), so the order in which the
-// shares of a node are added is fixed and no two threads ever update one accumulator in the same phase.
+// List format of the blocked kernels (host: build_cell_lists).  A tile's block is (L + 1) rows of kBSlices words,
+// slice-interleaved: rows 1..L are the slice's entries
+//     minus << 31 | new_node << 30 | slot << 16 | 8 * index into the tile buffer (arcs, then run sums)
+// sorted by node and cut into slices of EQUAL length: a node may straddle slices.  The walker adds the values of one node in
+// a register and touches shared memory once per node: an entry that opens a new node names the SLOT that takes the finished
+// sum of the node before it -- that node's accumulator, or the slice's scratch slot (PL + kBAccPad + slice) when it was the
+// slice's first node and earlier slices hold entries of the same node; any other entry names the dummy slot (PL).  The
+// slice's FIRST entry has nothing to flush and names its node instead (for the depth phases).  Row 0 = depth | slot of the
+// slice's last node << 8.  depth = position in the chain of slices that share the slice's first node: the scratch share is
+// added to the node's accumulator `depth` barrier phases after the walk, so the order in which the shares of a node are added
+// is fixed and no two threads ever update one accumulator in the same phase.
 // Padding (only behind the last entry of a tile) is a harmless entry instead of a branch: it adds the tile's ZERO slot
-// (index T + kMaxPieces - 1, written once; at most kMaxPieces - 1 pieces per tile) into the DUMMY accumulator (node PL).
+// (index T + kMaxPieces - 1, written once; at most kMaxPieces - 1 run sums per tile) to the running sum and names the dummy.
 constexpr uint32_t kBEntMinus = 0x80000000u, kBEntNew = 0x40000000u, kBEntNodeShift = 16, kBEntNodeMask = 0x3fffu, kBEntOffMask = 0xffffu;
-constexpr uint32_t kBMaxLocalNodes = kBEntNodeMask;  // PT + PH + dummy must fit the 14-bit node field
+constexpr uint32_t kBMaxLocalNodes = kBEntNodeMask;  // accumulators + dummy + scratch slots must fit the 14-bit slot field
 constexpr uint32_t kBAccPad = 2;  // accumulator slots behind the PL real ones (dummy + alignment)
 constexpr int kBPre = 8;          // list entries per fold thread requested together
+constexpr int kBFlush = 4;        // the short form of the last batch of a slice
 __host__ __device__ inline uint32_t block_pad_entry(uint32_t PL, uint32_t T) {
-  return kBEntNew | (PL << kBEntNodeShift) | ((T + kMaxPieces - 1) * 8u);
+  return (PL << kBEntNodeShift) | ((T + kMaxPieces - 1) * 8u);
 }
 __host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4 + 16; }  // + the stage's run descriptors
 // pass 1 never needs node values and accumulators at the same time (they alias), pass 2 needs both
-constexpr uint32_t kBMbarBytes = (kBComputeWarps * kBMaxRing + kBMaxList) * 8;
-__host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, uint32_t lblk, uint32_t nl, bool pass2, bool with_v) {
+constexpr uint32_t kBMbarBytes = (kWarps * kBMaxRing + kBMaxList) * 8;
+__host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, uint32_t lblk, uint32_t nl, uint32_t ntb, bool pass2, bool with_v, uint32_t ntile) {
   const size_t slot = pass2 ? block_slot_bytes(4, with_v ? 2 : 1) : block_slot_bytes(2, 0);
-  return ((pass2 ? 2 : 1) * ((size_t)PL + kBAccPad) + 2 * ((size_t)T + kMaxPieces)) * sizeof(double) + (size_t)kBComputeWarps * ring * slot +
-         (size_t)nl * lblk + kBMbarBytes + kFoldThreads * 8 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
+  return ((pass2 ? 2 : 1) * ((size_t)PL + kBAccPad) + ntb * ((size_t)T + kMaxPieces)) * sizeof(double) +
+         (size_t)(pass2 ? kBComputeWarps2 : kBComputeWarps1) * ring * slot +
+         (size_t)nl * lblk + kBMbarBytes + kFoldThreads * 8 + (size_t)ntile * 16 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
 }
-__device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, uint32_t lblk, uint32_t nl, bool pass2) {
+__device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, uint32_t lblk, uint32_t nl, uint32_t ntb, uint32_t ntile, bool pass2) {
   // bulk copies need 16-byte aligned shared-memory addresses: PL and T + kMaxPieces are even (host), the base is rounded up
   const uint32_t b = ((uint32_t)__cvta_generic_to_shared(base) + 15u) & ~15u;
   BlockSmem s;
   s.node.a = b;
   s.acc.a = pass2 ? b + (PL + kBAccPad) * 8u : b;
-  s.wt.a = s.acc.a + (PL + kBAccPad) * 8u;
+  s.scr = s.acc.a + (PL + kBAccPad) * 8u;  // list slots PL + kBAccPad + slice
+  s.wt.a = s.scr + kBSlices * 8u;
   s.wt_stride = (T + kMaxPieces) * 8u;
-  s.mbar = s.wt.a + 2u * s.wt_stride;
-  s.scr = s.mbar + kBMbarBytes;
-  s.lst = s.scr + kFoldThreads * 8u;
+  s.mbar = s.wt.a + ntb * s.wt_stride;
+  s.hdr = s.mbar + kBMbarBytes;
+  s.lst = s.hdr + ntile * 16u;
   s.ring = s.lst + nl * lblk;
   return s;
 }
@@ -276,61 +293,114 @@ struct BlockTileHdr {
   uint32_t e0, L, D;  // first word of the tile's block, entries per thread, deepest chain
   uint32_t q0, q1;    // the tile's pieces
 };
-__device__ __forceinline__ BlockTileHdr block_tile_hdr(const TileOp& to, uint32_t tile_id) {
-  const TileHdr h = tile_hdr(to, tile_id);
-  return BlockTileHdr{h.e0, h.L & 0xffffffu, h.L >> 24, h.q0, h.q1};
+__device__ __forceinline__ BlockTileHdr block_tile_hdr(const BlockSmem& s, uint32_t t) {  // tile t of this CTA's cell
+  uint32_t e0, L, q0, q1;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(L), "=r"(q0), "=r"(q1) : "r"(s.hdr + t * 16u));
+  return BlockTileHdr{e0, L & 0xffffffu, L >> 24, q0, q1};
 }
 // Adds the node sums of the tile held in buffer `wt` (arc values + run sums) into s.acc; `lst` is the shared-memory copy of
 // the tile's list block (bulk-copied ahead: a global load per batch of entries made the fold latency-bound -- 2.2 cycles
-// per arc with nothing else running, against 1.2 available in phase B of pass 1).
-__device__ __forceinline__ void block_fold_tile(const TileOp& to, const BlockSmem& s, uint32_t wt, uint32_t lst, const BlockTileHdr& h,
-                                                uint32_t dummy) {
-  (void)to;
-  const int ftid = threadIdx.x - kStreamThreads;
-  // Walk of my slice: straight-line code per entry (value load, sign, add; a node change is a predicated read-modify-write of
-  // the previous node's accumulator).  The share of my first node goes to my scratch word instead when earlier threads hold
-  // entries of the same node (depth > 0) and is added chain position by chain position afterwards.
-  const uint32_t mine = lst + (uint32_t)ftid * 4u;  // row q of my slice at mine + (q + 1) * 4 * kFoldThreads
-  const uint32_t depth = lds32<0>(mine);
-  const uint32_t my_scr = s.scr + (uint32_t)ftid * 8u;
-  if (depth) asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_scr), "d"(0.0));
-  uint32_t tgt = s.acc.a + dummy * 8u;       // accumulator of the node being added
-  uint32_t first_tgt = depth ? my_scr : 0u;  // non-zero until my first node has taken it
-  double sum = 0.0;
-  auto entry = [&](uint32_t ent, double x) __attribute__((always_inline)) {
-    const double val = __hiloint2double(__double2hiint(x) ^ (int)(ent & kBEntMinus), __double2loint(x));
-    if (ent & kBEntNew) {  // the previous node of this slice is complete
-      asm volatile("st.shared.f64 [%0], %1;" ::"r"(tgt), "d"(__dadd_rn(lds64_at(tgt), sum)));
-      const uint32_t own = s.acc.a + ((ent >> kBEntNodeShift) & kBEntNodeMask) * 8u;
-      tgt = first_tgt ? first_tgt : own;
-      first_tgt = 0u;
-      sum = 0.0;
-    }
-    sum = __dadd_rn(sum, val);
+// per arc with nothing else running, against 1.2 available in phase B of pass 1).  NFT fold threads walk the kBSlices slices
+// of the tile, thread f the slices f, f + NFT, ...
+// Walk of a slice: straight-line code per entry (value load, sign, add; a node change is a predicated read-modify-write of
+// the previous node's accumulator).  The share of the slice's first node goes to the slice's scratch word instead when
+// earlier slices hold entries of the same node (depth > 0) and is added chain position by chain position afterwards.
+template <int NFT>
+__device__ __forceinline__ void block_fold_tile(const BlockSmem& s, uint32_t wt, uint32_t lst, const BlockTileHdr& h, uint32_t dummy,
+                                                uint32_t pad, int ftid) {
+  constexpr int kPer = kBSlices / NFT;  // slices per thread, walked side by side (independent chains: twice the work in flight)
+  uint32_t depth[kPer], fin[kPer], row[kPer];
+  double sum[kPer];
+  auto slot_addr = [&](uint32_t word, int shift) __attribute__((always_inline)) {  // 14-bit slot field at bit `shift` (>= 3) -> address
+    return s.acc.a + ((word >> (shift - 3)) & (kBEntNodeMask << 3));
   };
-  uint32_t row = mine + 4u * kFoldThreads;
-  uint32_t q0 = 0;
-  for (; q0 + kBPre <= h.L; q0 += kBPre, row += kBPre * 4u * kFoldThreads) {  // whole batches: no bounds checks
-    uint32_t ent[kBPre];
-    double x[kBPre];
 #pragma unroll
-    for (int q = 0; q < kBPre; ++q) ent[q] = lds32_at(row + q * (4u * kFoldThreads));
-#pragma unroll
-    for (int q = 0; q < kBPre; ++q) x[q] = lds64_at(wt + (ent[q] & kBEntOffMask));  // the batch's tile values: independent loads
-#pragma unroll
-    for (int q = 0; q < kBPre; ++q) entry(ent[q], x[q]);
+  for (int j = 0; j < kPer; ++j) {
+    const uint32_t slice = (uint32_t)ftid + j * NFT;
+    const uint32_t mine = lst + slice * 4u;  // row q of the slice at mine + (q + 1) * 4 * kBSlices
+    const uint32_t r0 = lds32<0>(mine);
+    depth[j] = r0 & 0xffu;
+    fin[j] = slot_addr(r0, 8);
+    if (depth[j]) asm volatile("st.shared.f64 [%0], %1;" ::"r"(s.scr + slice * 8u), "d"(0.0));
+    sum[j] = 0.0;
+    row[j] = mine + 4u * kBSlices;
   }
-  for (; q0 < h.L; ++q0, row += 4u * kFoldThreads) {  // the rest, one by one (L is the same for every thread)
-    const uint32_t ent = lds32_at(row);
-    entry(ent, lds64_at(wt + (ent & kBEntOffMask)));
+  // NB entries of every slice of this thread: the entry words, then the tile values they name (independent loads), then the
+  // adds.  An entry that opens a new node first adds the finished sum to the slot it names (a slot is named by one entry of
+  // one slice per tile: no two threads update one slot in the same phase).  A branch-free form -- every entry one
+  // read-modify-write, the dummy slot when no node ends, the writes of four entries issued together -- walks faster alone
+  // but loads the shared-memory pipe the compute warps also need: pass 2 at 20M arcs 210 us per step against 203.5.
+  // FIRST: the slice's first entry names its node, not a slot (there is nothing to flush yet).  GUARD: only the first `rem`
+  // rows exist, the others are taken as padding entries (zero into the running sum).
+  auto batch = [&](auto nb_tag, auto guard_tag, auto first_tag, uint32_t rem) __attribute__((always_inline)) {
+    constexpr int NB = decltype(nb_tag)::value;
+    constexpr bool GUARD = decltype(guard_tag)::value, FIRST = decltype(first_tag)::value;
+    uint32_t ent[kPer][NB];
+    double x[kPer][NB];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        ent[j][q] = pad;
+        if (!GUARD || (uint32_t)q < rem) ent[j][q] = lds32_at(row[j] + q * (4u * kBSlices));
+      }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) x[j][q] = lds64_at(wt + (ent[j][q] & kBEntOffMask));  // the batch's tile values: independent loads
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const uint32_t e = ent[j][q];
+        const double xv = x[j][q];
+        const double val = __hiloint2double(__double2hiint(xv) ^ (int)(e & kBEntMinus), __double2loint(xv));
+        if (e & kBEntNew) {  // the node before is complete: one read-modify-write of the slot the entry names
+          if (!(FIRST && q == 0)) {
+            const uint32_t a = slot_addr(e, kBEntNodeShift);
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(__dadd_rn(lds64_at(a), sum[j])));
+          }
+          sum[j] = val;
+        } else {
+          sum[j] = __dadd_rn(sum[j], val);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) row[j] += NB * 4u * kBSlices;
+  };
+  using std::integral_constant;
+  using T8 = integral_constant<int, kBPre>;
+  using T4 = integral_constant<int, kBFlush>;
+  using Yes = integral_constant<bool, true>;
+  using No = integral_constant<bool, false>;
+  // L is the same for every slice; the first batch is peeled for the first-entry rule
+  auto tail = [&](auto first_tag, uint32_t rem) __attribute__((always_inline)) {
+    if (rem > (uint32_t)kBFlush)
+      batch(T8{}, Yes{}, first_tag, rem);
+    else if (rem > 0u)
+      batch(T4{}, Yes{}, first_tag, rem);
+  };
+  if (h.L >= (uint32_t)kBPre) {
+    batch(T8{}, No{}, Yes{}, 0u);
+    uint32_t q0 = kBPre;
+    for (; q0 + kBPre <= h.L; q0 += kBPre) batch(T8{}, No{}, No{}, 0u);
+    tail(No{}, h.L - q0);
+  } else {
+    tail(Yes{}, h.L);
   }
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(tgt), "d"(__dadd_rn(lds64_at(tgt), sum)));
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) asm volatile("st.shared.f64 [%0], %1;" ::"r"(fin[j]), "d"(__dadd_rn(lds64_at(fin[j]), sum[j])));
   if (h.D) {
-    const uint32_t e1 = h.L ? lds32_at(mine + 4u * kFoldThreads) : 0u;  // my first entry names the node my scratch word belongs to
-    const uint32_t dn = s.acc.a + ((e1 >> kBEntNodeShift) & kBEntNodeMask) * 8u;
     for (uint32_t d = 1; d <= h.D; ++d) {  // shares of straddling nodes, chain position by chain position
-      bar_sync_n(kBarFold, kFoldThreads);
-      if (depth == d) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dn), "d"(__dadd_rn(lds64_at(dn), lds64_at(my_scr))));
+      bar_sync_n(kBarFold, NFT);
+#pragma unroll
+      for (int j = 0; j < kPer; ++j)
+        if (depth[j] == d) {
+          const uint32_t slice = (uint32_t)ftid + j * NFT;
+          const uint32_t e1 = lds32_at(lst + slice * 4u + 4u * kBSlices);  // the slice's first entry names the node
+          const uint32_t dn = s.acc.a + ((e1 >> kBEntNodeShift) & kBEntNodeMask) * 8u;
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(dn), "d"(__dadd_rn(lds64_at(dn), lds64_at(s.scr + slice * 8u))));
+        }
     }
   }
 }
@@ -349,23 +419,25 @@ struct RingState {
   uint32_t slot, phase;  // compute warps: ring slot and mbarrier phase of the next stage
   uint32_t lphase;       // fold warps: bit b = phase of list buffer b's mbarrier
 };
-template <int N8, int N4, class CONSUME>
+template <int NCW, int N8, int N4, class CONSUME>
 __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
                                            const double* const (&src8)[N8], const uint32_t* const (&src4)[N4 ? N4 : 1],
                                            CONSUME consume, RingState& rs, const Trace* tr = nullptr, int tr_step = -1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t SPT = bo.tl.T / kBStage;  // stages per tile (a multiple of 8)
   const bool timed = tr != nullptr && tr->buf != nullptr && tr_step >= 0 && tr_step < tr->max_steps;
-  long long c_a = 0, c_b = 0, c_tot = 0, t_x = 0;  // diagnostics: cycles waiting for data / for the other role, total
+  long long c_a = 0, c_b = 0, c_l = 0, c_f = 0, c_tot = 0, t_x = 0;  // diagnostics: cycles waiting for data / for the other role, total
   if (timed) c_tot = -clock64();
-  if (warp < kBComputeWarps) {
-    const uint32_t nk = c.nst > (uint32_t)warp ? (c.nst - warp + kBComputeWarps - 1) / kBComputeWarps : 0;  // my stages
+  constexpr int NFT = kBlock - 32 * NCW;  // fold threads
+  static_assert(kBSlices % NFT == 0, "every fold thread walks the same number of slices");
+  if (warp < NCW) {
+    const uint32_t nk = c.nst > (uint32_t)warp ? (c.nst - warp + NCW - 1) / NCW : 0;  // my stages: g = warp, warp + NCW, ...
     const uint32_t ring0 = s.ring + (uint32_t)warp * RING * slot_bytes, bar0 = s.mbar + (uint32_t)warp * kBMaxRing * 8u;
     constexpr uint32_t kTx = N8 * kBStage * 8 + N4 * kBStage * 4 + 16;
     constexpr uint32_t kDescOff = N8 * kBStage * 8 + N4 * kBStage * 4;  // the stage's run descriptors sit behind the arrays
     auto issue = [&](uint32_t k, uint32_t sl) __attribute__((always_inline)) {  // lane 0 only: stage k of this warp into slot sl
       const uint32_t bar = bar0 + sl * 8u, dst = ring0 + sl * slot_bytes;
-      const size_t pos = (size_t)c.c0 + ((size_t)k * kBComputeWarps + warp) * kBStage;
+      const size_t pos = (size_t)c.c0 + ((size_t)k * NCW + warp) * kBStage;
       mbar_expect_tx(bar, kTx);
 #pragma unroll
       for (int a = 0; a < N8; ++a) bulk_g2s(dst + a * (kBStage * 8), src8[a] + pos, kBStage * 8, bar);
@@ -380,20 +452,26 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
         sl = sl + 1 == RING ? 0 : sl + 1;
       }
     }
-    uint32_t k = 0;
+    uint32_t k = 0, tb_i = 0;  // tb_i = t % ntb: the tile buffer of tile t
+    const uint32_t ntb = bo.ntb;
     for (uint32_t t = 0; t < c.ntiles; ++t) {
       if (timed) t_x = clock64();
-      if (t >= 2) bar_sync_n(kBarEmpty + (t & 1u), kBlock);  // the fold of tile t - 2 has left this buffer
+      if (t >= ntb) bar_sync_n(kBBarEmpty + tb_i, kBlock);  // the fold of tile t - ntb has left this buffer
       if (timed) c_b += clock64() - t_x;
-      const uint32_t wt0 = s.wt.a + (t & 1u) * s.wt_stride;
-      uint32_t g = t * SPT + warp;
-      for (uint32_t i = 0; i < SPT / kBComputeWarps && g < c.nst; ++i, g += kBComputeWarps) {
+      const uint32_t wt0 = s.wt.a + tb_i * s.wt_stride;
+      // my stages inside tile t: g = warp (mod NCW) -- the round robin runs across tile boundaries, every warp gets the same
+      // number of stages (+- 1) whatever the tile size
+      const uint32_t tb = t * SPT, te = min(tb + SPT, c.nst);
+      uint32_t g = tb + ((uint32_t)warp + NCW - tb % NCW) % NCW;
+      for (; g < te; g += NCW) {
         if (timed) t_x = clock64();
         mbar_wait(bar0 + rs.slot * 8u, rs.phase);
         if (timed) c_a += clock64() - t_x;
+        if (timed) t_x = clock64();
         if (!(bo.dbg & 2u))
           consume(c.c0 + g * kBStage, ring0 + rs.slot * slot_bytes, wt0 + (g - t * SPT) * (kBStage * 8u), wt0, ring0 + rs.slot * slot_bytes + kDescOff, lane);
         __syncwarp();  // every lane has read its slot words
+        if (timed) c_f += clock64() - t_x;
         if (lane == 0 && k + RING < nk) issue(k + RING, rs.slot);
         ++k;
         if (++rs.slot == RING) {
@@ -401,61 +479,61 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
           rs.phase ^= 1u;
         }
       }
-      bar_arrive_n(kBarFull + (t & 1u), kBlock);
+      bar_arrive_n(kBBarFull + tb_i, kBlock);
+      tb_i = tb_i + 1 == ntb ? 0 : tb_i + 1;
     }
     // drain: every arrival of the fold warps is matched by a wait, so that the barriers are clean for the next sweep
-    for (uint32_t u = c.ntiles > 2 ? c.ntiles - 2 : 0; u < c.ntiles; ++u) bar_sync_n(kBarEmpty + (u & 1u), kBlock);
+    for (uint32_t u = c.ntiles > ntb ? c.ntiles - ntb : 0; u < c.ntiles; ++u) bar_sync_n(kBBarEmpty + u % ntb, kBlock);
     fence_proxy_async();  // the vector just written is bulk-copied by the next sweep (after the grid barrier in between)
     if (timed && threadIdx.x == 0) {
       unsigned long long* q = tr->buf + ((size_t)blockIdx.x * tr->max_steps + tr_step) * kTraceMarks;
       q[16] = (unsigned long long)c_a;                 // compute warp 0: waiting for bulk copies
       q[17] = (unsigned long long)c_b;                 // ... for the fold to release a tile buffer
       q[18] = (unsigned long long)(c_tot + clock64()); // ... whole sweep
+      q[23] = (unsigned long long)c_f;                 // ... consuming stages
     }
   } else {
     // Fold warps.  The list block of tile t is bulk-copied into list buffer t % nl by fold thread 0: tiles 0 .. nl - 1 at the
     // start of the sweep, tile t - 1 + nl as soon as every fold thread has left tile t - 1 (= has passed the full-barrier of
     // tile t).  Short sweeps (small cells) thus have their whole list in flight from the start.
-    const uint32_t tile0 = blockIdx.x * bo.tl.ntile, dummy = bo.PT + bo.PH, nl = bo.nl;
-    const uint32_t lbar = s.mbar + kBComputeWarps * kBMaxRing * 8u;
-    const bool issuer = threadIdx.x == kStreamThreads;
+    const uint32_t dummy = bo.PT + bo.PH, nl = bo.nl;
+    const uint32_t lbar = s.mbar + kWarps * kBMaxRing * 8u;
+    const int ftid = (int)threadIdx.x - 32 * NCW;
+    const bool issuer = ftid == 0;
     auto fetch = [&](const BlockTileHdr& h, uint32_t b) __attribute__((always_inline)) {  // issuer only
-      const uint32_t bytes = (h.L + 1u) * (4u * kFoldThreads);
+      const uint32_t bytes = (h.L + 1u) * (4u * kBSlices);
       mbar_expect_tx(lbar + b * 8u, bytes);
       bulk_g2s(s.lst + b * bo.lblk, bo.tl.lent + h.e0, bytes, lbar + b * 8u);
     };
-    BlockTileHdr h0 = block_tile_hdr(bo.tl, tile0), h1 = h0, hf = h0;
-    if (c.ntiles > 1) h1 = block_tile_hdr(bo.tl, tile0 + 1);
-    if (c.ntiles) {
-      if (issuer) {
-        for (uint32_t u = 0; u < nl && u < c.ntiles; ++u) fetch(block_tile_hdr(bo.tl, tile0 + u), u);
-        if (nl < c.ntiles) hf = block_tile_hdr(bo.tl, tile0 + nl);  // the next block to fetch
-      }
-    }
-    uint32_t b = 0;  // list buffer of tile t
+    if (c.ntiles && issuer)
+      for (uint32_t u = 0; u < nl && u < c.ntiles; ++u) fetch(block_tile_hdr(s, u), u);
+    uint32_t b = 0, tb_i = 0;  // list buffer / tile buffer of tile t
+    const uint32_t ntb = bo.ntb;
     for (uint32_t t = 0; t < c.ntiles; ++t) {
-      BlockTileHdr h2 = h1;
-      if (t + 2 < c.ntiles) h2 = block_tile_hdr(bo.tl, tile0 + t + 2);
+      const BlockTileHdr h0 = block_tile_hdr(s, t);
       if (timed) t_x = clock64();
-      bar_sync_n(kBarFull + (t & 1u), kBlock);
+      bar_sync_n(kBBarFull + tb_i, kBlock);
       if (timed) c_a += clock64() - t_x;
-      if (issuer && t >= 1 && t - 1 + nl < c.ntiles) {  // every fold thread has left tile t - 1: its buffer is free
-        fetch(hf, b == 0 ? nl - 1 : b - 1);
-        if (t + nl < c.ntiles) hf = block_tile_hdr(bo.tl, tile0 + t + nl);
-      }
+      if (issuer && t >= 1 && t - 1 + nl < c.ntiles)  // every fold thread has left tile t - 1: its buffer is free
+        fetch(block_tile_hdr(s, t - 1 + nl), b == 0 ? nl - 1 : b - 1);
+      if (timed) t_x = clock64();
       mbar_wait(lbar + b * 8u, (rs.lphase >> b) & 1u);
+      if (timed) c_l += clock64() - t_x;
       rs.lphase ^= 1u << b;
+      if (timed) t_x = clock64();
       if (!(bo.dbg & 1u))
-        block_fold_tile(bo.tl, s, s.wt.a + (t & 1u) * s.wt_stride, s.lst + b * bo.lblk, h0, dummy);
-      bar_arrive_n(kBarEmpty + (t & 1u), kBlock);
-      h0 = h1;
-      h1 = h2;
+        block_fold_tile<NFT>(s, s.wt.a + tb_i * s.wt_stride, s.lst + b * bo.lblk, h0, dummy, block_pad_entry(dummy, bo.tl.T), ftid);
+      if (timed) c_f += clock64() - t_x;
+      bar_arrive_n(kBBarEmpty + tb_i, kBlock);
+      tb_i = tb_i + 1 == ntb ? 0 : tb_i + 1;
       b = b + 1 == nl ? 0 : b + 1;
     }
-    if (timed && threadIdx.x == kStreamThreads) {
+    if (timed && ftid == 0) {
       unsigned long long* q = tr->buf + ((size_t)blockIdx.x * tr->max_steps + tr_step) * kTraceMarks;
       q[19] = (unsigned long long)c_a;                 // fold warp 0: waiting for a full tile
       q[20] = (unsigned long long)(c_tot + clock64()); // ... whole sweep
+      q[21] = (unsigned long long)c_l;                 // ... waiting for list blocks
+      q[22] = (unsigned long long)c_f;                 // ... folding
     }
   }
   __syncthreads();
@@ -463,20 +541,25 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
 
 // mbarriers of the rings, and the zero slot of both tile buffers that padding list entries read
 __device__ __forceinline__ void init_block_smem(const BlockOp& bo, const BlockSmem& s) {
-  if (threadIdx.x < kBComputeWarps * kBMaxRing + kBMaxList) mbar_init(s.mbar + threadIdx.x * 8u, 1);
-  if (threadIdx.x < 2) sm_st(SmArr{s.wt.a + threadIdx.x * s.wt_stride}, bo.tl.T + kMaxPieces - 1, 0.0);
+  if (threadIdx.x < kWarps * kBMaxRing + kBMaxList) mbar_init(s.mbar + threadIdx.x * 8u, 1);
+  for (uint32_t t = threadIdx.x; t < bo.tl.ntile; t += kBlock) {
+    const TileHdr h = tile_hdr(bo.tl, blockIdx.x * bo.tl.ntile + t);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s.hdr + t * 16u), "r"(h.e0), "r"(h.L), "r"(h.q0), "r"(h.q1) : "memory");
+  }
+  if (threadIdx.x < bo.ntb) sm_st(SmArr{s.wt.a + threadIdx.x * s.wt_stride}, bo.tl.T + kMaxPieces - 1, 0.0);
   fence_mbar_init();
   __syncthreads();
 }
 
 // node partial sums of an arbitrary cell-order arc vector X over the CTA's cell (init: the un-normalised b)
+template <int NCW>
 __device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
                                               const double* X, RingState& rs) {
   zero_block_acc(bo, s);
   __syncthreads();
   const double* const src8[1] = {X};
   const uint32_t* const src4[1] = {nullptr};
-  fold_sweep<1, 0>(
+  fold_sweep<NCW, 1, 0>(
       bo, s, c, RING, slot_bytes, src8, src4,
       [&](uint32_t, uint32_t slot, uint32_t wt, uint32_t wt_tile, uint32_t desc, int lane) __attribute__((always_inline)) {
         const uint32_t sl = slot + lane * 8u, w = wt + lane * 8u;
@@ -498,7 +581,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
   extern __shared__ double smem[];
   __shared__ CtaShared sh;
   const uint32_t PL = bo.PT + bo.PH, p = op.p, m = bo.m, M = bo.Mpad;
-  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, bo.lblk, bo.nl, false);
+  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, bo.lblk, bo.nl, bo.ntb, bo.tl.ntile, false);
   const BlockCtx c = block_ctx(bo, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t RING = bo.ring1;
@@ -536,7 +619,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
     }
     fence_proxy_async();
     __syncthreads();  // the cell's share of W_cur is written (and fenced towards the async proxy) before it is bulk-copied
-    block_sums_of(bo, s, c, RING, slot_bytes, Wc, rs);
+    block_sums_of<kBComputeWarps1>(bo, s, c, RING, slot_bytes, Wc, rs);
     publish_block_partials(bo, s, c, 0);
     bnorm = sqrt(tile_sync<true>(acc, to, a.gs, epoch, sh));
     if (bnorm <= a.tol) status = ST_ZERO_B;
@@ -603,7 +686,10 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
       fence_proxy_async();  // w~ is bulk-copied by phase B
       trace_mark(gs.trace, j, 3);
       gs.trace_base = 4;
-      const double alpha = tile_sync<true, false>(acc, to, gs, epoch, sh);
+      // all-reduce only: what phase B reads of phase A's output (w~ of the own cell and of the owned node rows) was written by
+      // this CTA, ordered by the CTA barriers inside the call (and the proxy fence above for the bulk copies) -- no release /
+      // acquire fence at GPU scope, which costs 1.6 us each with a sweep's stores in flight
+      const double alpha = to.fab.world > 1 ? fabric_sync<true, false>(acc, to, epoch, sh) : grid_sync<true, false>(acc, gs, epoch, sh);
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
       acc = 0.0;
@@ -620,7 +706,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
       {
         const double* const src8[2] = {Wn, Wc};
         const uint32_t* const src4[1] = {nullptr};
-        fold_sweep<2, 0>(
+        fold_sweep<kBComputeWarps1, 2, 0>(
             bo, s, c, RING, slot_bytes, src8, src4,
             [&](uint32_t pos, uint32_t slot, uint32_t wt, uint32_t wt_tile, uint32_t desc, int ln) __attribute__((always_inline)) {
               const uint32_t sl = slot + ln * 8u;
@@ -689,7 +775,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
   extern __shared__ double smem[];
   __shared__ CtaShared sh;
   const uint32_t PL = bo.PT + bo.PH, p = op.p, m = bo.m, M = bo.Mpad;
-  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, bo.lblk, bo.nl, true);
+  const BlockSmem s = carve_blocks(smem, PL, bo.tl.T, bo.lblk, bo.nl, bo.ntb, bo.tl.ntile, true);
   const BlockCtx c = block_ctx(bo, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t RING = WITH_V ? bo.ring2v : bo.ring2;
@@ -739,7 +825,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
     }
     fence_proxy_async();
     __syncthreads();
-    block_sums_of(bo, s, c, RING, slot_bytes, Braw, rs);
+    block_sums_of<kBComputeWarps2>(bo, s, c, RING, slot_bytes, Braw, rs);
     publish_block_partials(bo, s, c, 0);
     tile_sync<false>(0.0, to, a.gs, epoch, sh);
   }
@@ -833,9 +919,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
         }
       };
       if (WITH_V)
-        fold_sweep<4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, rs, &gs.trace, j);
+        fold_sweep<kBComputeWarps2, 4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, rs, &gs.trace, j);
       else
-        fold_sweep<4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, rs, &gs.trace, j);
+        fold_sweep<kBComputeWarps2, 4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, rs, &gs.trace, j);
     }
     trace_mark(gs.trace, j, 2);
     publish_block_partials(bo, s, c, (j + 1) & 1);

@@ -28,7 +28,7 @@ namespace tpl {
 struct HostBlocks {
   bool ok = false;
   uint32_t GR = 0, GC = 0, PT = 0, PH = 0, Mpad = 0, T = 0, ntile = 0;
-  uint32_t ring1 = 0, ring2 = 0, ring2v = 0, lblk = 0, nl = 2;
+  uint32_t ring1 = 0, ring2 = 0, ring2v = 0, lblk = 0, nl = 2, ntb = 2;
   std::vector<uint32_t> cell_off, tbs, hbs, tbn, hbn, th, gidx;
   std::vector<double> d;
   std::vector<uint4> thdr, pdesc;  // pdesc: per 128-arc stage up to four same-tail runs (start | (len - 1) << 8 | tile slot << 16)
@@ -56,9 +56,9 @@ inline std::vector<uint32_t> weight_blocks(const std::vector<uint64_t>& weight, 
 
 // Ring depths for which the kernels fit in `smem_limit` bytes with tiles of T arcs and list buffers of lblk bytes; `need` = the
 // least number of ring slots pass 2 must get.
-inline bool blocks_fit(uint32_t PL, size_t smem_limit, uint32_t T, uint32_t lblk, int need, uint32_t& ring1, uint32_t& ring2, uint32_t& ring2v) {
+inline bool blocks_fit(uint32_t PL, size_t smem_limit, uint32_t T, uint32_t lblk, uint32_t ntb, uint32_t ntile, int need, uint32_t& ring1, uint32_t& ring2, uint32_t& ring2v) {
   const size_t budget = smem_limit > 3072 ? smem_limit - 3072 : 0;  // static shared memory of the kernels + margin
-  auto fits = [&](int ring, bool pass2, bool v) { return block_smem_bytes(PL, T, ring, lblk, 2, pass2, v) <= budget; };
+  auto fits = [&](int ring, bool pass2, bool v) { return block_smem_bytes(PL, T, ring, lblk, 2, ntb, pass2, v, ntile) <= budget; };
   if (!fits(need, true, false) || !fits(2, true, true) || !fits(2, false, false)) return false;
   ring2 = fits(4, true, false) ? 4 : fits(3, true, false) ? 3 : 2;
   ring2v = fits(3, true, true) ? 3 : 2;
@@ -149,10 +149,15 @@ inline bool build_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const 
         depth = (w.s_node[s0 - L] == w.s_node[s0 - 1]) ? prev_depth + 1 : 1;  // thread i-1 holds only that node: one deeper
       prev_depth = depth;
       maxdepth = std::max(maxdepth, depth);
-      lent[base + i] = depth;
+      // the accumulator slot that takes the sum of node `u` of this slice: the slice's scratch slot for the share of a node
+      // that earlier slices also hold, the node's own slot otherwise
+      const uint32_t scratch = PL + kBAccPad + i;
+      auto slot_of = [&](uint32_t u) { return depth && u == w.s_node[s0] ? scratch : u; };
+      lent[base + i] = depth | ((s0 < s1 ? slot_of(w.s_node[s1 - 1]) : PL) << 8);
       for (uint32_t e = s0; e < s1; ++e) {
         const bool first = e == s0 || w.s_node[e] != w.s_node[e - 1];
-        lent[base + (size_t)(e - s0 + 1) * B + i] = w.s_code[e] | (w.s_node[e] << kBEntNodeShift) | (first ? kBEntNew : 0u);
+        const uint32_t field = e == s0 ? w.s_node[e] : first ? slot_of(w.s_node[e - 1]) : PL;
+        lent[base + (size_t)(e - s0 + 1) * B + i] = w.s_code[e] | (field << kBEntNodeShift) | (first ? kBEntNew : 0u);
       }
     }
     if (maxdepth > 255) return false;
@@ -204,7 +209,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   for (uint32_t b = 0; b < h.GC; ++b) PH = std::max(PH, h.hbs[b + 1] - h.hbs[b]);
   PT = std::max(2u, (PT + 1u) & ~1u);  // even: 16-byte aligned shared-memory arrays
   PH = std::max(2u, (PH + 1u) & ~1u);
-  if (PT > 0x8000u || PH > 0x8000u || PT + PH + kBAccPad > kBMaxLocalNodes) return;  // 15-bit local ids, 14-bit list nodes
+  if (PT > 0x8000u || PH > 0x8000u || PT + PH + kBAccPad + kFoldThreads > kBMaxLocalNodes + 1) return;  // 15-bit local ids, 14-bit list slots
   h.PT = PT;
   h.PH = PH;
   std::vector<uint32_t> node_tb(p, 0), node_hb(p, 0);
@@ -264,12 +269,14 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   std::vector<std::vector<uint32_t>> lent(Gc), piece(Gc);
   const uint32_t padded_max = (uint32_t)((max_cell + kBStage - 1) / kBStage * kBStage);
   // at least ~8 tiles per cell, so that the fold of one tile overlaps the stream of the next also on small instances
-  const uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max / 8 + 1023) / 1024 * 1024));
+  uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max / 8 + 1023) / 1024 * 1024));
+  if (const char* e = std::getenv("TPL_BLOCK_T")) want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (uint32_t)std::atoi(e) / 1024 * 1024));  // tuning experiments
+  if (const char* e = std::getenv("TPL_BLOCK_NTB")) h.ntb = std::min<uint32_t>(kBMaxTileBufs, std::max<uint32_t>(2, (uint32_t)std::atoi(e)));  // tuning experiments
   bool done = false;
   for (int need = 3; need >= 2 && !done; --need)
     for (uint32_t T = want; T >= 1024 && !done; T -= 1024) {
       // cheap bound first: L >= entries / threads >= (arcs of a full tile) / threads
-      if (!blocks_fit(PT + PH, smem_limit, T, (std::min(T, padded_max) / kFoldThreads + 1) * 4u * kFoldThreads, need, h.ring1, h.ring2, h.ring2v))
+      if (!blocks_fit(PT + PH, smem_limit, T, (std::min(T, padded_max) / kFoldThreads + 1) * 4u * kFoldThreads, h.ntb, std::max<uint32_t>(1, (padded_max + T - 1) / T), need, h.ring1, h.ring2, h.ring2v))
         continue;
       h.T = T;
       h.ntile = std::max<uint32_t>(1, (padded_max + T - 1) / T);
@@ -306,7 +313,7 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
       }
       if (bad) return;
       h.lblk = (Lmax + 1) * 4u * kFoldThreads;
-      done = blocks_fit(PT + PH, smem_limit, T, h.lblk, need, h.ring1, h.ring2, h.ring2v);
+      done = blocks_fit(PT + PH, smem_limit, T, h.lblk, h.ntb, h.ntile, need, h.ring1, h.ring2, h.ring2v);
     }
   lap("tile lists");
   if (!done) return;
@@ -314,9 +321,9 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
     const size_t budget = smem_limit > 3072 ? smem_limit - 3072 : 0;
     h.nl = 2;
     while (h.nl < (uint32_t)kBMaxList && h.nl < h.ntile &&
-           block_smem_bytes(PT + PH, h.T, (int)h.ring2v, h.lblk, h.nl + 1, true, true) <= budget &&
-           block_smem_bytes(PT + PH, h.T, (int)h.ring2, h.lblk, h.nl + 1, true, false) <= budget &&
-           block_smem_bytes(PT + PH, h.T, (int)h.ring1, h.lblk, h.nl + 1, false, false) <= budget)
+           block_smem_bytes(PT + PH, h.T, (int)h.ring2v, h.lblk, h.nl + 1, h.ntb, true, true, h.ntile) <= budget &&
+           block_smem_bytes(PT + PH, h.T, (int)h.ring2, h.lblk, h.nl + 1, h.ntb, true, false, h.ntile) <= budget &&
+           block_smem_bytes(PT + PH, h.T, (int)h.ring1, h.lblk, h.nl + 1, h.ntb, false, false, h.ntile) <= budget)
       ++h.nl;
   }
   size_t nl = 0, np = 0;
@@ -373,7 +380,7 @@ inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const u
     uint32_t prev_node = 0, prev_depth = 0, maxdepth = 0;
     bool prev_single = false, any = false, ended = false;
     for (uint32_t i = 0; i < B; ++i) {
-      const uint32_t depth = lent[hd.x + i];
+      const uint32_t depth = lent[hd.x + i] & 0xffu, final_slot = lent[hd.x + i] >> 8;
       uint32_t first_node = 0, last_node = 0, cnt = 0;
       bool single = true;
       for (uint32_t q = 0; q < L; ++q) {
@@ -383,15 +390,31 @@ inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const u
           continue;
         }
         if (ended) return 4;
-        const uint32_t node = (e >> kBEntNodeShift) & kBEntNodeMask, idx = (e & kBEntOffMask) / 8u;
+        const uint32_t field = (e >> kBEntNodeShift) & kBEntNodeMask, idx = (e & kBEntOffMask) / 8u;
         if ((e & kBEntOffMask) % 8u) return 17;
+        // the node is implied by what the entry reads: a head (minus), a run sum, or a tail
+        uint32_t node;
+        if (e & kBEntMinus) {
+          if (idx >= na) return 9;
+          node = hl[t0 + idx];
+        } else if (idx >= T) {
+          if (idx - T >= runs.size()) return 10;
+          node = tl[t0 + runs[idx - T].first];
+        } else {
+          if (idx >= na) return 13;
+          node = tl[t0 + idx];
+        }
         if (node >= PL) return 5;
         const bool isnew = (e & kBEntNew) != 0;
+        const uint32_t scratch = PL + kBAccPad + i;
         if (cnt == 0) {
-          if (!isnew) return 6;
+          if (!isnew || field != node) return 6;  // the first entry names the slice's first node (used by the depth phases)
           first_node = node;
         } else {
           if (isnew != (node != last_node) || node < last_node) return 7;
+          // a node change flushes the finished node: into the scratch slot when it is the slice's shared first node
+          const uint32_t target = depth && last_node == first_node ? scratch : last_node;
+          if (field != (isnew ? target : PL)) return 18;
           if (node != last_node) single = false;
         }
         if (any && cnt == 0 && node < prev_node) return 8;  // sorted across slices
@@ -416,6 +439,7 @@ inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const u
       uint32_t want = 0;
       if (cnt && any && first_node == prev_node) want = prev_single ? prev_depth + 1 : 1;
       if (depth != want) return 14;
+      if (final_slot != (cnt == 0 ? PL : depth && last_node == first_node ? PL + kBAccPad + i : last_node)) return 19;
       maxdepth = std::max(maxdepth, depth);
       if (cnt) {
         prev_node = last_node;

@@ -812,7 +812,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       tpl::BlockOp& bo = op->blk;
       bo = tpl::BlockOp{};
       bo.GR = hb.GR; bo.GC = hb.GC; bo.PT = hb.PT; bo.PH = hb.PH; bo.Mpad = hb.Mpad; bo.m = (uint32_t)m;
-      bo.ring1 = hb.ring1; bo.ring2 = hb.ring2; bo.ring2v = hb.ring2v; bo.lblk = hb.lblk; bo.nl = hb.nl;
+      bo.ring1 = hb.ring1; bo.ring2 = hb.ring2; bo.ring2v = hb.ring2v; bo.lblk = hb.lblk; bo.nl = hb.nl; bo.ntb = hb.ntb;
       if (const char* e = std::getenv("TPL_BLOCK_DBG")) bo.dbg = (uint32_t)std::atoi(e);  // timing experiments (tpl_blocks.cuh)
       bo.tl.T = hb.T;
       bo.tl.ntile = hb.ntile;
@@ -832,9 +832,9 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       for (auto& bb : op->bbuf)
         if (!rc) rc = dev_alloc(op, &bb, (size_t)hb.Mpad + p);
       const uint32_t PL = hb.PT + hb.PH;
-      op->smem_blk1 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring1, hb.lblk, hb.nl, false, false);
-      op->smem_blk2 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2, hb.lblk, hb.nl, true, false);
-      op->smem_blk2v = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2v, hb.lblk, hb.nl, true, true);
+      op->smem_blk1 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring1, hb.lblk, hb.nl, hb.ntb, false, false, hb.ntile);
+      op->smem_blk2 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2, hb.lblk, hb.nl, hb.ntb, true, false, hb.ntile);
+      op->smem_blk2v = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2v, hb.lblk, hb.nl, hb.ntb, true, true, hb.ntile);
       op->blocked_ok = !rc;
       for (size_t q = 0; q + 1 < hb.cell_off.size(); ++q) op->blk_max_cell = std::max(op->blk_max_cell, hb.cell_off[q + 1] - hb.cell_off[q]);
       if (!rc) rc = setup_local_fabric(op, true);
@@ -1028,7 +1028,7 @@ int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   for (uint32_t e : hb.gidx) hsh = (hsh ^ e) * 1099511628211ull;
   stats[13] = hsh;
   stats[14] = (uint64_t)tpl::check_blocks(m, p, tail, head, d, d_len, hb);
-  stats[15] = tpl::block_smem_bytes(hb.PT + hb.PH, hb.T, (int)hb.ring2, hb.lblk, hb.nl, true, false);
+  stats[15] = tpl::block_smem_bytes(hb.PT + hb.PH, hb.T, (int)hb.ring2, hb.lblk, hb.nl, hb.ntb, true, false, hb.ntile);
   stats[8] |= (uint64_t)hb.nl << 24;
   return TPL_OK;
 }
