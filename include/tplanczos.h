@@ -172,6 +172,14 @@ int tpl_tiles_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* hea
  * padding, pieces, hash of the layout, check code (0 = consistent), shared-memory bytes (pass 2)}. */
 int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len, int ctas,
                     size_t smem_limit, int threads, uint64_t stats[16]);
+/* Diagnostics: the tables of a KKT handle as they sit in device memory, checked on the host.  Handles of 2^20 arcs and more
+ * build their node lists and their blocked layout ON THE DEVICE (TPL_HOST_BUILD=1 / TPL_DEVICE_BUILD=1 in the environment
+ * force the host / the device builder for any size); this call downloads them, runs the host checker of the blocked layout
+ * over them and compares the node lists with a host construction.
+ * stats = {built on the device, blocked layout present, check code of the blocked layout (0 = consistent), hash of the
+ * layout (the one tpl_blocks_plan reports for the host builder), list words, tile arcs, node-list words that differ,
+ * node-list words}. */
+int tpl_op_layout_check(tpl_op* op, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len, uint64_t stats[8]);
 /* Diagnostics (host only, no device needed): builds the 2-D cell partition the resident kernels would use on a grid
  * of `ctas` CTAs with `smem_limit` bytes of shared memory each and checks its tables on the host.
  * stats = {fits, tail blocks, head blocks, arc slots per cell, node lines, most entry rows, most node-sum groups,

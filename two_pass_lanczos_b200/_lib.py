@@ -58,6 +58,7 @@ SIGNATURES = {
     "tpl_tiles_plan": (C.c_int, [C.c_size_t, C.c_size_t, c_u32p, c_u32p, C.c_int, C.c_uint32, C.c_int, c_u64p]),
     "tpl_blocks_plan": (C.c_int, [C.c_size_t, C.c_size_t, c_u32p, c_u32p, c_dp, C.c_size_t, C.c_int, C.c_size_t, C.c_int, c_u64p]),
     "tpl_cells_plan": (C.c_int, [C.c_size_t, C.c_size_t, c_u32p, c_u32p, C.c_int, C.c_size_t, c_u64p]),
+    "tpl_op_layout_check": (C.c_int, [C.c_void_p, c_u32p, c_u32p, c_dp, C.c_size_t, c_u64p]),
     "tpl_op_trace_enable": (C.c_int, [C.c_void_p, C.c_size_t]),
     "tpl_op_trace_read": (C.c_int, [C.c_void_p, c_u64p, C.c_size_t, c_szp, c_szp, c_szp]),
     "tpl_pass_one": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_dp, c_dp, c_szp, c_dp]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtplanczos.so")
 SOURCES = ["tpl_engine.cu", "tpl_loader.cpp", "tpl_ftk.cpp"]
-HEADERS = ["tpl_kernels.cuh", "tpl_dense.cuh", "tpl_cells.cuh", "tpl_cells_host.h", "tpl_tiles.cuh", "tpl_tiles_host.h", "tpl_blocks.cuh", "tpl_blocks_host.h", "tpl_csr.cuh", "tpl_sharded.cuh", "tpl_internal.h", os.path.join("..", "..", "include", "tplanczos.h")]
+HEADERS = ["tpl_kernels.cuh", "tpl_dense.cuh", "tpl_cells.cuh", "tpl_cells_host.h", "tpl_tiles.cuh", "tpl_tiles_host.h", "tpl_blocks.cuh", "tpl_blocks_host.h", "tpl_build.cuh", "tpl_csr.cuh", "tpl_sharded.cuh", "tpl_internal.h", os.path.join("..", "..", "include", "tplanczos.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -18,6 +19,7 @@
 #include "tpl_internal.h"
 #include "tpl_blocks.cuh"
 #include "tpl_blocks_host.h"
+#include "tpl_build.cuh"
 #include "tpl_cells_host.h"
 #include "tpl_csr.cuh"
 #include "tpl_dense.cuh"
@@ -180,6 +182,8 @@ struct tpl_op {
   bool fab_connected = false;  // world > 1 and every peer's block is mapped: the persistent tiled kernels span all ranks
   unsigned fab_epoch = 0;      // barrier epoch the next fused pass starts from (never reset: peers write into our slots)
   size_t smem_tile1 = 0, smem_tile2 = 0;
+  size_t blk_lent_words = 0;   // words of the blocked tile lists (blk.tl.lent)
+  bool device_built = false;   // node lists and blocked layout were constructed on the device (tpl_build.cuh)
   bool blocked_ok = false;     // blocked streaming kernels (tpl_blocks.cuh): 2-D node-block partition, cell-order vectors
   tpl::BlockOp blk{};
   size_t smem_blk1 = 0, smem_blk2 = 0, smem_blk2v = 0;
@@ -241,6 +245,14 @@ int dev_upload(tpl_op* op, const T** out, const std::vector<T>& host) {
   if (!host.empty()) CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = p;
   return TPL_OK;
+}
+// a device buffer allocated elsewhere (tpl_build.cuh) becomes the handle's
+template <class T>
+void dev_adopt(tpl_op* op, T* p, size_t count) {
+  if (!p) return;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  op->allocs.emplace_back((void*)p, bytes);
+  op->device_bytes += bytes;
 }
 int dev_free(tpl_op* op, void* p) {
   if (!p) return TPL_OK;
@@ -313,7 +325,7 @@ void build_segments(HostLongRows& h, const std::vector<uint64_t>& row_ent, int G
   }
 }
 
-int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
+int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d, const uint32_t* ent_idx_dev = nullptr) {
   d.nlong = (uint32_t)h.row.size();
   d.max_segs = h.max_segs;
   d.max_ents = h.max_ents;
@@ -321,7 +333,11 @@ int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d) {
   if (int rc = dev_upload(op, &d.row, h.row)) return rc;
   if (int rc = dev_upload(op, &d.seg_ptr, h.seg_ptr)) return rc;
   if (int rc = dev_upload(op, &d.ent_ptr, h.ent_ptr)) return rc;
-  if (int rc = dev_upload(op, &d.ent_idx, h.ent_idx)) return rc;
+  if (ent_idx_dev) {
+    d.ent_idx = ent_idx_dev;  // built on the device (already adopted by the handle)
+  } else if (int rc = dev_upload(op, &d.ent_idx, h.ent_idx)) {
+    return rc;
+  }
   if (int rc = dev_upload(op, &d.cta_ptr, h.cta_ptr)) return rc;
   d.ent_val = nullptr;
   if (!h.ent_val.empty())
@@ -675,9 +691,25 @@ int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op*
   return TPL_OK;
 }
 
+namespace {
+constexpr size_t kDeviceBuildArcs = 1u << 20;  // from here on the tables are built on the device
+// TPL_BUILD_TIMING=1: wall-clock laps of operator construction on stderr
+struct BuildLaps {
+  bool on = std::getenv("TPL_BUILD_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "from_kkt %-36s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len,
                     int device, tpl_op** out) {
   tpl::clear_error();
+  BuildLaps laps;
   if (!out || (m && (!tail || !head)) || (d_len && !d)) return fail(TPL_ERR_PANIC, "null argument");
   if (d_len > m) return fail(TPL_ERR_PARAMETER_MISMATCH, "Parameter mismatch: `d` expects size %zu, but got %zu.", m, d_len);
   const size_t n = m + p;
@@ -686,25 +718,70 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   for (size_t j = 0; j < m; ++j)
     if (tail[j] >= p || head[j] >= p)
       return fail(TPL_ERR_SPARSE_CONSTRUCTION, "Internal error: Failed to construct the sparse matrix from triplets.");
+  laps.lap("validate");
   tpl_op* op = new tpl_op;
   int rc = open_device(op, device);
   if (rc) {
     delete op;
     return rc;
   }
+  laps.lap("open device");
   op->format = 2;
   op->n = (uint32_t)n;
+  // Large instances build their tables on the device (tpl_build.cuh); the host builders below construct the small ones and
+  // check the device's work (tpl_op_layout_check).  TPL_HOST_BUILD=1 / TPL_DEVICE_BUILD=1 force either way.
+  bool device_build = m >= kDeviceBuildArcs;
+  if (std::getenv("TPL_HOST_BUILD")) device_build = false;
+  if (std::getenv("TPL_DEVICE_BUILD")) device_build = true;
+  op->device_built = device_build;
+  op->inc.m = (uint32_t)m;
+  op->inc.p = (uint32_t)p;
+  {  // d (zero-padded to m), tail, head straight from the caller's arrays
+    double* dd = nullptr;
+    uint32_t *t = nullptr, *hd = nullptr;
+    rc = dev_alloc(op, &dd, m);
+    if (!rc) rc = dev_alloc(op, &t, m);
+    if (!rc) rc = dev_alloc(op, &hd, m);
+    if (!rc && m) {
+      CUDA_TRY(cudaMemsetAsync(dd, 0, m * sizeof(double), op->stream));
+      if (d_len) CUDA_TRY(cudaMemcpyAsync(dd, d, d_len * sizeof(double), cudaMemcpyHostToDevice, op->stream));
+      CUDA_TRY(cudaMemcpyAsync(t, tail, m * sizeof(uint32_t), cudaMemcpyHostToDevice, op->stream));
+      CUDA_TRY(cudaMemcpyAsync(hd, head, m * sizeof(uint32_t), cudaMemcpyHostToDevice, op->stream));
+      CUDA_TRY(cudaStreamSynchronize(op->stream));
+    }
+    op->inc.d = dd;
+    op->inc.tail = t;
+    op->inc.head = hd;
+  }
+  laps.lap("upload d, tail, head");
   // node -> arc lists, ascending arc index inside each node (tail: +x_j, head: -x_j; self-loops cancel)
   HostLongRows h;
   std::vector<uint64_t> row_ent(p + 1, 0);
-  for (size_t j = 0; j < m; ++j)
-    if (tail[j] != head[j]) {
-      ++row_ent[tail[j] + 1];
-      ++row_ent[head[j] + 1];
+  uint32_t* ent_idx_dev = nullptr;
+  // the vector workspace of the blocked kernels (three Lanczos vectors and x in cell order, at most 128 padding slots per
+  // cell) doubles as the builders' scratch
+  void* work[4] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t work_doubles = m + (size_t)op->G * tpl::kBStage + p;
+  if (device_build)
+    for (void*& w : work) {
+      double* q = nullptr;
+      if (!rc) rc = dev_alloc(op, &q, work_doubles);
+      w = q;
     }
-  for (size_t u = 0; u < p; ++u) row_ent[u + 1] += row_ent[u];
-  h.ent_idx.resize(row_ent[p]);
-  {
+  if (device_build && !rc) {
+    if (const int e = tpl::build_node_lists_device(m, p, op->inc.tail, op->inc.head, op->stream, work, &ent_idx_dev, row_ent)) {
+      tpl_op_free(op);
+      return fail(TPL_ERR_CUDA, "CUDA error while building the node lists on the device: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    dev_adopt(op, ent_idx_dev, (size_t)row_ent[p]);
+  } else {
+    for (size_t j = 0; j < m; ++j)
+      if (tail[j] != head[j]) {
+        ++row_ent[tail[j] + 1];
+        ++row_ent[head[j] + 1];
+      }
+    for (size_t u = 0; u < p; ++u) row_ent[u + 1] += row_ent[u];
+    h.ent_idx.resize(row_ent[p]);
     std::vector<uint64_t> fill(row_ent.begin(), row_ent.end() - 1);
     for (size_t j = 0; j < m; ++j)
       if (tail[j] != head[j]) {
@@ -715,15 +792,8 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   h.row.resize(p);
   for (size_t u = 0; u < p; ++u) h.row[u] = (uint32_t)(m + u);
   build_segments(h, row_ent, op->G);
-  std::vector<double> dd(m, 0.0);
-  if (d_len) std::memcpy(dd.data(), d, d_len * sizeof(double));
-  std::vector<uint32_t> t(tail, tail + m), hd(head, head + m);
-  op->inc.m = (uint32_t)m;
-  op->inc.p = (uint32_t)p;
-  rc = dev_upload(op, &op->inc.d, dd);
-  if (!rc) rc = dev_upload(op, &op->inc.tail, t);
-  if (!rc) rc = dev_upload(op, &op->inc.head, hd);
-  if (!rc) rc = upload_long_rows(op, h, op->inc.lr);
+  if (!rc) rc = upload_long_rows(op, h, op->inc.lr, ent_idx_dev);
+  laps.lap("node -> arc lists");
   // resident shape: per-CTA node -> local-arc lists (tail: +, head: - with bit 15), ascending local arc index
   {
     const int G = op->G;
@@ -771,6 +841,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       op->resident_ok = !rc;
     }
   }
+  laps.lap("resident lists");
   // cell shape: 2-D partition of the arcs, per-cell jagged-diagonal tail lists and head lists, tagged-atom exchange buffers
   if (!rc) {
     int max_optin = 0;
@@ -802,12 +873,23 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       }
     }
   }
+  laps.lap("cell tables");
   // blocked streaming shape (tpl_blocks.cuh): node blocks, cell-order operator, tile lists over local node ids
   if (!rc && m >= 1 && p >= 1) {
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
-    tpl::HostBlocks hb;
-    tpl::build_blocks(m, p, tail, head, d, d_len, op->G, (size_t)max_optin, hb);
+    tpl::HostBlocks hb_host;
+    tpl::DeviceBlocks db;
+    if (device_build) {
+      if (const int e = tpl::build_blocks_device(m, p, op->inc.tail, op->inc.head, op->inc.d, op->G, (size_t)max_optin, op->stream, work, db)) {
+        tpl_op_free(op);
+        return fail(TPL_ERR_CUDA, "CUDA error while building the blocked layout on the device: %s", cudaGetErrorString((cudaError_t)e));
+      }
+    } else {
+      tpl::build_blocks(m, p, tail, head, d, d_len, op->G, (size_t)max_optin, hb_host);
+    }
+    const tpl::HostBlocks& hb = device_build ? db.meta : hb_host;
+    laps.lap(device_build ? "blocked layout (device)" : "blocked layout (host)");
     if (hb.ok) {
       tpl::BlockOp& bo = op->blk;
       bo = tpl::BlockOp{};
@@ -821,16 +903,40 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       if (!rc) rc = dev_upload(op, &bo.hbs, hb.hbs);
       if (!rc) rc = dev_upload(op, &bo.tbn, hb.tbn);
       if (!rc) rc = dev_upload(op, &bo.hbn, hb.hbn);
-      if (!rc) rc = dev_upload(op, &bo.d, hb.d);
-      if (!rc) rc = dev_upload(op, &bo.th, hb.th);
-      if (!rc) rc = dev_upload(op, &bo.gidx, hb.gidx);
-      if (!rc) rc = dev_upload(op, &bo.pdesc, hb.pdesc);
-      if (!rc) rc = dev_upload(op, &bo.tl.thdr, hb.thdr);
-      if (!rc) rc = dev_upload(op, &bo.tl.lent, hb.lent);
-      if (!rc) rc = dev_upload(op, &bo.tl.piece, hb.piece);
-      if (!rc) rc = dev_alloc(op, &bo.xc, (size_t)hb.Mpad);
-      for (auto& bb : op->bbuf)
-        if (!rc) rc = dev_alloc(op, &bb, (size_t)hb.Mpad + p);
+      if (device_build) {
+        dev_adopt(op, db.d, hb.Mpad);
+        dev_adopt(op, db.th, hb.Mpad);
+        dev_adopt(op, db.gidx, hb.Mpad);
+        dev_adopt(op, db.pdesc, hb.Mpad / tpl::kBStage);
+        dev_adopt(op, db.thdr, (size_t)hb.GR * hb.GC * hb.ntile);
+        dev_adopt(op, db.lent, db.lent_words);
+        bo.d = db.d;
+        bo.th = db.th;
+        bo.gidx = db.gidx;
+        bo.pdesc = db.pdesc;
+        bo.tl.thdr = db.thdr;
+        bo.tl.lent = db.lent;
+        bo.tl.piece = nullptr;
+        op->blk_lent_words = db.lent_words;
+      } else {
+        if (!rc) rc = dev_upload(op, &bo.d, hb.d);
+        if (!rc) rc = dev_upload(op, &bo.th, hb.th);
+        if (!rc) rc = dev_upload(op, &bo.gidx, hb.gidx);
+        if (!rc) rc = dev_upload(op, &bo.pdesc, hb.pdesc);
+        if (!rc) rc = dev_upload(op, &bo.tl.thdr, hb.thdr);
+        if (!rc) rc = dev_upload(op, &bo.tl.lent, hb.lent);
+        if (!rc) rc = dev_upload(op, &bo.tl.piece, hb.piece);
+        op->blk_lent_words = hb.lent.size();
+      }
+      if (device_build) {  // the builders' scratch becomes the vector workspace
+        bo.xc = static_cast<double*>(work[3]);
+        for (int q = 0; q < 3; ++q) op->bbuf[q] = static_cast<double*>(work[q]);
+        for (void*& w : work) w = nullptr;
+      } else {
+        if (!rc) rc = dev_alloc(op, &bo.xc, (size_t)hb.Mpad);
+        for (auto& bb : op->bbuf)
+          if (!rc) rc = dev_alloc(op, &bb, (size_t)hb.Mpad + p);
+      }
       const uint32_t PL = hb.PT + hb.PH;
       op->smem_blk1 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring1, hb.lblk, hb.nl, hb.ntb, false, false, hb.ntile);
       op->smem_blk2 = tpl::block_smem_bytes(PL, hb.T, (int)hb.ring2, hb.lblk, hb.nl, hb.ntb, true, false, hb.ntile);
@@ -840,6 +946,9 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       if (!rc) rc = setup_local_fabric(op, true);
     }
   }
+  for (void* w : work)
+    if (w) dev_free(op, w);  // no blocked layout: the scratch is not needed
+  laps.lap("blocked layout (upload)");
   // tiled streaming shape: per-CTA, per-tile entry lists; T = the largest tile (multiple of the stream batch, at most
   // 16384) for which pass 2's layout (node segment + accumulators + tile) fits in shared memory
   if (!rc && p >= 1 && p < (1u << 17) && !(op->blocked_ok && op->blk_max_cell >= 4 * 10240)) {
@@ -866,11 +975,13 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
       }
     }
   }
+  laps.lap("tiled lists");
   const size_t seg_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
   op->inc.stage_nodes = (p * sizeof(double) + seg_bytes <= kSmemBudget) ? 1 : 0;
   op->smem_bytes = seg_bytes + (op->inc.stage_nodes ? p * sizeof(double) : 0);
   op->matrix_bytes = 24ull * m + 4ull * p;  // (d, tail, head) + node->arc lists + list pointers
   if (!rc) rc = finish_setup(op);
+  laps.lap("finish setup");
   if (rc) {
     std::string keep = tpl::g_err;
     tpl_op_free(op);
@@ -988,6 +1099,72 @@ int tpl_tiles_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* hea
   stats[5] = lmax;
   stats[6] = hsh;
   stats[7] = tpl::kFoldThreads;
+  return TPL_OK;
+}
+
+int tpl_op_layout_check(tpl_op* op, const uint32_t* tail, const uint32_t* head, const double* d, size_t d_len, uint64_t stats[8]) {
+  tpl::clear_error();
+  if (!op || !stats || !tail || !head || (d_len && !d)) return fail(TPL_ERR_PANIC, "null argument");
+  if (op->format != 2 || op->comm) return fail(TPL_ERR_PANIC, "tpl_op_layout_check needs an unsharded KKT handle");
+  CUDA_TRY(cudaSetDevice(op->device));
+  CUDA_TRY(cudaStreamSynchronize(op->stream));
+  std::fill(stats, stats + 8, 0ull);
+  const size_t m = op->inc.m, p = op->inc.p;
+  stats[0] = op->device_built;
+  stats[1] = op->blocked_ok;
+  auto fetch = [&](auto& vec, const auto* dev, size_t count) -> int {
+    vec.resize(count);
+    if (count) CUDA_TRY(cudaMemcpy(vec.data(), dev, count * sizeof(vec[0]), cudaMemcpyDeviceToHost));
+    return TPL_OK;
+  };
+  if (op->blocked_ok) {
+    const tpl::BlockOp& bo = op->blk;
+    tpl::HostBlocks h;
+    h.GR = bo.GR; h.GC = bo.GC; h.PT = bo.PT; h.PH = bo.PH; h.Mpad = bo.Mpad; h.T = bo.tl.T; h.ntile = bo.tl.ntile;
+    h.ring1 = bo.ring1; h.ring2 = bo.ring2; h.ring2v = bo.ring2v; h.lblk = bo.lblk; h.nl = bo.nl; h.ntb = bo.ntb;
+    const size_t Gc = (size_t)bo.GR * bo.GC;
+    if (int rc = fetch(h.cell_off, bo.cell_off, Gc + 1)) return rc;
+    if (int rc = fetch(h.tbs, bo.tbs, bo.GR + 1)) return rc;
+    if (int rc = fetch(h.hbs, bo.hbs, bo.GC + 1)) return rc;
+    if (int rc = fetch(h.tbn, bo.tbn, h.tbs[bo.GR])) return rc;
+    if (int rc = fetch(h.hbn, bo.hbn, h.hbs[bo.GC])) return rc;
+    if (int rc = fetch(h.d, bo.d, bo.Mpad)) return rc;
+    if (int rc = fetch(h.th, bo.th, bo.Mpad)) return rc;
+    if (int rc = fetch(h.gidx, bo.gidx, bo.Mpad)) return rc;
+    if (int rc = fetch(h.pdesc, bo.pdesc, bo.Mpad / tpl::kBStage)) return rc;
+    if (int rc = fetch(h.thdr, bo.tl.thdr, Gc * bo.tl.ntile)) return rc;
+    if (int rc = fetch(h.lent, bo.tl.lent, op->blk_lent_words)) return rc;
+    h.ok = true;
+    stats[2] = (uint64_t)tpl::check_blocks(m, p, tail, head, d, d_len, h);
+    uint64_t hsh = 1469598103934665603ull;
+    for (uint32_t e : h.lent) hsh = (hsh ^ e) * 1099511628211ull;
+    for (uint32_t e : h.th) hsh = (hsh ^ e) * 1099511628211ull;
+    for (uint32_t e : h.gidx) hsh = (hsh ^ e) * 1099511628211ull;
+    stats[3] = hsh;
+    stats[4] = h.lent.size();
+    stats[5] = h.T;
+  }
+  {  // node -> arc lists against a host construction
+    std::vector<uint64_t> ptr(p + 1, 0);
+    for (size_t j = 0; j < m; ++j)
+      if (tail[j] != head[j]) {
+        ++ptr[tail[j] + 1];
+        ++ptr[head[j] + 1];
+      }
+    for (size_t u = 0; u < p; ++u) ptr[u + 1] += ptr[u];
+    std::vector<uint32_t> want(ptr[p]), got;
+    std::vector<uint64_t> fill(ptr.begin(), ptr.end() - 1);
+    for (size_t j = 0; j < m; ++j)
+      if (tail[j] != head[j]) {
+        want[fill[tail[j]]++] = (uint32_t)j;
+        want[fill[head[j]]++] = (uint32_t)j | tpl::kSignBit;
+      }
+    if (int rc = fetch(got, op->inc.lr.ent_idx, want.size())) return rc;
+    uint64_t bad = 0;
+    for (size_t e = 0; e < want.size(); ++e) bad += want[e] != got[e];
+    stats[6] = bad;
+    stats[7] = want.size();
+  }
   return TPL_OK;
 }
 

@@ -116,6 +116,18 @@ class LinOp:
         """kernel family a whole-pass solve runs: cells / chunks / tiled / gather / csr / sharded"""
         return _lib.load().tpl_op_kernel_shape(self._h).decode()
 
+    def layout_check(self, tail, head, d) -> dict:
+        """Downloads the handle's tables (built on the device from 2^20 arcs on) and checks them on the host
+        (tpl_op_layout_check): blocked layout consistent, node lists equal to a host construction."""
+        tail = np.ascontiguousarray(tail, dtype=np.uint32)
+        head = np.ascontiguousarray(head, dtype=np.uint32)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        st = (C.c_uint64 * 8)()
+        _lib.check(_lib.load().tpl_op_layout_check(self._h, tail.ctypes.data_as(c_u32p), head.ctypes.data_as(c_u32p),
+                                                   d.ctypes.data_as(c_dp), len(d), st))
+        keys = ("device_built", "blocked", "check", "hash", "list_words", "tile_arcs", "node_list_mismatches", "node_list_words")
+        return dict(zip(keys, (int(x) for x in st)))
+
     def trace_enable(self, max_steps: int):
         _lib.check(_lib.load().tpl_op_trace_enable(self._h, max_steps))
 
