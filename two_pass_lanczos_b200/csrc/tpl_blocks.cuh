@@ -93,33 +93,35 @@ struct BlockSmem {
 // added to the node's accumulator `depth` barrier phases after the walk, so the order in which the shares of a node are added
 // is fixed and no two threads ever update one accumulator in the same phase.
 // Padding (only behind the last entry of a tile) is a harmless entry instead of a branch: it adds the tile's ZERO slot
-// (index T + kMaxPieces - 1, written once; at most kMaxPieces - 1 run sums per tile) to the running sum and names the dummy.
+// (the last of the block_piece_slots(T) words behind the T arc values; written once) to the running sum and names the dummy.
 constexpr uint32_t kBEntMinus = 0x80000000u, kBEntNew = 0x40000000u, kBEntNodeShift = 16, kBEntNodeMask = 0x3fffu, kBEntOffMask = 0xffffu;
 constexpr uint32_t kBMaxLocalNodes = kBEntNodeMask;  // accumulators + dummy + scratch slots must fit the 14-bit slot field
 constexpr uint32_t kBAccPad = 2;  // accumulator slots behind the PL real ones (dummy + alignment)
 constexpr int kBPre = 8;          // list entries per fold thread requested together
 constexpr int kBFlush = 4;        // the short form of the last batch of a slice
+// words of a tile buffer behind its T arc values: at most four run sums per 128-arc stage, then the zero slot (even total)
+__host__ __device__ inline uint32_t block_piece_slots(uint32_t T) { return T / 32 + 8; }
 __host__ __device__ inline uint32_t block_pad_entry(uint32_t PL, uint32_t T) {
-  return (PL << kBEntNodeShift) | ((T + kMaxPieces - 1) * 8u);
+  return (PL << kBEntNodeShift) | ((T + block_piece_slots(T) - 1) * 8u);
 }
 __host__ __device__ inline size_t block_slot_bytes(int n8, int n4) { return (size_t)n8 * kBStage * 8 + (size_t)n4 * kBStage * 4 + 16; }  // + the stage's run descriptors
 // pass 1 never needs node values and accumulators at the same time (they alias), pass 2 needs both
 constexpr uint32_t kBMbarBytes = (kWarps * kBMaxRing + kBMaxList) * 8;
 __host__ __device__ inline size_t block_smem_bytes(uint32_t PL, uint32_t T, int ring, uint32_t lblk, uint32_t nl, uint32_t ntb, bool pass2, bool with_v, uint32_t ntile) {
   const size_t slot = pass2 ? block_slot_bytes(4, with_v ? 2 : 1) : block_slot_bytes(2, 0);
-  return ((pass2 ? 2 : 1) * ((size_t)PL + kBAccPad) + ntb * ((size_t)T + kMaxPieces)) * sizeof(double) +
+  return ((pass2 ? 2 : 1) * ((size_t)PL + kBAccPad) + ntb * ((size_t)T + block_piece_slots(T))) * sizeof(double) +
          (size_t)(pass2 ? kBComputeWarps2 : kBComputeWarps1) * ring * slot +
          (size_t)nl * lblk + kBMbarBytes + kFoldThreads * 8 + (size_t)ntile * 16 + 16;  // + 16: the carve-up starts at the next 16-byte boundary
 }
 __device__ __forceinline__ BlockSmem carve_blocks(double* base, uint32_t PL, uint32_t T, uint32_t lblk, uint32_t nl, uint32_t ntb, uint32_t ntile, bool pass2) {
-  // bulk copies need 16-byte aligned shared-memory addresses: PL and T + kMaxPieces are even (host), the base is rounded up
+  // bulk copies need 16-byte aligned shared-memory addresses: PL and T + block_piece_slots(T) are even (host), the base is rounded up
   const uint32_t b = ((uint32_t)__cvta_generic_to_shared(base) + 15u) & ~15u;
   BlockSmem s;
   s.node.a = b;
   s.acc.a = pass2 ? b + (PL + kBAccPad) * 8u : b;
   s.scr = s.acc.a + (PL + kBAccPad) * 8u;  // list slots PL + kBAccPad + slice
   s.wt.a = s.scr + kBSlices * 8u;
-  s.wt_stride = (T + kMaxPieces) * 8u;
+  s.wt_stride = (T + block_piece_slots(T)) * 8u;
   s.mbar = s.wt.a + ntb * s.wt_stride;
   s.hdr = s.mbar + kBMbarBytes;
   s.lst = s.hdr + ntile * 16u;
@@ -546,7 +548,7 @@ __device__ __forceinline__ void init_block_smem(const BlockOp& bo, const BlockSm
     const TileHdr h = tile_hdr(bo.tl, blockIdx.x * bo.tl.ntile + t);
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s.hdr + t * 16u), "r"(h.e0), "r"(h.L), "r"(h.q0), "r"(h.q1) : "memory");
   }
-  if (threadIdx.x < bo.ntb) sm_st(SmArr{s.wt.a + threadIdx.x * s.wt_stride}, bo.tl.T + kMaxPieces - 1, 0.0);
+  if (threadIdx.x < bo.ntb) sm_st(SmArr{s.wt.a + threadIdx.x * s.wt_stride}, bo.tl.T + block_piece_slots(bo.tl.T) - 1, 0.0);
   fence_mbar_init();
   __syncthreads();
 }

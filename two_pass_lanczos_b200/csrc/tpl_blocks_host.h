@@ -105,7 +105,7 @@ inline bool build_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const 
         uint32_t j = i;
         while (j < s1 && tl[j] == tl[i] && tl[j] != hl[j]) ++j;
         const uint32_t len = j - i;
-        if (len >= kBPieceMin && used < 4 && npieces < kMaxPieces - 1) {
+        if (len >= kBPieceMin && used < 4 && npieces < block_piece_slots(T) - 1) {
           d4[used++] = (i - s0) | ((len - 1) << 8) | (npieces << 16);
           w.e_node.push_back(tl[i]);
           w.e_code.push_back((T + npieces) * 8u);
@@ -374,7 +374,7 @@ inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const u
         runs.emplace_back(s0 - t0 + start, len);
       }
     }
-    if (runs.size() > kMaxPieces - 1) return 3;
+    if (runs.size() > block_piece_slots(T) - 1) return 3;
     std::fill(seen_t.begin(), seen_t.end(), 0);
     std::fill(seen_h.begin(), seen_h.end(), 0);
     uint32_t prev_node = 0, prev_depth = 0, maxdepth = 0;

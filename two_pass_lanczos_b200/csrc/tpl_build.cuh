@@ -110,7 +110,7 @@ __global__ void cell_order_kernel(size_t m, const uint64_t* key, const uint32_t*
 // One CTA (256 threads = one per slice) per tile of a cell; the device form of build_cell_lists, identical output.
 //   a. the tile's local tails / heads into shared memory (loop or padding: tail == head == 0);
 //   b. one thread per 128-arc stage finds the stage's same-tail runs of >= kBPieceMin arcs (the first four are candidates);
-//      the candidates are numbered across the stages in order and the first kMaxPieces - 1 become run sums;
+//      the candidates are numbered across the stages in order and the first block_piece_slots(T) - 1 become run sums (all of them: four per stage fit);
 //   c. entries: tail side in arc order (a run = one entry at its first arc), then head side; key = node << 13 | order;
 //   d. WRITE: a bitonic sort of the (key, code) pairs puts them in the host's order (by node, a node's tail side in arc order,
 //      then its head side); slice i takes entries [i L, (i + 1) L); depth of a slice whose first node X continues from the
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) tile_lists_kernel(const TileListArgs
     uint32_t d4[4] = {kBNoPiece, kBNoPiece, kBNoPiece, kBNoPiece};
     for (uint32_t q = 0; q < ncand[tid]; ++q) {
       const uint32_t id = first + q;
-      if (id >= kMaxPieces - 1) break;
+      if (id >= block_piece_slots(T) - 1) break;
       const uint32_t start = cand[tid * 4 + q] & 0xffu, len = cand[tid * 4 + q] >> 8;
       d4[q] = start | ((len - 1) << 8) | (id << 16);
       tcode[s0 + start] = (T + id) * 8u;
