@@ -453,7 +453,7 @@ def run_b200(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, inst),
             "arm": {"format": "incidence", "kernel_shape": shape, "operator_build_s": round(build_s, 4),
-                    "operator_build_note": "host tables + H2D of the operator, outside the timed region as in the reference's "
+                    "operator_build_note": "operator tables (host builders below 2^20 arcs, on the device above) + H2D of the operator, outside the timed region as in the reference's "
                                            "protocol (src/bin/tradeoff.rs:265-288 times the solver call only)"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "ms", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n + 16 * k,
