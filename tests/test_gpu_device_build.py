@@ -92,3 +92,61 @@ def test_large_instances_build_on_the_device_by_default():
     assert op.kernel_shape() == "blocked"
     small = datagen.gen_kkt(60_000, 3, 7, "wc")
     assert _build(None, small.m, small.p, small.tail, small.head, small.d).layout_check(small.tail, small.head, small.d)["device_built"] == 0
+
+
+@pytest.mark.parametrize("case", ["all_loops", "many_nodes", "two_nodes"])
+def test_degenerate_large_instances_build_like_the_host(case):
+    """Shapes the blocked layout cannot or need not hold: the device path must end where the host path ends."""
+    rng = np.random.default_rng(11)
+    m = (1 << 20) + 77
+    if case == "all_loops":  # every arc a self-loop: no incidence entries at all, A = diag(D, 0)
+        p = 3
+        tail = rng.integers(0, p, m).astype(np.uint32)
+        head = tail.copy()
+    elif case == "many_nodes":  # more nodes than a block holds (local ids are 15 bits): gather kernels
+        p = 3_000_000
+        tail = rng.integers(0, p, m).astype(np.uint32)
+        head = rng.integers(0, p, m).astype(np.uint32)
+    else:  # one tail and one head node: a single run per stage, the hub straddles every slice
+        p = 2
+        tail = np.zeros(m, dtype=np.uint32)
+        head = np.ones(m, dtype=np.uint32)
+    d = rng.uniform(1.0, 2.0, m)
+    dev = _build(None, m, p, tail, head, d)
+    host = _build("TPL_HOST_BUILD", m, p, tail, head, d)
+    got, want = dev.layout_check(tail, head, d), host.layout_check(tail, head, d)
+    assert got["device_built"] == 1 and want["device_built"] == 0
+    assert got["blocked"] == want["blocked"] and got["check"] == 0 and want["check"] == 0
+    assert got["hash"] == want["hash"] and got["node_list_mismatches"] == 0
+    assert dev.kernel_shape() == host.kernel_shape()
+    n = m + p
+    b = rng.standard_normal(n)
+    assert np.array_equal(dev.apply(b), host.apply(b))
+    assert np.array_equal(tpl.lanczos_two_pass(dev, b, 12, "inv"), tpl.lanczos_two_pass(host, b, 12, "inv"))
+
+
+@pytest.mark.parametrize("builder", ["TPL_HOST_BUILD", "TPL_DEVICE_BUILD"])
+def test_sparse_graph_with_a_million_nodes_matches_the_oracle(builder):
+    """More node rows than a CTA's shared memory holds segment sums for (they go through HBM scratch, tpl_kernels.cuh
+    seg_put / seg_get) and more nodes than the blocked layout's 15-bit local ids: the gather kernels, against the oracle."""
+    from oracle import np_oracle as npo
+    from oracle import oracle as orc
+    rng = np.random.default_rng(23)
+    p, m = 1_000_000, 1_500_000
+    tail = rng.integers(0, p, m).astype(np.uint32)
+    head = rng.integers(0, p, m).astype(np.uint32)
+    d = rng.uniform(1.0, 10.0, m)
+    j = np.arange(m, dtype=np.uint64)
+    t, h = tail.astype(np.uint64), head.astype(np.uint64)
+    ones = np.ones(m)
+    oop = orc.SparseColMat.try_new_from_triplets(
+        m + p, m + p, np.concatenate([j, m + t, m + h, j, j]), np.concatenate([j, j, j, m + t, m + h]),
+        np.concatenate([d, ones, -ones, ones, -ones]))
+    gop = _build(builder, m, p, tail, head, d)
+    assert gop.kernel_shape() == "gather"
+    x = rng.standard_normal(m + p)
+    assert helpers.rel(gop.apply(x), oop.apply(x)) < 1e-14
+    b = helpers.seeded_b(m + p)
+    x_gpu = tpl.lanczos_two_pass(gop, b / np.linalg.norm(b), 25, "exp")
+    x_cpu = orc.lanczos_two_pass(oop, b / np.linalg.norm(b), 25, npo.exp_tk_solver)
+    assert helpers.rel(x_gpu, x_cpu) <= 1e-10

@@ -111,7 +111,7 @@ __device__ __forceinline__ void sell_long_segments(const LongRows& lr, const dou
         if (eb + lane + 32 * q < e1) acc = __dadd_rn(acc, __dmul_rn(val[q], __dmul_rn(x[q], s)));
     }
     acc = warp_sum(acc);
-    if (lane == 0) sm_seg[sg - s0] = acc;
+    if (lane == 0) seg_put(lr, sm_seg, sg, s0, acc);
   }
 }
 

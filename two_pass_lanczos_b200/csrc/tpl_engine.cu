@@ -275,6 +275,7 @@ bool is_device_ptr(const void* p) {
 }
 
 // ---------------------------------------------------------------- long-row (segment) format
+constexpr size_t kSegSmemMax = 96 * 1024;  // most shared memory a CTA spends on segment sums
 struct HostLongRows {
   std::vector<uint32_t> row, seg_ptr, ent_ptr, ent_idx, cta_ptr;
   std::vector<double> ent_val;
@@ -284,11 +285,12 @@ struct HostLongRows {
 // row_ent[q]..row_ent[q+1] is the entry range of long row q inside ent_idx/ent_val (already filled).
 void build_segments(HostLongRows& h, const std::vector<uint64_t>& row_ent, int G) {
   const size_t nlong = h.row.size();
-  uint64_t L = 256;
-  for (;;) {
+  uint64_t L = 256, longest = 0;
+  for (size_t q = 0; q < nlong; ++q) longest = std::max<uint64_t>(longest, row_ent[q + 1] - row_ent[q]);
+  for (;;) {  // longer segments until a CTA's share of segment sums is small -- as far as that helps: a row is at least one segment
     uint64_t segs = 0;
     for (size_t q = 0; q < nlong; ++q) segs += (row_ent[q + 1] - row_ent[q] + L - 1) / L;
-    if (segs <= (uint64_t)G * 3072) break;
+    if (segs <= (uint64_t)G * 3072 || L >= longest) break;
     L *= 2;
   }
   h.seg_ptr.assign(nlong + 1, 0);
@@ -342,6 +344,13 @@ int upload_long_rows(tpl_op* op, const HostLongRows& h, tpl::LongRows& d, const 
   d.ent_val = nullptr;
   if (!h.ent_val.empty())
     if (int rc = dev_upload(op, &d.ent_val, h.ent_val)) return rc;
+  // Operators with very many rows in this format (the node rows of a sparse graph with millions of nodes): a CTA's segment
+  // sums do not fit in shared memory; they go through a scratch array in HBM instead.
+  d.seg_scratch = nullptr;
+  if ((size_t)h.max_segs * sizeof(double) > kSegSmemMax) {
+    if (int rc = dev_alloc(op, &d.seg_scratch, h.seg_ptr.empty() ? 1 : (size_t)h.seg_ptr.back())) return rc;
+    d.max_segs = 1;
+  }
   return TPL_OK;
 }
 
@@ -645,7 +654,7 @@ int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, co
   }
   if (!rc) rc = upload_long_rows(op, h, op->sell.lr);
   op->matrix_bytes = 12ull * nnz + 4ull * (n + 1);
-  op->smem_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
+  op->smem_bytes = sizeof(double) * std::max<size_t>(op->sell.lr.max_segs, 1);
   if (!rc) rc = finish_setup(op);
   if (rc) {
     std::string keep = tpl::g_err;
@@ -976,7 +985,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
     }
   }
   laps.lap("tiled lists");
-  const size_t seg_bytes = sizeof(double) * std::max<size_t>(h.max_segs, 1);
+  const size_t seg_bytes = sizeof(double) * std::max<size_t>(op->inc.lr.max_segs, 1);
   op->inc.stage_nodes = (p * sizeof(double) + seg_bytes <= kSmemBudget) ? 1 : 0;
   op->smem_bytes = seg_bytes + (op->inc.stage_nodes ? p * sizeof(double) : 0);
   op->matrix_bytes = 24ull * m + 4ull * p;  // (d, tail, head) + node->arc lists + list pointers

@@ -45,6 +45,8 @@ struct LongRows {
   const uint32_t* ent_idx;  // [nent]    column (incidence: bit 31 set = coefficient -1)
   const double* ent_val;    // [nent]    CSR only
   const uint32_t* cta_ptr;  // [G+1]     long rows owned by each CTA
+  double* seg_scratch;      // [nseg] or nullptr: where the segment sums go when a CTA's share does not fit in shared memory
+                            // (operators with millions of rows in this format: every node row of a sparse graph)
 };
 
 struct IncidenceOp {  // A = [[D, E^T], [E, 0]], arc j: +1 at tail, -1 at head
@@ -328,6 +330,17 @@ __device__ __forceinline__ void cta_chunk(uint32_t total, uint32_t& lo, uint32_t
   hi = (a + chunk) < total ? (uint32_t)(a + chunk) : total;
 }
 
+// Segment sums live in shared memory, or -- written and read by the same CTA around a CTA barrier, through L2 -- in
+// lr.seg_scratch when the CTA's share is too large for it.
+__device__ __forceinline__ void seg_put(const LongRows& lr, double* sm_seg, uint32_t sg, uint32_t s0, double v) {
+  if (lr.seg_scratch)
+    __stcg(lr.seg_scratch + sg, v);
+  else
+    sm_seg[sg - s0] = v;
+}
+__device__ __forceinline__ double seg_get(const LongRows& lr, const double* sm_seg, uint32_t sg, uint32_t s0) {
+  return lr.seg_scratch ? __ldcg(lr.seg_scratch + sg) : sm_seg[sg - s0];
+}
 // Sums the segments of the long rows owned by this CTA into sm_seg (one warp per segment, lanes
 // stride the entries, xor-shuffle tree).  The order depends only on the operator, never on the grid.
 template <class DEV>
@@ -344,13 +357,13 @@ __device__ __forceinline__ void long_row_segments(const DEV& dev, const LongRows
 #pragma unroll 4
     for (uint32_t e = e0 + lane; e < e1; e += 32) acc = dev.entry(lr, e, X, s, acc);
     acc = warp_sum(acc);
-    if (lane == 0) sm_seg[sg - s0] = acc;
+    if (lane == 0) seg_put(lr, sm_seg, sg, s0, acc);
   }
 }
 __device__ __forceinline__ double long_row_total(const LongRows& lr, uint32_t q, const double* sm_seg, uint32_t s0) {
   const uint32_t a = __ldg(lr.seg_ptr + q), b = __ldg(lr.seg_ptr + q + 1);
   double t = 0.0;
-  for (uint32_t sg = a; sg < b; ++sg) t = __dadd_rn(t, sm_seg[sg - s0]);
+  for (uint32_t sg = a; sg < b; ++sg) t = __dadd_rn(t, seg_get(lr, sm_seg, sg, s0));
   return t;
 }
 
