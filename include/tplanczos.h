@@ -111,6 +111,18 @@ int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, co
  * column-major with leading dimension lda >= n, copied to the device.  The matrix must be symmetric (as Lanczos
  * requires; the kernels read column i as row i).  SURVEY 8f, N4. */
 int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op** out);
+/* Dense complex HERMITIAN operator (`T: ComplexField` with T = c64, src/algorithms/mod.rs:167): n x n complex,
+ * column-major, every entry stored (re, im), leading dimension lda >= n COMPLEX entries.  The handle's vectors are n complex
+ * numbers in the same interleaved storage, i.e. 2 n doubles: tpl_op_nrows() returns 2 n, and every entry point of this header
+ * takes and returns such vectors as they are -- with real alpha and beta (T::Real) the recurrence on the interleaved storage IS
+ * the complex recurrence (<v, w> = Re(v^H w), ||w||, w - alpha v), only the product A x is complex.  The kernels read column i
+ * conjugated as row i.  No test of the reference instantiates a complex operator: parity is checked against a complex128
+ * restatement of the same recurrence (tests/test_gpu_dense.py). */
+int tpl_op_from_dense_hermitian(size_t n, const double* a, size_t lda, int device, tpl_op** out);
+int tpl_op_is_complex(const tpl_op* op); /* 1: vectors are interleaved complex numbers (tpl_op_nrows() / 2 of them) */
+/* Diagonal operator diag(d_0 .. d_{n-1}) (the synthetic spectra of src/bin/stability.rs:98-193 and orthogonality.rs): a
+ * convenience over tpl_op_from_csc. */
+int tpl_op_from_diagonal(size_t n, const double* diag, int device, tpl_op** out);
 /* Network-incidence form of A = [[D, E^T], [E, 0]]: reads arc tail/head instead of stored +-1.
  * d_len <= m honours the loader's short-D quirk (rows >= d_len have no diagonal entry). */
 int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* head, const double* d,

@@ -39,6 +39,9 @@ SIGNATURES = {
                                     C.POINTER(C.c_int)]),
     "tpl_op_from_csc": (C.c_int, [C.c_size_t, c_u64p, c_u64p, c_dp, C.c_int, C.POINTER(C.c_void_p)]),
     "tpl_op_from_dense": (C.c_int, [C.c_size_t, c_dp, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "tpl_op_from_dense_hermitian": (C.c_int, [C.c_size_t, c_dp, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "tpl_op_is_complex": (C.c_int, [C.c_void_p]),
+    "tpl_op_from_diagonal": (C.c_int, [C.c_size_t, c_dp, C.c_int, C.POINTER(C.c_void_p)]),
     "tpl_op_from_kkt": (C.c_int, [C.c_size_t, C.c_size_t, c_u32p, c_u32p, c_dp, C.c_size_t, C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "tpl_op_from_kkt_system": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

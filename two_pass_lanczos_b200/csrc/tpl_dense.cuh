@@ -14,11 +14,16 @@
 namespace tpl {
 
 struct DenseOp {
-  uint32_t n;
+  uint32_t n;       // REAL dimension of the vectors (a Hermitian operator of n_c complex rows: n = 2 n_c)
   uint32_t stage;   // the operand vector (n doubles) is staged in shared memory
-  size_t lda;
-  const double* a;  // column-major, symmetric
+  uint32_t cplx;    // 1: complex Hermitian, entries (re, im) interleaved; vectors are n_c complex numbers, interleaved
+  size_t lda;       // column stride in ENTRIES (doubles, or complex numbers)
+  const double* a;  // column-major, symmetric / Hermitian
 };
+// Complex Hermitian operators (`T: ComplexField`, src/algorithms/mod.rs:167) ride on the real code: with real alpha and beta
+// (T::Real) every vector operation of the recurrence -- <v, w> = Re(v^H w), w - alpha v, ||w||, the scaling by 1 / beta -- IS
+// the real operation on the interleaved (re, im) storage; only the product A x is complex.  A "row unit" below is a row of
+// the real operator or a complex row, which finishes two real rows (2 i: real part, 2 i + 1: imaginary part).
 
 constexpr int kDenseUnroll = 8;
 
@@ -50,6 +55,64 @@ __device__ __forceinline__ double dense_row(const DenseOp& op, uint32_t i, const
   return warp_sum(t);
 }
 
+// (A x)_i of a Hermitian operator: row i is the conjugate of column i, so with c_j = a_ji (read coalesced, 16 bytes per entry)
+//   Re y_i = sum_j Re c_j Re x_j + Im c_j Im x_j,   Im y_i = sum_j Re c_j Im x_j - Im c_j Re x_j.
+__device__ __forceinline__ double2 dense_row_c(const DenseOp& op, uint32_t i, const double* X, double s, const double* sm_x, int lane) {
+  constexpr int U = kDenseUnroll / 2;
+  const double2* col = reinterpret_cast<const double2*>(op.a) + (size_t)i * op.lda;
+  const uint32_t nc = op.n / 2;
+  double ar[U], ai[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) ar[u] = ai[u] = 0.0;
+  for (uint32_t j0 = lane; j0 < nc; j0 += 32 * U) {
+    double2 c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t j = j0 + 32 * u;
+      c[u] = j < nc ? __ldcs(col + j) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t j = j0 + 32 * u;
+      if (j < nc) {
+        double xr, xi;
+        if (sm_x) {
+          xr = sm_x[2 * j];
+          xi = sm_x[2 * j + 1];
+        } else {
+          const double2 xv = __ldcg(reinterpret_cast<const double2*>(X) + j);
+          xr = __dmul_rn(xv.x, s);
+          xi = __dmul_rn(xv.y, s);
+        }
+        ar[u] = __dadd_rn(__dadd_rn(ar[u], __dmul_rn(c[u].x, xr)), __dmul_rn(c[u].y, xi));
+        ai[u] = __dsub_rn(__dadd_rn(ai[u], __dmul_rn(c[u].x, xi)), __dmul_rn(c[u].y, xr));
+      }
+    }
+  }
+  double tr = 0.0, ti = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    tr = __dadd_rn(tr, ar[u]);
+    ti = __dadd_rn(ti, ai[u]);
+  }
+  return make_double2(warp_sum(tr), warp_sum(ti));
+}
+// the rows a warp finishes for row unit i: `fin(row, t)` once (real) or twice (complex: real and imaginary part)
+template <class FIN>
+__device__ __forceinline__ void dense_unit(const DenseOp& op, uint32_t i, const double* X, double s, const double* sm_x, int lane, FIN fin) {
+  if (op.cplx) {
+    const double2 t = dense_row_c(op, i, X, s, sm_x, lane);
+    if (lane == 0) {
+      fin(2 * i, t.x);
+      fin(2 * i + 1, t.y);
+    }
+  } else {
+    const double t = dense_row(op, i, X, s, sm_x, lane);
+    if (lane == 0) fin(i, t);
+  }
+}
+__device__ __forceinline__ uint32_t dense_units(const DenseOp& op) { return op.cplx ? op.n / 2 : op.n; }
+
 __device__ __forceinline__ const double* dense_stage(const DenseOp& op, const double* X, double s, double* sm) {
   if (!op.stage) return nullptr;
   for (uint32_t j = threadIdx.x; j < op.n; j += kBlock) sm[j] = __dmul_rn(__ldcg(X + j), s);
@@ -66,8 +129,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_dense_kernel(const DenseOp op
   int rot = st0.rot, steps = st0.steps, status = st0.status;
   double sc = st0.s_cur, sp = st0.s_prev, bp = st0.beta_prev, bnorm = st0.b_norm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t lo, hi;
-  cta_chunk(op.n, lo, hi);
+  uint32_t lo, hi;  // row units of this CTA; rlo .. rhi the real rows they finish
+  cta_chunk(dense_units(op), lo, hi);
+  const uint32_t rlo = op.cplx ? 2 * lo : lo, rhi = op.cplx ? 2 * hi : hi;
   double* const buf0 = a.buf[0];
   double* const buf1 = a.buf[1];
   double* const buf2 = a.buf[2];
@@ -77,7 +141,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_dense_kernel(const DenseOp op
     double* Wp = pick(rot);
     double* Wc = pick((rot + 1) % 3);
     double acc = 0.0;
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kBlock) {
+    for (uint32_t i = rlo + threadIdx.x; i < rhi; i += kBlock) {
       const double bi = __ldg(a.b + i);
       __stcg(Wc + i, bi);
       __stcg(Wp + i, 0.0);
@@ -104,25 +168,24 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_dense_kernel(const DenseOp op
       const double* sm_x = dense_stage(op, Wc, sc, smem);
       __syncthreads();
       double acc = 0.0;
-      for (uint32_t i = lo + warp; i < hi; i += kWarps) {
-        const double t = dense_row(op, i, Wc, sc, sm_x, lane);
-        if (lane == 0) {
-          const double v = __dmul_rn(__ldcg(Wc + i), sc);
-          const double wt = rec_sub(t, bp, __dmul_rn(__ldcg(Wp + i), sp));
+      for (uint32_t i = lo + warp; i < hi; i += kWarps)
+        dense_unit(op, i, Wc, sc, sm_x, lane, [&](uint32_t r, double t) {
+          const double v = __dmul_rn(__ldcg(Wc + r), sc);
+          const double wt = rec_sub(t, bp, __dmul_rn(__ldcg(Wp + r), sp));
           acc = fma(v, wt, acc);
-          __stcg(Wn + i, wt);
-          if (WITH_V) __stcs(Vcol + i, v);
-        }
-      }
+          __stcg(Wn + r, wt);
+          if (WITH_V) __stcs(Vcol + r, v);
+        });
       const double alpha = grid_sync<true>(acc, a.gs, epoch, sh);
       // ---------------- phase B: w = w~ - alpha v, beta partial (same row ownership: lane 0 of the row's warp wrote w~)
       acc = 0.0;
       for (uint32_t i = lo + warp; i < hi; i += kWarps) {
-        if (lane == 0) {
-          const double w = rec_sub(__ldcg(Wn + i), alpha, __dmul_rn(__ldcg(Wc + i), sc));
-          __stcg(Wn + i, w);
-          acc = fma(w, w, acc);
-        }
+        if (lane == 0)
+          for (uint32_t r = op.cplx ? 2 * i : i; r < (op.cplx ? 2 * i + 2 : i + 1); ++r) {
+            const double w = rec_sub(__ldcg(Wn + r), alpha, __dmul_rn(__ldcg(Wc + r), sc));
+            __stcg(Wn + r, w);
+            acc = fma(w, w, acc);
+          }
       }
       const double beta = sqrt(grid_sync<true>(acc, a.gs, epoch, sh));
       if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -162,7 +225,8 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_dense_kernel(const DenseOp op
   unsigned int epoch = a.st->epoch;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t lo, hi;
-  cta_chunk(op.n, lo, hi);
+  cta_chunk(dense_units(op), lo, hi);
+  const uint32_t rlo = op.cplx ? 2 * lo : lo, rhi = op.cplx ? 2 * hi : hi;
   double* const buf0 = a.buf[0];
   double* const buf1 = a.buf[1];
   double* const buf2 = a.buf[2];
@@ -173,7 +237,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_dense_kernel(const DenseOp op
   double sc = 1.0 / a.b_norm, sp = 1.0, bp = 0.0;
   {
     const double y0 = __ldg(a.y);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kBlock) {
+    for (uint32_t i = rlo + threadIdx.x; i < rhi; i += kBlock) {
       const double bi = __ldg(a.b + i);
       const double v = __dmul_rn(bi, sc);
       __stcg(buf1 + i, bi);
@@ -194,17 +258,15 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_dense_kernel(const DenseOp op
     const double yj = __ldg(a.y + j + 1);
     const double* sm_x = dense_stage(op, Wc, sc, smem);
     __syncthreads();
-    for (uint32_t i = lo + warp; i < hi; i += kWarps) {
-      const double t = dense_row(op, i, Wc, sc, sm_x, lane);
-      if (lane == 0) {
-        const double v = __dmul_rn(__ldcg(Wc + i), sc);
-        const double w = rec_sub(rec_sub(t, bp, __dmul_rn(__ldcg(Wp + i), sp)), alpha, v);
+    for (uint32_t i = lo + warp; i < hi; i += kWarps)
+      dense_unit(op, i, Wc, sc, sm_x, lane, [&](uint32_t r, double t) {
+        const double v = __dmul_rn(__ldcg(Wc + r), sc);
+        const double w = rec_sub(rec_sub(t, bp, __dmul_rn(__ldcg(Wp + r), sp)), alpha, v);
         const double vn = __dmul_rn(w, sinv);
-        __stcg(Wn + i, w);
-        __stcg(a.x + i, __dadd_rn(__ldcg(a.x + i), __dmul_rn(yj, vn)));
-        if (WITH_V) __stcs(Vcol + i, vn);
-      }
-    }
+        __stcg(Wn + r, w);
+        __stcg(a.x + r, __dadd_rn(__ldcg(a.x + r), __dmul_rn(yj, vn)));
+        if (WITH_V) __stcs(Vcol + r, vn);
+      });
     grid_sync<false>(0.0, a.gs, epoch, sh);
     sp = sc;
     sc = sinv;
@@ -221,11 +283,8 @@ __global__ void __launch_bounds__(kBlock, 1) apply_dense_kernel(const DenseOp op
   const double* sm_x = dense_stage(op, x, 1.0, smem);
   __syncthreads();
   uint32_t lo, hi;
-  cta_chunk(op.n, lo, hi);
-  for (uint32_t i = lo + warp; i < hi; i += kWarps) {
-    const double t = dense_row(op, i, x, 1.0, sm_x, lane);
-    if (lane == 0) y[i] = t;
-  }
+  cta_chunk(dense_units(op), lo, hi);
+  for (uint32_t i = lo + warp; i < hi; i += kWarps) dense_unit(op, i, x, 1.0, sm_x, lane, [&](uint32_t r, double t) { y[r] = t; });
 }
 
 }  // namespace tpl

@@ -666,10 +666,31 @@ int tpl_op_from_csc(size_t n, const uint64_t* colptr, const uint64_t* rowidx, co
   return TPL_OK;
 }
 
+namespace {
+int dense_operator(size_t n, const double* a, size_t lda, bool cplx, int device, tpl_op** out);
+}
 int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op** out) {
+  return dense_operator(n, a, lda, false, device, out);
+}
+int tpl_op_from_dense_hermitian(size_t n, const double* a, size_t lda, int device, tpl_op** out) {
+  return dense_operator(n, a, lda, true, device, out);
+}
+int tpl_op_is_complex(const tpl_op* op) { return op && op->format == 3 && op->dense.cplx ? 1 : 0; }
+int tpl_op_from_diagonal(size_t n, const double* diag, int device, tpl_op** out) {
+  tpl::clear_error();
+  if (!out || (n && !diag)) return fail(TPL_ERR_PANIC, "null argument");
+  std::vector<uint64_t> colptr(n + 1), rowidx(n);
+  for (size_t i = 0; i < n; ++i) colptr[i] = rowidx[i] = i;
+  colptr[n] = n;
+  return tpl_op_from_csc(n, colptr.data(), rowidx.data(), diag, device, out);
+}
+namespace {
+// n = rows of the matrix (complex rows when cplx); the handle's vectors have n (2 n when cplx) doubles
+int dense_operator(size_t n, const double* a, size_t lda, bool cplx, int device, tpl_op** out) {
   tpl::clear_error();
   if (!out || (n && !a)) return fail(TPL_ERR_PANIC, "null argument");
-  if (n == 0 || n >= 0x7fffffffull || lda < n)
+  const size_t w = cplx ? 2 : 1;  // doubles per entry
+  if (n == 0 || n * w >= 0x7fffffffull || lda < n)
     return fail(TPL_ERR_DIMENSION_MISMATCH, "Dimension mismatch: operator has %zu columns but vector has %zu rows.", n, lda);
   tpl_op* op = new tpl_op;
   int rc = open_device(op, device);
@@ -678,17 +699,18 @@ int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op*
     return rc;
   }
   op->format = 3;
-  op->n = (uint32_t)n;
+  op->n = (uint32_t)(n * w);
   double* ad = nullptr;
-  rc = dev_alloc(op, &ad, n * n);
-  if (!rc && cudaMemcpy2D(ad, n * sizeof(double), a, lda * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice) != cudaSuccess)
+  rc = dev_alloc(op, &ad, n * n * w);
+  if (!rc && cudaMemcpy2D(ad, n * w * sizeof(double), a, lda * w * sizeof(double), n * w * sizeof(double), n, cudaMemcpyHostToDevice) != cudaSuccess)
     rc = fail(TPL_ERR_CUDA, "CUDA error: copying the dense operator to the device failed");
-  op->dense.n = (uint32_t)n;
+  op->dense.n = (uint32_t)(n * w);
+  op->dense.cplx = cplx ? 1u : 0u;
   op->dense.lda = n;
   op->dense.a = ad;
-  op->dense.stage = n * sizeof(double) <= kSmemBudget ? 1u : 0u;
-  op->smem_bytes = op->dense.stage ? n * sizeof(double) : 0;
-  op->matrix_bytes = 8ull * n * n;
+  op->dense.stage = n * w * sizeof(double) <= kSmemBudget ? 1u : 0u;
+  op->smem_bytes = op->dense.stage ? n * w * sizeof(double) : 0;
+  op->matrix_bytes = 8ull * w * n * n;
   if (!rc) rc = finish_setup(op);
   if (rc) {
     std::string keep = tpl::g_err;
@@ -699,6 +721,7 @@ int tpl_op_from_dense(size_t n, const double* a, size_t lda, int device, tpl_op*
   *out = op;
   return TPL_OK;
 }
+}  // namespace
 
 namespace {
 constexpr size_t kDeviceBuildArcs = 1u << 20;  // from here on the tables are built on the device

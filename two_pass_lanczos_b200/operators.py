@@ -14,10 +14,18 @@ def _vec_ptr(v):
     """(pointer, keepalive, is_torch) for a host numpy vector or a torch tensor (host or CUDA)."""
     if hasattr(v, "data_ptr"):  # torch tensor; CUDA tensors are consumed in place (no copy)
         t = v.contiguous()
+        if str(t.dtype) == "torch.complex128":  # n complex numbers = 2 n doubles, interleaved (Hermitian operators)
+            import torch
+
+            t = torch.view_as_real(t).reshape(-1)
         if str(t.dtype) != "torch.float64":
-            raise TypeError("vectors must be float64")
+            raise TypeError("vectors must be float64 (complex128 for a Hermitian operator)")
         return C.c_void_p(t.data_ptr()), t, True
-    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+    a = np.asarray(v)
+    if np.iscomplexobj(a):
+        a = np.ascontiguousarray(a.astype(np.complex128, copy=False).reshape(-1)).view(np.float64)
+    else:
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
     return C.c_void_p(a.ctypes.data), a, False
 
 
@@ -34,6 +42,8 @@ class LinOp:
         """`_vec_ptr` plus the two checks a bare pointer cannot carry: the vector has nrows() entries (else the reference's
         DimensionMismatch, src/error.rs:29-35) and, for a CUDA tensor, the handle works on torch's CURRENT stream so that
         it is ordered after the kernels that produced the tensor and before the ones that will consume the result."""
+        if self.is_complex and not hasattr(v, "data_ptr") and not np.iscomplexobj(v) and np.size(v) * 2 == self.nrows():
+            v = np.asarray(v, dtype=np.complex128)  # a real vector for a Hermitian operator
         ptr, keep, is_torch = _vec_ptr(v)
         _lib.check(_lib.load().tpl_op_check_len(self._h, int(keep.numel()) if is_torch else int(keep.shape[0])))
         if is_torch and keep.is_cuda:
@@ -43,6 +53,23 @@ class LinOp:
             if self._stream != cur:
                 self.set_stream(cur)
         return ptr, keep, is_torch
+
+    @property
+    def is_complex(self) -> bool:
+        """Hermitian operator: vectors are complex128 arrays (stored interleaved, nrows() = 2 x their length)."""
+        if getattr(self, "_cplx", None) is None:
+            self._cplx = bool(_lib.load().tpl_op_is_complex(self._h))
+        return self._cplx
+
+    def _out(self, x):
+        """Result vectors of a Hermitian operator go back as complex128 views of the interleaved storage."""
+        if not self.is_complex:
+            return x
+        if hasattr(x, "data_ptr"):
+            import torch
+
+            return torch.view_as_complex(x.reshape(*x.shape[:-1], x.shape[-1] // 2, 2))
+        return x.view(np.complex128)
 
     # -- construction ---------------------------------------------------------------------------
     @classmethod
@@ -75,6 +102,26 @@ class LinOp:
         return cls(h)
 
     @classmethod
+    def from_dense_hermitian(cls, a, device: int = -1) -> "LinOp":
+        """Dense complex Hermitian operator (`T: ComplexField`, src/algorithms/mod.rs:167): vectors in and out are complex128,
+        alpha / beta stay real.  16 n^2 bytes per product."""
+        a = np.asfortranarray(np.asarray(a, dtype=np.complex128))
+        if a.ndim != 2 or a.shape[0] != a.shape[1]:
+            raise ValueError("a square matrix is required")
+        h = C.c_void_p()
+        _lib.check(_lib.load().tpl_op_from_dense_hermitian(a.shape[0], C.cast(a.ctypes.data, c_dp), a.shape[0], device,
+                                                           C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_diagonal(cls, diag, device: int = -1) -> "LinOp":
+        """diag(d): the synthetic spectra of src/bin/stability.rs / orthogonality.rs."""
+        diag = np.ascontiguousarray(diag, dtype=np.float64)
+        h = C.c_void_p()
+        _lib.check(_lib.load().tpl_op_from_diagonal(len(diag), diag.ctypes.data_as(c_dp), device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
     def from_kkt(cls, m, p, tail, head, d, device: int = -1) -> "LinOp":
         tail = np.ascontiguousarray(tail, dtype=np.uint32)
         head = np.ascontiguousarray(head, dtype=np.uint32)
@@ -99,10 +146,10 @@ class LinOp:
         if is_torch and keep.is_cuda:
             y = keep.new_empty(keep.shape)
             _lib.check(_lib.load().tpl_op_apply(self._h, xp, C.c_void_p(y.data_ptr())))
-            return y
+            return self._out(y)
         y = np.empty(self.nrows())
         _lib.check(_lib.load().tpl_op_apply(self._h, xp, C.c_void_p(y.ctypes.data)))
-        return y
+        return self._out(y)
 
     # -- engine knobs / introspection -----------------------------------------------------------------
     def set_stream(self, cuda_stream: int):

@@ -65,7 +65,7 @@ def _solve(entry: str, operator: LinOp, b, k: int, f_tk_solver):
 
         raise LanczosError(6, f"The user-provided f(T_k) solver failed: {errors[0]}")
     _lib.check(rc)
-    return x
+    return operator._out(x)
 
 
 def lanczos(operator: LinOp, b, k: int, f_tk_solver):
