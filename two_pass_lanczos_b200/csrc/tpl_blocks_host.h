@@ -268,8 +268,10 @@ inline void build_blocks(size_t m, size_t p, const uint32_t* tail, const uint32_
   std::vector<std::vector<uint4>> thdr(Gc);
   std::vector<std::vector<uint32_t>> lent(Gc), piece(Gc);
   const uint32_t padded_max = (uint32_t)((max_cell + kBStage - 1) / kBStage * kBStage);
-  // at least ~8 tiles per cell, so that the fold of one tile overlaps the stream of the next also on small instances
-  uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max / 8 + 1023) / 1024 * 1024));
+  // the largest tile that fits (up to the cell itself): per-tile hand-offs and depth phases cost more than the overlap of
+  // fold and stream gains, at every size (1 M arcs: 0.47 of the HBM peak with one 3072-arc tile rule against 0.43 with
+  // eight tiles per cell; 3 M arcs: 0.71 against 0.60)
+  uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max + 1023) / 1024 * 1024));
   if (const char* e = std::getenv("TPL_BLOCK_T")) want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (uint32_t)std::atoi(e) / 1024 * 1024));  // tuning experiments
   if (const char* e = std::getenv("TPL_BLOCK_NTB")) h.ntb = std::min<uint32_t>(kBMaxTileBufs, std::max<uint32_t>(2, (uint32_t)std::atoi(e)));  // tuning experiments
   bool done = false;

@@ -464,7 +464,7 @@ inline int build_blocks_device(size_t m, size_t p, const uint32_t* tail, const u
   TPL_BUILD_TRY(cudaStreamSynchronize(stream));
   // 4. tile size (the rule of build_blocks) and the lists
   const uint32_t padded_max = (uint32_t)((max_cell + kBStage - 1) / kBStage * kBStage);
-  uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max / 8 + 1023) / 1024 * 1024));
+  uint32_t want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (padded_max + 1023) / 1024 * 1024));
   if (const char* e = std::getenv("TPL_BLOCK_T")) want = std::min<uint32_t>(4096, std::max<uint32_t>(1024, (uint32_t)std::atoi(e) / 1024 * 1024));
   if (const char* e = std::getenv("TPL_BLOCK_NTB")) h.ntb = std::min<uint32_t>(kBMaxTileBufs, std::max<uint32_t>(2, (uint32_t)std::atoi(e)));
   uint32_t *ne_dev = nullptr, *fail_dev = nullptr;

@@ -1349,13 +1349,14 @@ int launch_cells(tpl_op* op, KERNEL kernel, const ARGS& args, size_t smem) {
   op->launches += 1;
   return TPL_OK;
 }
-// mode 0: the blocked streaming kernels from ~1.5M arcs on one GPU (cells of >= 10k arcs; measured: 0.61 vs 0.56 of the HBM
-// roofline at 2M arcs, 0.92 vs 0.74 at 20M, but 0.40 vs 0.48 at 1M, where a sweep is only a few tiles long), the tiled ones
-// below; mode 5 forces the blocked kernels, mode 2 the tiled ones.  A sharded handle runs the family that owns its exchange block.
+// mode 0: the blocked streaming kernels from ~1M arcs on one GPU (cells of >= 6.5k arcs; measured: 0.51 vs 0.49 of the HBM
+// roofline at 1M arcs, 0.67 vs 0.57 at 2M, 0.95 vs 0.74 at 20M, but 0.37 vs 0.38 at 700k, where a sweep is two tiles long), the
+// tiled ones below; mode 5 forces the blocked kernels, mode 2 the tiled ones.  A sharded handle runs the family that owns its
+// exchange block.
 bool use_blocked(const tpl_op* op) {
   if (op->format != 2 || !op->blocked_ok) return false;
   if (op->mode == 5 || (op->comm && op->mode == 0)) return true;
-  return op->mode == 0 && (op->blk_max_cell >= 10240 || !op->tiled_ok);
+  return op->mode == 0 && (op->blk_max_cell >= 6528 || !op->tiled_ok);
 }
 bool use_tiled(const tpl_op* op) { return op->format == 2 && op->tiled_ok && (op->mode == 0 || op->mode == 2); }
 
