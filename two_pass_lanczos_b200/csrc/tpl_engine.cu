@@ -164,7 +164,7 @@ struct tpl_op {
   double* x_d = nullptr;
   double* coef_d = nullptr;  // [header | alphas cap | betas cap | y cap]
   size_t coef_cap = 0;
-  uint4* slots = nullptr;      // grid-sync slots [2][G]
+  uint4* slots = nullptr;      // grid-sync lines [2][G][kSlotAtoms]
   bool resident_ok = false;    // the per-CTA slice of the incidence operator fits in shared memory
   tpl::ResidentOp res{};
   size_t smem_res1 = 0, smem_res2 = 0;
@@ -384,7 +384,7 @@ int open_device(tpl_op* op, int device) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (!prop.cooperativeLaunch) return fail(TPL_ERR_CUDA, "CUDA error: device lacks cooperative launch");
-  op->G = prop.multiProcessorCount;
+  op->G = std::min<int>(prop.multiProcessorCount, (int)tpl::kMaxGridCtas);  // one CTA per SM (grid_sync gathers at most kMaxGridCtas payloads)
   CUDA_TRY(cudaStreamCreateWithFlags(&op->stream, cudaStreamNonBlocking));
   for (auto& ev : op->ev) CUDA_TRY(cudaEventCreate(&ev));
   return TPL_OK;
@@ -459,8 +459,8 @@ int finish_setup(tpl_op* op) {
     if (int rc = dev_alloc(op, &b, n)) return rc;
   if (int rc = dev_alloc(op, &op->b_d, n)) return rc;
   if (int rc = dev_alloc(op, &op->x_d, n)) return rc;
-  if (int rc = dev_alloc(op, &op->slots, 2 * (size_t)op->G)) return rc;
-  CUDA_TRY(cudaMemset(op->slots, 0, sizeof(uint4) * 2 * op->G));
+  if (int rc = dev_alloc(op, &op->slots, 2 * (size_t)op->G * tpl::kSlotAtoms)) return rc;
+  CUDA_TRY(cudaMemset(op->slots, 0, sizeof(uint4) * 2 * op->G * tpl::kSlotAtoms));
   if (int rc = ensure_coef(op, 1024)) return rc;
   // opt in to the dynamic shared memory the kernels need and check the grid is co-resident
   const size_t smem = op->smem_bytes;
@@ -986,7 +986,7 @@ int tpl_op_from_kkt(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   if (!rc && p >= 1 && p < (1u << 17) && !(op->blocked_ok && op->blk_max_cell >= 4 * 10240)) {
     int max_optin = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
-    const long budget = (long)max_optin - 2048 - (long)(2 * p + 2 * tpl::kMaxPieces) * 8;
+    const long budget = (long)max_optin - 3072 - (long)(2 * p + 2 * tpl::kMaxPieces) * 8;  // static shared memory of the kernels + margin
     const uint32_t step = tpl::kUnrollB * tpl::kStreamThreads;  // a tile is a whole number of the largest stream batch
     uint32_t T = budget > 0 ? (uint32_t)std::min<long>(8192 / step * step, budget / 16 / step * step) : 0;  // two tile buffers
     const size_t A = (m + op->G - 1) / op->G;
@@ -1455,7 +1455,7 @@ int reset_sync_state(tpl_op* op) {
   st.status = tpl::ST_RUNNING;
   st.epoch = op->fab_connected ? op->fab_epoch : 0;
   std::memcpy(op->h_pin, &st, sizeof st);
-  CUDA_TRY(cudaMemsetAsync(op->slots, 0, sizeof(uint4) * 2 * op->G, op->stream));
+  CUDA_TRY(cudaMemsetAsync(op->slots, 0, sizeof(uint4) * 2 * op->G * tpl::kSlotAtoms, op->stream));
   CUDA_TRY(cudaMemcpyAsync(op->coef_d, op->h_pin, sizeof st, cudaMemcpyHostToDevice, op->stream));
   return TPL_OK;
 }

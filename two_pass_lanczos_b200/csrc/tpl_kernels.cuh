@@ -80,7 +80,7 @@ struct Trace {  // optional per-CTA phase timestamps (diagnostics; buf == nullpt
 constexpr int kTraceMarks = 64;  // 0..31 thread 0 of the CTA, 32..47 / 48..62 lane 0 of warp w (two stamps), 63 globaltimer
 
 struct GridSync {
-  uint4* slots;  // [2][G] {payload lo, epoch, payload hi, epoch}, double-buffered by epoch parity
+  uint4* slots;  // [2][G][kSlotAtoms] one 128-byte line of {payload lo, epoch, payload hi, epoch} atoms per CTA, double-buffered by epoch parity
   Trace trace;
   int trace_step;  // step the marks taken inside grid_sync belong to
   int trace_base;  // first mark index used by this grid_sync call
@@ -163,25 +163,32 @@ __device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint4* p) {
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+constexpr unsigned int kMaxGridCtas = 160;  // CTAs of a persistent grid (one per SM)
+constexpr unsigned int kSlotAtoms = 8;      // 16-byte atoms of a CTA's barrier line
 struct CtaShared {
   double warp_part[kWarps];
   double result;
+  double gather[kMaxGridCtas];  // the payloads of all CTAs (grid_sync)
 };
 
-// Grid-wide sum (REDUCE) and/or barrier.  After a CTA-wide __syncthreads, lane 0 of warp 0 publishes ONE
-// 16-byte slot holding the CTA's partial sum and the epoch twice ({lo, epoch, hi, epoch}: each 8-byte half
-// carries its own flag, so a reader never combines halves of different epochs -- the layout of NCCL's LL
-// protocol).  Warp 0 of every CTA then polls all G slots, five independent loads per lane per round, and adds
-// the payloads in a fixed order: the result is identical in every CTA and from run to run.  Slots are
-// double-buffered by epoch parity (no CTA can be two episodes ahead of another).  No atomics.
+// Grid-wide sum (REDUCE) and/or barrier.  Every CTA owns one 128-byte LINE per epoch parity: eight 16-byte atoms
+// {payload lo, epoch, payload hi, epoch} -- each 8-byte half carries its own flag, so a reader never combines halves of
+// different epochs (the layout of NCCL's LL protocol) -- all holding the CTA's partial sum.  After a CTA-wide __syncthreads
+// eight lanes publish the line in ONE store instruction; thread t of every CTA then polls line t (atom blockIdx.x mod 8, so
+// that the G readers of a line spread over its four sectors), the payloads meet in shared memory and every warp adds them in
+// the same fixed order: the result is identical in every CTA and from run to run.  Double-buffered by epoch parity (no CTA
+// can be two episodes ahead of another).  No atomics.
+// Measured (scripts/ubench/sync_bench.cu, 148 CTAs): 16-byte slots packed 8 to a line, polled by one warp -- the first
+// form of this barrier -- 5 200 cycles; whole lines polled by a thread each ~2 300: partially written 32-byte sectors and
+// 148 pollers on 19 hot lines were the cost, not latency.
 //   FENCED = true : full barrier semantics for plain global data written before the call (release fence before
-//                   the slot is published, acquire fence after all slots were seen) -- streaming kernels.
-//   FENCED = false: pure all-reduce of self-validating slots; nothing else is ordered -- dataflow kernels, whose
+//                   the line is published, acquire fence after all lines were seen) -- streaming kernels.
+//   FENCED = false: pure all-reduce of self-validating lines; nothing else is ordered -- dataflow kernels, whose
 //                   other exchanged data carries its own tags.
 template <bool REDUCE, bool FENCED = true>
 __device__ __forceinline__ double grid_sync(double v, const GridSync& gs, unsigned int& epoch, CtaShared& sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned int G = gridDim.x;
+  const unsigned int G = gridDim.x;  // <= kMaxGridCtas (checked at launch)
   epoch += 1;
   if (REDUCE) {
     v = warp_sum(v);
@@ -189,57 +196,41 @@ __device__ __forceinline__ double grid_sync(double v, const GridSync& gs, unsign
   }
   __syncthreads();
   trace_mark(gs.trace, gs.trace_step, gs.trace_base + 0);
+  uint4* lines = gs.slots + (size_t)(epoch & 1u) * G * kSlotAtoms;
   if (warp == 0) {
-    uint4* slots = gs.slots + (size_t)(epoch & 1u) * G;
     double t = 0.0;
     if (REDUCE) {
       t = lane < kWarps ? sh.warp_part[lane] : 0.0;
       t = warp_sum(t);
     }
-    if (lane == 0) {
+    if (lane < (int)kSlotAtoms) {
       const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
-      if (FENCED) fence_acq_rel_gpu();
-      st_relaxed_gpu_v4(slots + blockIdx.x, make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
-    }
-    trace_mark(gs.trace, gs.trace_step, gs.trace_base + 1);
-    double s = 0.0;
-    for (unsigned int base = 0; base < G; base += 160) {
-      uint4 f[5];
-      unsigned int spins = 0;
-      for (;;) {
-        // five independent loads per lane per round (no short-circuit: one L2 round trip per round)
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const unsigned int i = base + lane + 32 * q;
-          f[q] = ld_relaxed_gpu_v4(slots + (i < G ? i : G - 1));
-        }
-        bool ok = true;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const unsigned int i = base + lane + 32 * q;
-          ok = ok & ((i >= G) | ((f[q].y == epoch) & (f[q].w == epoch)));
-        }
-        if (ok) break;
-        if (++spins > kSpinLimit) __trap();
-      }
-      if (REDUCE) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-          if (base + lane + 32 * q < G)
-            s += __longlong_as_double((long long)(((unsigned long long)f[q].z << 32) | f[q].x));
-      }
-    }
-    __syncwarp();
-    trace_mark(gs.trace, gs.trace_step, gs.trace_base + 2);
-    if (FENCED) fence_acq_rel_gpu();
-    if (REDUCE) {
-      s = warp_sum(s);
-      if (lane == 0) sh.result = s;
+      if (FENCED) fence_acq_rel_gpu();  // release: orders the CTA's earlier writes (cumulative over the barrier above)
+      st_relaxed_gpu_v4(lines + (size_t)blockIdx.x * kSlotAtoms + lane, make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
     }
   }
+  trace_mark(gs.trace, gs.trace_step, gs.trace_base + 1);
+  for (unsigned int i = threadIdx.x; i < G; i += kBlock) {
+    const uint4* src = lines + (size_t)i * kSlotAtoms + (blockIdx.x & (kSlotAtoms - 1));
+    uint4 f;
+    unsigned int spins = 0;
+    for (;;) {
+      f = ld_relaxed_gpu_v4(src);
+      if ((f.y == epoch) & (f.w == epoch)) break;
+      if (++spins > kSpinLimit) __trap();
+    }
+    if (FENCED) fence_acq_rel_gpu();  // acquire: the poller has seen the line; the barrier below passes it on to the CTA
+    if (REDUCE) sh.gather[i] = __longlong_as_double((long long)(((unsigned long long)f.z << 32) | f.x));
+  }
   __syncthreads();
+  trace_mark(gs.trace, gs.trace_step, gs.trace_base + 2);
+  double s = 0.0;
+  if (REDUCE) {  // every warp adds the same numbers in the same order
+    for (unsigned int i = lane; i < G; i += 32) s += sh.gather[i];
+    s = warp_sum(s);
+  }
   trace_mark(gs.trace, gs.trace_step, gs.trace_base + 3);
-  return REDUCE ? sh.result : 0.0;
+  return REDUCE ? s : 0.0;
 }
 
 // ----------------------------------------------------------------------------- operator products
