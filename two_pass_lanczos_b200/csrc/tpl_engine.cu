@@ -413,9 +413,10 @@ int ensure_coef(tpl_op* op, size_t k) {
 // ONE family per handle -- the blocked streaming kernels when their layout exists, else the tiled ones -- whose block is
 // then re-allocated for `world` ranks and exported (op->fab_block).
 tpl::Fabric& active_fabric(tpl_op* op) { return op->blocked_ok ? op->blk.tl.fab : op->tile.fab; }
-void fabric_layout(const tpl_op* op, bool blocked, const tpl::Fabric& f, size_t& part, size_t& nodes) {
+void fabric_layout(const tpl_op* op, bool blocked, const tpl::Fabric& f, size_t& part, size_t& nodes, size_t& slot_off) {
   part = blocked ? 2 * (size_t)f.Bp * f.world * (op->blk.GC + op->blk.GR) : 2 * (size_t)f.Gtot * f.Bp;
   nodes = 2 * (size_t)op->inc.p + 2;
+  slot_off = ((part + nodes) * sizeof(double) + 127) / 128 * 128;  // barrier lines: 128-byte aligned
 }
 int alloc_fabric(tpl_op* op, bool blocked, int rank, int world, void** block_slot) {
   const size_t p = op->inc.p;
@@ -432,16 +433,16 @@ int alloc_fabric(tpl_op* op, bool blocked, int rank, int world, void** block_slo
   f.world = world;
   f.Gtot = (uint32_t)(world * G);
   f.Bp = (uint32_t)(G * R);
-  size_t part, nodes;
-  fabric_layout(op, blocked, f, part, nodes);
-  const size_t bytes = (part + nodes) * sizeof(double) + 2 * (size_t)f.Gtot * sizeof(uint4);
+  size_t part, nodes, slot_off;
+  fabric_layout(op, blocked, f, part, nodes, slot_off);
+  const size_t bytes = slot_off + 2 * (size_t)f.Gtot * tpl::kSlotAtoms * sizeof(uint4);
   char* block = nullptr;
   if (int rc = dev_alloc(op, &block, bytes)) return rc;
   CUDA_TRY(cudaMemset(block, 0, bytes));
   *block_slot = block;
   f.partials[rank] = reinterpret_cast<double*>(block);
   f.nodebuf[rank] = f.partials[rank] + part;
-  f.slots[rank] = reinterpret_cast<uint4*>(f.nodebuf[rank] + nodes);
+  f.slots[rank] = reinterpret_cast<uint4*>(block + slot_off);
   return TPL_OK;
 }
 int setup_local_fabric(tpl_op* op, bool blocked) { return alloc_fabric(op, blocked, 0, 1, blocked ? &op->blk_block : &op->tile_block); }
@@ -2253,8 +2254,8 @@ int tpl_op_fabric_import(tpl_op* op, const uint8_t* handles, int count) {
   if (op->fab_connected) return TPL_OK;
   DeviceGuard g(op->device);
   tpl::Fabric& f = active_fabric(op);
-  size_t part, nodes;
-  fabric_layout(op, op->blocked_ok, f, part, nodes);
+  size_t part, nodes, slot_off;
+  fabric_layout(op, op->blocked_ok, f, part, nodes, slot_off);
   for (int r = 0; r < op->world; ++r) {
     if (r == op->rank) continue;
     cudaIpcMemHandle_t h;
@@ -2264,7 +2265,7 @@ int tpl_op_fabric_import(tpl_op* op, const uint8_t* handles, int count) {
     op->fab_peers.push_back(peer);
     f.partials[r] = reinterpret_cast<double*>(peer);
     f.nodebuf[r] = f.partials[r] + part;
-    f.slots[r] = reinterpret_cast<uint4*>(f.nodebuf[r] + nodes);
+    f.slots[r] = reinterpret_cast<uint4*>(static_cast<char*>(peer) + slot_off);
   }
   op->fab_connected = true;
   op->fab_epoch = 0;

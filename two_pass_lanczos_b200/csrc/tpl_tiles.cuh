@@ -297,8 +297,8 @@ __device__ __forceinline__ uint4 ld_acquire_sys_v4(const uint4* p) {
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
-// Barrier + all-reduce over the CTAs of ALL ranks (world > 1): the same self-validating 16-byte slots as grid_sync, but every
-// CTA pushes its slot into every rank's replica over NVLink (lane r -> rank r) and polls only its local replica.  System-scope
+// Barrier + all-reduce over the CTAs of ALL ranks (world > 1): the same self-validating lines as grid_sync, but every
+// CTA pushes its line into every rank's replica over NVLink and polls only its local replica.  System-scope
 // fences order the peer-memory data written before the call (partials, node values) before the slot, and the local reads
 // after the poll.  The payloads are added in slot order: the result is identical in every CTA of every rank.
 // FENCED = false: pure barrier + all-reduce, for the alpha reduction of pass 1 -- no peer memory is written in the phase
@@ -323,15 +323,20 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
     const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
     const uint32_t src = f.rank * gridDim.x + blockIdx.x;
     if (FENCED) fence_acq_rel_sys();
-    if (lane < f.world)
-      st_relaxed_sys_v4(f.slots[lane] + (size_t)(epoch & 1u) * f.Gtot + src,
-                        make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
+    // a whole 128-byte line per (source CTA, target rank): eight lanes store its eight atoms in one instruction, four ranks
+    // per instruction (as in grid_sync: partially written sectors and packed slots were the cost of the first form)
+    for (int r0 = 0; r0 < f.world; r0 += 4) {
+      const int r = r0 + (lane >> 3);
+      if (r < f.world)
+        st_relaxed_sys_v4(f.slots[r] + ((size_t)(epoch & 1u) * f.Gtot + src) * kSlotAtoms + (lane & 7),
+                          make_uint4((unsigned)bits, epoch, (unsigned)(bits >> 32), epoch));
+    }
   }
   // The slots are polled in chunks of 160 (five per lane); chunk w by warp w, all chunks at the same time (8 ranks: 1184
   // slots, one L2 round trip instead of eight).  Slot order inside a chunk is lane-strided, the lanes are combined by the
   // xor tree and the chunk sums are added in chunk order: a fixed order, identical in every CTA of every rank.
   const uint32_t nchunks = (f.Gtot + 159) / 160;
-  const uint4* slots = f.slots[f.rank] + (size_t)(epoch & 1u) * f.Gtot;
+  const uint4* slots = f.slots[f.rank] + (size_t)(epoch & 1u) * f.Gtot * kSlotAtoms + (blockIdx.x & (kSlotAtoms - 1));
   for (uint32_t ch = warp; ch < nchunks; ch += kWarps) {
     const uint32_t base = ch * 160;
     uint4 q4[5];
@@ -342,7 +347,8 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
         const uint32_t i = base + lane + 32 * q;
         // FENCED: acquire loads pair with the peers' fence + store (a trailing fence would also wait for the acknowledgement
         // of our own slot stores, a whole NVLink round trip)
-        q4[q] = FENCED ? ld_acquire_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1)) : ld_relaxed_sys_v4(slots + (i < f.Gtot ? i : f.Gtot - 1));
+        const uint4* src_line = slots + (size_t)(i < f.Gtot ? i : f.Gtot - 1) * kSlotAtoms;  // one atom of the source's line
+        q4[q] = FENCED ? ld_acquire_sys_v4(src_line) : ld_relaxed_sys_v4(src_line);
       }
       bool ok = true;
 #pragma unroll
