@@ -217,9 +217,10 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_csr_kernel(const SellOp op, c
           if (WITH_V) __stcs(Vcol + i, v);
         }
       }
-      const double alpha = grid_sync<true>(acc, a.gs, epoch, sh);
+      // (all-reduce only: phase B reads what this CTA wrote in phase A, ordered by the CTA barriers inside the call)
+      const double alpha = grid_sync<true, false>(acc, a.gs, epoch, sh);
 
-      // ---------------- phase B: w = w~ - alpha v, beta partial (same row ownership: every thread re-reads the w~ it wrote)
+      // ---------------- phase B: w = w~ - alpha v, beta partial (same row ownership: the CTA re-reads the w~ it wrote)
       acc = 0.0;
 #pragma unroll 4
       for (uint32_t i = rlo + threadIdx.x; i < rhi; i += kBlock) {

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_dense_kernel(const DenseOp op
           __stcg(Wn + r, wt);
           if (WITH_V) __stcs(Vcol + r, v);
         });
-      const double alpha = grid_sync<true>(acc, a.gs, epoch, sh);
+      const double alpha = grid_sync<true, false>(acc, a.gs, epoch, sh);  // all-reduce only: phase B reads this CTA's own rows
       // ---------------- phase B: w = w~ - alpha v, beta partial (same row ownership: lane 0 of the row's warp wrote w~)
       acc = 0.0;
       for (uint32_t i = lo + warp; i < hi; i += kWarps) {

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_kernel(const OP op, const Pas
           if (WITH_V) __stcs(Vcol + i, v);
         }
       }
-      const double alpha = grid_sync<true>(acc, a.gs, epoch, sh);
+      const double alpha = grid_sync<true, false>(acc, a.gs, epoch, sh);  // all-reduce only: phase B reads this CTA's own rows
 
       // ---------------- phase B (same row ownership: every thread re-reads the w~ it wrote)
       acc = 0.0;

@@ -381,7 +381,7 @@ __device__ __forceinline__ double fabric_sync(double v, const TileOp& to, unsign
 template <bool REDUCE, bool FENCED = true>
 __device__ __forceinline__ double tile_sync(double v, const TileOp& to, const GridSync& gs, unsigned int& epoch, CtaShared& sh) {
   if (to.fab.world > 1) return fabric_sync<REDUCE, FENCED>(v, to, epoch, sh);
-  return grid_sync<REDUCE>(v, gs, epoch, sh);
+  return grid_sync<REDUCE, FENCED>(v, gs, epoch, sh);
 }
 
 // Tile loop shared by every phase that produces a new vector, warp-specialised: the STREAM warps (0..7) move the chunk
