@@ -38,19 +38,31 @@ struct SellBatch {
   bool live[kCsrU];
   double t[kCsrU];
 };
-__device__ __forceinline__ void sell_rows(const SellOp& op, uint32_t slice0, uint32_t stride, uint32_t shi, const double* X, double s,
+// First load level of a batch (slice pointers, row lengths): requested one batch AHEAD by the sweeps, so that a batch costs two
+// dependent round trips (entries, operand gathers) instead of three.
+struct SellHeads {
+  uint32_t base[kCsrU], len[kCsrU];  // len: 0xff = no short row here
+};
+__device__ __forceinline__ void sell_heads(const SellOp& op, uint32_t slice0, uint32_t stride, uint32_t shi, SellHeads& h) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < kCsrU; ++q) {
+    const uint32_t sl = slice0 + q * stride, row = sl * 32u + lane;
+    const bool in = sl < shi;
+    h.base[q] = in ? __ldg(op.sptr + sl) : 0u;
+    h.len[q] = in && row < op.n ? (uint32_t)__ldg(op.rlen + row) : 0xffu;
+  }
+}
+__device__ __forceinline__ void sell_rows(const SellOp& op, uint32_t slice0, uint32_t stride, const SellHeads& h, const double* X, double s,
                                           SellBatch& b) {
   const int lane = threadIdx.x & 31;
   uint32_t base[kCsrU], len[kCsrU];
 #pragma unroll
   for (int q = 0; q < kCsrU; ++q) {
-    const uint32_t sl = slice0 + q * stride;
-    const bool in = sl < shi;
-    b.row[q] = sl * 32u + lane;
-    base[q] = in ? __ldg(op.sptr + sl) : 0u;
-    const uint32_t l = in && b.row[q] < op.n ? (uint32_t)__ldg(op.rlen + b.row[q]) : 0xffu;
-    b.live[q] = l != 0xffu;
-    len[q] = b.live[q] ? l : 0u;
+    b.row[q] = (slice0 + q * stride) * 32u + lane;
+    base[q] = h.base[q];
+    b.live[q] = h.len[q] != 0xffu;
+    len[q] = b.live[q] ? h.len[q] : 0u;
   }
   uint32_t c[kCsrU][kCsrW];
   double a[kCsrU][kCsrW];
@@ -183,16 +195,20 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_csr_kernel(const SellOp op, c
 
       // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
       double acc = 0.0;
+      SellHeads hd, hd_next;
+      sell_heads(op, slo + warp, kWarps, shi, hd);
       for (uint32_t s0 = slo + warp; s0 < shi; s0 += kCsrU * kWarps) {
         SellBatch bt;
         double wc[kCsrU], wp[kCsrU];
+        sell_heads(op, s0 + kCsrU * kWarps, kWarps, shi, hd_next);  // the next batch's pointers and lengths
 #pragma unroll
         for (int q = 0; q < kCsrU; ++q) {  // the vectors of the four rows are requested together with the slice data
           const uint32_t i = min((s0 + q * kWarps) * 32u + lane, op.n - 1);
           wc[q] = __ldcg(Wc + i);
           wp[q] = __ldcg(Wp + i);
         }
-        sell_rows(op, s0, kWarps, shi, Wc, sc, bt);
+        sell_rows(op, s0, kWarps, hd, Wc, sc, bt);
+        hd = hd_next;
 #pragma unroll
         for (int q = 0; q < kCsrU; ++q)
           if (bt.live[q]) {
@@ -222,12 +238,27 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_csr_kernel(const SellOp op, c
 
       // ---------------- phase B: w = w~ - alpha v, beta partial (same row ownership: the CTA re-reads the w~ it wrote)
       acc = 0.0;
-#pragma unroll 4
-      for (uint32_t i = rlo + threadIdx.x; i < rhi; i += kBlock) {
-        if (__ldg(op.rlen + i) == 0xffu) continue;
-        const double w = rec_sub(__ldcg(Wn + i), alpha, __dmul_rn(__ldcg(Wc + i), sc));
-        __stcg(Wn + i, w);
-        acc = fma(w, w, acc);
+      // eight rows per thread in flight, loads unconditional (a row-length test in front of the loads serialised them: the
+      // sweep ran at 40 % of the HBM rate, ncu long-scoreboard stalls, profiles/r2_ncu_csr5M.txt)
+      for (uint32_t i0 = rlo + threadIdx.x; i0 < rhi; i0 += 8 * kBlock) {
+        double wn[8], wc[8];
+        uint32_t rl[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t i = min(i0 + u * kBlock, rhi - 1);
+          wn[u] = __ldcg(Wn + i);
+          wc[u] = __ldcg(Wc + i);
+          rl[u] = __ldg(op.rlen + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t i = i0 + u * kBlock;
+          if (i < rhi && rl[u] != 0xffu) {
+            const double w = rec_sub(wn[u], alpha, __dmul_rn(wc[u], sc));
+            __stcg(Wn + i, w);
+            acc = fma(w, w, acc);
+          }
+        }
       }
       for (uint32_t q = r0 + threadIdx.x; q < r1; q += kBlock) {
         const uint32_t i = __ldg(lr.row + q);
@@ -323,9 +354,12 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_csr_kernel(const SellOp op, c
       __stcg(a.x + i, __dadd_rn(xx, __dmul_rn(yj, vn)));
       if (WITH_V) __stcs(Vcol + i, vn);
     };
+    SellHeads hd, hd_next;
+    sell_heads(op, slo + warp, kWarps, shi, hd);
     for (uint32_t s0 = slo + warp; s0 < shi; s0 += kCsrU * kWarps) {
       SellBatch bt;
       double vc[kCsrU], vp[kCsrU], xx[kCsrU];
+      sell_heads(op, s0 + kCsrU * kWarps, kWarps, shi, hd_next);
 #pragma unroll
       for (int q = 0; q < kCsrU; ++q) {
         const uint32_t i = min((s0 + q * kWarps) * 32u + lane, op.n - 1);
@@ -333,7 +367,8 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_csr_kernel(const SellOp op, c
         vp[q] = __ldcg(Vp + i);
         xx[q] = __ldcg(a.x + i);
       }
-      sell_rows(op, s0, kWarps, shi, Vc, 1.0, bt);
+      sell_rows(op, s0, kWarps, hd, Vc, 1.0, bt);
+      hd = hd_next;
 #pragma unroll
       for (int q = 0; q < kCsrU; ++q)
         if (bt.live[q]) finish(bt.row[q], bt.t[q], vc[q], vp[q], xx[q]);
@@ -359,9 +394,13 @@ __global__ void __launch_bounds__(kBlock, 1) apply_csr_kernel(const SellOp op, c
   const int warp = threadIdx.x >> 5;
   uint32_t slo, shi;
   cta_slices(op, slo, shi);
+  SellHeads hd, hd_next;
+  sell_heads(op, slo + warp, kWarps, shi, hd);
   for (uint32_t s0 = slo + warp; s0 < shi; s0 += kCsrU * kWarps) {
     SellBatch bt;
-    sell_rows(op, s0, kWarps, shi, x, 1.0, bt);
+    sell_heads(op, s0 + kCsrU * kWarps, kWarps, shi, hd_next);
+    sell_rows(op, s0, kWarps, hd, x, 1.0, bt);
+    hd = hd_next;
 #pragma unroll
     for (int q = 0; q < kCsrU; ++q)
       if (bt.live[q]) y[bt.row[q]] = bt.t[q];
