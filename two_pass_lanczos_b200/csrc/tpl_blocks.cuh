@@ -236,8 +236,8 @@ __device__ __forceinline__ void stage_block_nodes(const BlockOp& bo, const Block
   for (uint32_t i = threadIdx.x; i < c.nt; i += kBlock) sm_st(s.node, i, __dmul_rn(__ldcg(Xnode + __ldg(bo.tbn + c.t0 + i)), sc));
   for (uint32_t i = threadIdx.x; i < c.nh; i += kBlock) sm_st(s.node, bo.PT + i, __dmul_rn(__ldcg(Xnode + __ldg(bo.hbn + c.h0 + i)), sc));
 }
-__device__ __forceinline__ void zero_block_acc(const BlockOp& bo, const BlockSmem& s) {
-  for (uint32_t i = threadIdx.x; i < bo.PT + bo.PH + kBAccPad; i += kBlock) sm_st(s.acc, i, 0.0);
+__device__ __forceinline__ void zero_block_acc(const BlockOp& bo, const BlockSmem& s, int tid = threadIdx.x, int nthreads = kBlock) {
+  for (uint32_t i = tid; i < bo.PT + bo.PH + kBAccPad; i += nthreads) sm_st(s.acc, i, 0.0);
 }
 
 // This CTA's partial sums (s.acc) -> the owners' buffers, parity `par`.  Destination-indexed: node u of rank rk keeps
@@ -257,15 +257,18 @@ __device__ __forceinline__ void publish_block_partials(const BlockOp& bo, const 
     __stcg(f.partials[rk] + ((size_t)par * f.Bp + (u - rk * f.Bp)) * SL + f.rank * per + bo.GC + c.r, sm_ld(s.acc, bo.PT + i));
   }
 }
-// T_u = sum of the world * (GC + GR) partials of an owned node: lanes stride the words, xor tree -- a fixed order
-__device__ __forceinline__ double block_node_total(const BlockOp& bo, uint32_t par, uint32_t u, int lane) {
+// T_u = sum of the world * (GC + GR) partials of an owned node: lanes stride the words, xor tree -- a fixed order.
+// block_node_lanes is the first half (the lane's share, loads only), warp_sum of it the total: the callers request the
+// shares of several nodes (and the node's other operands) before they wait for any of them.
+__device__ __forceinline__ double block_node_lanes(const BlockOp& bo, uint32_t par, uint32_t u, int lane) {
   const Fabric& f = bo.tl.fab;
   const uint32_t SL = f.world * (bo.GC + bo.GR);
   const double* Pin = f.partials[f.rank] + ((size_t)par * f.Bp + (u - f.rank * f.Bp)) * SL;
   double a = 0.0;
   for (uint32_t q = lane; q < SL; q += 32) a = __dadd_rn(a, __ldcg(Pin + q));
-  return warp_sum(a);
+  return a;
 }
+constexpr int kBOwnRounds = 2;  // owned node rows a warp has in flight
 
 // Same-tail runs of a stage, summed by the compute warp that has just produced the values (they are still in its registers):
 // lane l holds arcs l, l + 32, l + 64, l + 96 of the stage.  A run [start, start + len) adds its arcs per lane in that order,
@@ -421,10 +424,12 @@ struct RingState {
   uint32_t slot, phase;  // compute warps: ring slot and mbarrier phase of the next stage
   uint32_t lphase;       // fold warps: bit b = phase of list buffer b's mbarrier
 };
-template <int NCW, int N8, int N4, class CONSUME>
+// `pre(ftid, NFT)` runs on the fold threads before their first tile (they would otherwise wait for it): zeroing the
+// accumulators and whatever else the sweep's input does not depend on; a barrier among the fold threads follows.
+template <int NCW, int N8, int N4, class CONSUME, class PRE>
 __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
                                            const double* const (&src8)[N8], const uint32_t* const (&src4)[N4 ? N4 : 1],
-                                           CONSUME consume, RingState& rs, const Trace* tr = nullptr, int tr_step = -1) {
+                                           CONSUME consume, PRE pre, RingState& rs, const Trace* tr = nullptr, int tr_step = -1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t SPT = bo.tl.T / kBStage;  // stages per tile (a multiple of 8)
   const bool timed = tr != nullptr && tr->buf != nullptr && tr_step >= 0 && tr_step < tr->max_steps;
@@ -509,6 +514,8 @@ __device__ __forceinline__ void fold_sweep(const BlockOp& bo, const BlockSmem& s
     };
     if (c.ntiles && issuer)
       for (uint32_t u = 0; u < nl && u < c.ntiles; ++u) fetch(block_tile_hdr(s, u), u);
+    pre(ftid, NFT);
+    bar_sync_n(kBarFold, NFT);
     uint32_t b = 0, tb_i = 0;  // list buffer / tile buffer of tile t
     const uint32_t ntb = bo.ntb;
     for (uint32_t t = 0; t < c.ntiles; ++t) {
@@ -557,8 +564,6 @@ __device__ __forceinline__ void init_block_smem(const BlockOp& bo, const BlockSm
 template <int NCW>
 __device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem& s, const BlockCtx& c, uint32_t RING, uint32_t slot_bytes,
                                               const double* X, RingState& rs) {
-  zero_block_acc(bo, s);
-  __syncthreads();
   const double* const src8[1] = {X};
   const uint32_t* const src4[1] = {nullptr};
   fold_sweep<NCW, 1, 0>(
@@ -572,7 +577,7 @@ __device__ __forceinline__ void block_sums_of(const BlockOp& bo, const BlockSmem
         sts64<768>(w, x[3]);
         stage_pieces(x, desc, wt_tile, bo.tl.T, lane);
       },
-      rs);
+      [&](int ftid, int nft) __attribute__((always_inline)) { zero_block_acc(bo, s, ftid, nft); }, rs);
 }
 
 // =============================================================================================
@@ -638,6 +643,21 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
       // ---------------- phase A: w~ = A v - beta_{j-1} v_{j-1}, alpha partial
       gs.trace_step = j;
       trace_mark(gs.trace, j, 0);
+      // node rows of the owned block: the operands of the warp's first rows are requested BEFORE the node values are staged
+      // (two independent chains of L2 round trips at the top of every step; one behind the other they cost 5.7 k cycles)
+      double own_t[kBOwnRounds], own_x[kBOwnRounds], own_p[kBOwnRounds];
+#pragma unroll
+      for (int r = 0; r < kBOwnRounds; ++r) {
+        const uint32_t u = c.ulo + warp + r * kWarps;
+        own_t[r] = own_x[r] = own_p[r] = 0.0;
+        if (u < c.uhi) {
+          own_t[r] = block_node_lanes(bo, j & 1, u, lane);
+          if (lane == 0) {
+            own_x[r] = __ldcg(Xnode + u);
+            own_p[r] = __ldcg(Wp + M + u);
+          }
+        }
+      }
       stage_block_nodes(bo, s, c, Xnode, sc);
       __syncthreads();
       trace_mark(gs.trace, j, 1);
@@ -647,15 +667,24 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
         for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) __stcs(Vcol + m + u, __dmul_rn(__ldcg(Xnode + u), sc));
       }
       double acc = 0.0;
-      for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
-        const double t = __dmul_rn(sc, block_node_total(bo, j & 1, u, lane));
+      auto own_row = [&](uint32_t u, double lanes, double xn, double wpu) __attribute__((always_inline)) {
+        const double t = __dmul_rn(sc, warp_sum(lanes));
         if (lane == 0) {
-          const double v = __dmul_rn(__ldcg(Xnode + u), sc);
-          const double vp = __dmul_rn(__ldcg(Wp + M + u), sp);
+          const double v = __dmul_rn(xn, sc);
+          const double vp = __dmul_rn(wpu, sp);
           const double wt = rec_sub(t, bp, vp);
           acc = fma(v, wt, acc);
           __stcg(Wn + M + u, wt);
         }
+      };
+#pragma unroll
+      for (int r = 0; r < kBOwnRounds; ++r) {
+        const uint32_t u = c.ulo + warp + r * kWarps;
+        if (u < c.uhi) own_row(u, own_t[r], own_x[r], own_p[r]);
+      }
+      for (uint32_t u = c.ulo + warp + kBOwnRounds * kWarps; u < c.uhi; u += kWarps) {  // (more than 32 owned rows per CTA)
+        const double lanes = block_node_lanes(bo, j & 1, u, lane);
+        own_row(u, lanes, lane == 0 ? __ldcg(Xnode + u) : 0.0, lane == 0 ? __ldcg(Wp + M + u) : 0.0);
       }
       trace_mark(gs.trace, j, 2);
       for (uint32_t base = c.c0; base < c.c1; base += kUnroll * kBlock) {
@@ -695,15 +724,18 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
 
       // ---------------- phase B: w = w~ - alpha v, beta partial, partial node sums of w
       acc = 0.0;
-      zero_block_acc(bo, s);  // (aliases s.node: phase A is over)
-      for (uint32_t u = c.ulo + threadIdx.x; u < c.uhi; u += kBlock) {
-        const double v = __dmul_rn(__ldcg(Wc + M + u), sc);
-        const double w = rec_sub(__ldcg(Wn + M + u), alpha, v);
-        __stcg(Wn + M + u, w);
-        publish_node(to, p, j & 1, u, w);
-        acc = fma(w, w, acc);
-      }
-      __syncthreads();  // accumulators are zero before the first fold
+      // the fold threads zero the accumulators (they alias s.node: phase A is over) and finish the owned node rows while the
+      // compute warps already stream the first tile
+      auto phase_b_pre = [&](int ftid, int nft) __attribute__((always_inline)) {
+        zero_block_acc(bo, s, ftid, nft);
+        for (uint32_t u = c.ulo + ftid; u < c.uhi; u += nft) {
+          const double v = __dmul_rn(__ldcg(Wc + M + u), sc);
+          const double w = rec_sub(__ldcg(Wn + M + u), alpha, v);
+          __stcg(Wn + M + u, w);
+          publish_node(to, p, j & 1, u, w);
+          acc = fma(w, w, acc);
+        }
+      };
       trace_mark(gs.trace, j, 8);
       {
         const double* const src8[2] = {Wn, Wc};
@@ -732,7 +764,7 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_blocked_kernel(const Incidenc
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc = fma(w[q], w[q], acc);
             },
-            rs, &gs.trace, j);
+            phase_b_pre, rs, &gs.trace, j);
       }
       trace_mark(gs.trace, j, 9);
       publish_block_partials(bo, s, c, (j + 1) & 1);
@@ -847,27 +879,54 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
     trace_mark(gs.trace, j, 0);
 
     stage_block_nodes(bo, s, c, Xnode, 1.0);
-    zero_block_acc(bo, s);
-    if (j > 0) {
-      // the published node values are v_{j+1}, regenerated by the previous step: their share of x (and of the basis column)
-      // is added here, by every rank for its replica (each CTA its share of the nodes)
-      const double yprev = __ldg(a.y + j);
-      for (uint32_t u = vlo + threadIdx.x; u < vhi; u += kBlock) {
-        const double vn = __ldcg(Xnode + u);
-        __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(yprev, vn)));
-        if (WITH_V) __stcs(a.V + (size_t)j * a.ldv + m + u, vn);
+    // What the sweep's input does not depend on runs on the fold threads while the compute warps already stream the first
+    // tile: zeroing the accumulators, the node share of x (and of the basis column), the owned node rows.
+    auto pass2_pre = [&](int ftid, int nft) __attribute__((always_inline)) {
+      const int fw = ftid >> 5, nfw = nft >> 5;
+      double own_t[kBOwnRounds], own_x[kBOwnRounds], own_p[kBOwnRounds];  // operands of the warp's first rows, requested together
+#pragma unroll
+      for (int r = 0; r < kBOwnRounds; ++r) {
+        const uint32_t u = c.ulo + fw + r * nfw;
+        own_t[r] = own_x[r] = own_p[r] = 0.0;
+        if (u < c.uhi) {
+          own_t[r] = block_node_lanes(bo, j & 1, u, lane);
+          if (lane == 0) {
+            own_x[r] = __ldcg(Xnode + u);
+            own_p[r] = __ldcg(Vp + M + u);
+          }
+        }
       }
-    }
-    for (uint32_t u = c.ulo + warp; u < c.uhi; u += kWarps) {  // node rows of the owned block
-      const double t = __dmul_rn(sc_cur, block_node_total(bo, j & 1, u, lane));
-      if (lane == 0) {
-        const double w = rec_sub(rec_sub(t, bp, __ldcg(Vp + M + u)), alpha, __ldcg(Xnode + u));
-        const double vn = __dmul_rn(w, sinv);
-        __stcg(Vn + M + u, vn);
-        publish_node(to, p, j & 1, u, vn);
+      zero_block_acc(bo, s, ftid, nft);
+      if (j > 0) {
+        // the published node values are v_{j+1}, regenerated by the previous step: their share of x (and of the basis column)
+        // is added here, by every rank for its replica (each CTA its share of the nodes)
+        const double yprev = __ldg(a.y + j);
+        for (uint32_t u = vlo + ftid; u < vhi; u += nft) {
+          const double vn = __ldcg(Xnode + u);
+          __stcg(a.x + m + u, __dadd_rn(__ldcg(a.x + m + u), __dmul_rn(yprev, vn)));
+          if (WITH_V) __stcs(a.V + (size_t)j * a.ldv + m + u, vn);
+        }
       }
-    }
-    __syncthreads();  // node values are staged, accumulators are zero
+      auto own_row = [&](uint32_t u, double lanes, double xn, double vpu) __attribute__((always_inline)) {
+        const double t = __dmul_rn(sc_cur, warp_sum(lanes));
+        if (lane == 0) {
+          const double w = rec_sub(rec_sub(t, bp, vpu), alpha, xn);
+          const double vn = __dmul_rn(w, sinv);
+          __stcg(Vn + M + u, vn);
+          publish_node(to, p, j & 1, u, vn);
+        }
+      };
+#pragma unroll
+      for (int r = 0; r < kBOwnRounds; ++r) {
+        const uint32_t u = c.ulo + fw + r * nfw;
+        if (u < c.uhi) own_row(u, own_t[r], own_x[r], own_p[r]);
+      }
+      for (uint32_t u = c.ulo + fw + kBOwnRounds * nfw; u < c.uhi; u += nfw) {
+        const double lanes = block_node_lanes(bo, j & 1, u, lane);
+        own_row(u, lanes, lane == 0 ? __ldcg(Xnode + u) : 0.0, lane == 0 ? __ldcg(Vp + M + u) : 0.0);
+      }
+    };
+    __syncthreads();  // node values are staged
     trace_mark(gs.trace, j, 1);
     {
       const double* const src8[4] = {Vc, Vp, xc, bo.d};
@@ -921,9 +980,9 @@ __global__ void __launch_bounds__(kBlock, 1) pass2_blocked_kernel(const Incidenc
         }
       };
       if (WITH_V)
-        fold_sweep<kBComputeWarps2, 4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, rs, &gs.trace, j);
+        fold_sweep<kBComputeWarps2, 4, 2>(bo, s, c, RING, slot_bytes, src8, src4, body, pass2_pre, rs, &gs.trace, j);
       else
-        fold_sweep<kBComputeWarps2, 4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, rs, &gs.trace, j);
+        fold_sweep<kBComputeWarps2, 4, 1>(bo, s, c, RING, slot_bytes, src8, src4n, body, pass2_pre, rs, &gs.trace, j);
     }
     trace_mark(gs.trace, j, 2);
     publish_block_partials(bo, s, c, (j + 1) & 1);
