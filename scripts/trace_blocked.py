@@ -45,8 +45,8 @@ alg.lanczos_pass_one(op, b, k)
 t1 = op.trace_read()
 SYNC = ["sync: after bar", "sync: published", "sync: all slots seen", "sync: after final bar"]
 EXTRA = [(16, "compute warp 0 waits for bulk copies"), (17, "compute warp 0 waits for the fold"), (18, "compute warp 0 whole sweep"),
-         (23, "compute warp 0 consuming stages"), (19, "fold thread 0 waits for a full tile"), (21, "fold thread 0 waits for list blocks"),
-         (22, "fold thread 0 folding"), (20, "fold thread 0 whole sweep")]
+         (23, "compute warp 0 consuming stages"), (24, "compute warp 0 last stage consumed at"), (19, "fold thread 0 waits for a full tile"), (21, "fold thread 0 waits for list blocks"),
+         (22, "fold thread 0 folding"), (25, "fold thread 0 preamble done at"), (26, "fold thread 0 first tile full at"), (20, "fold thread 0 whole sweep")]
 report("pass 1 blocked", t1, list(range(15)),
        ["step start", "nodes staged", "owner rows A", "phase A arcs done"] + ["alpha " + s for s in SYNC] +
        ["owner rows B + zero acc", "phase B sweep done", "partials published"] + ["beta " + s for s in SYNC], EXTRA)
