@@ -2,8 +2,9 @@
 between the non-padding cell-order positions and the arcs, every packed tail/head word decodes to its arc inside the cell's
 node blocks (with the CSC-order and self-loop flags), cells are sorted by (tail, arc index) and padded to whole 128-arc stages,
 every non-loop arc is once on its local tail and once on its local head in the lists of its tile, the list slices have equal
-length with correct new-node flags and chain depths (check_cell_lists), and the layout does not depend on the number of host
-threads."""
+length with correct new-node flags, slot fields and chain depths, a host emulation of the kernel's list walk (running sums,
+slot flushes, scratch shares added depth by depth) over exact integer values reproduces every node sum of every tile
+(check_cell_lists), and the layout does not depend on the number of host threads."""
 import ctypes as C
 
 import numpy as np

@@ -455,6 +455,50 @@ inline int check_cell_lists(uint32_t n, uint32_t PL, const uint32_t* tl, const u
       const bool loop = tl[t0 + a] == hl[t0 + a];
       if (seen_t[a] != (loop ? 0 : 1) || seen_h[a] != (loop ? 0 : 1)) return 16;
     }
+    // The walk itself, as block_fold_tile performs it (tpl_blocks.cuh), on small integers (every sum exact): tile buffer =
+    // arc values, run sums behind them, zero slot last; every slice adds its entries into a running sum, an entry that opens
+    // a node first adds the finished sum to the slot it names (the first entry of a slice names its node instead: nothing to
+    // flush), the last sum goes to the slot of row 0; then the scratch shares, depth by depth.  The accumulators must hold
+    // +x on the tail and -x on the head of every non-loop arc.
+    {
+      const uint32_t slots = block_piece_slots(T), nacc = PL + kBAccPad + B;
+      std::vector<double> wt((size_t)T + slots, 0.0), acc(nacc, 0.0), want(PL, 0.0);
+      for (uint32_t a = 0; a < na; ++a) {
+        wt[a] = (double)((int)((t0 + a) * 7u % 13u) - 6);
+        if (tl[t0 + a] != hl[t0 + a]) {
+          want[tl[t0 + a]] += wt[a];
+          want[hl[t0 + a]] -= wt[a];
+        }
+      }
+      for (size_t r = 0; r < runs.size(); ++r)
+        for (uint32_t a = runs[r].first; a < runs[r].first + runs[r].second; ++a) wt[T + r] += wt[a];
+      const uint32_t dummy = PL;
+      for (uint32_t i = 0; i < B; ++i) {
+        const uint32_t row0 = lent[hd.x + i], depth = row0 & 0xffu;
+        if (depth) acc[PL + kBAccPad + i] = 0.0;
+        double sum = 0.0;
+        for (uint32_t q = 0; q < L; ++q) {
+          const uint32_t e = lent[hd.x + (size_t)(q + 1) * B + i];
+          const double x = wt[(e & kBEntOffMask) / 8u], val = (e & kBEntMinus) ? -x : x;
+          if (e & kBEntNew) {
+            if (q != 0) acc[(e >> kBEntNodeShift) & kBEntNodeMask] += sum;
+            sum = val;
+          } else {
+            sum += val;
+          }
+        }
+        acc[(row0 >> 8) & kBEntNodeMask] += sum;
+      }
+      for (uint32_t d = 1; d <= D; ++d)
+        for (uint32_t i = 0; i < B; ++i)
+          if ((lent[hd.x + i] & 0xffu) == d) {
+            const uint32_t e1 = lent[hd.x + B + i];
+            acc[(e1 >> kBEntNodeShift) & kBEntNodeMask] += acc[PL + kBAccPad + i];
+          }
+      (void)dummy;
+      for (uint32_t u = 0; u < PL; ++u)
+        if (acc[u] != want[u]) return 20;
+    }
   }
   return 0;
 }
