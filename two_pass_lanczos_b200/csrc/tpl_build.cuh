@@ -612,3 +612,4 @@ inline int build_node_lists_device(size_t m, size_t p, const uint32_t* tail, con
 }
 
 }  // namespace tpl
+#undef TPL_BUILD_TRY
