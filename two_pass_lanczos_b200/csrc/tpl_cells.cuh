@@ -108,7 +108,7 @@ struct CellSmem {  // shared-window byte addresses
   uint32_t sums;   // f64 [8 * max_slots] node sums of this cell in push order
   uint32_t n0, n1, nx, T;  // f64 [8 * max_own] owned node rows: current / previous vector, x (pass 2), node sums
   uint32_t arv;    // f64 [Gc] all-reduce values by slot
-  uint32_t wpart;  // f64 [kWarps]
+  uint32_t wpart;  // f64 [kWarps + 2]
   uint32_t walk;   // uint4 [max_groups * 32]
   uint32_t ent4;   // uint2 [max_rows * 32]
   uint32_t lines;  // u32 [max_lines]
@@ -120,7 +120,7 @@ struct CellSmem {  // shared-window byte addresses
 
 __host__ __device__ inline size_t cell_smem_bytes(const CellOp& co, bool pass2) {
   size_t dbl = 2 * (size_t)co.Amax + 8 + kLine * co.max_lines + co.max_tl + 8 + kLine * co.max_slots +
-               (size_t)kLine * co.max_own * (pass2 ? 4 : 3) + co.Gc + kWarps;
+               (size_t)kLine * co.max_own * (pass2 ? 4 : 3) + co.Gc + kWarps + 2;
   dbl = (dbl + 1) & ~(size_t)1;
   const size_t u32 = (size_t)co.max_lines + co.max_slots + 2 * (size_t)co.max_own;
   return dbl * 8 + (size_t)co.max_groups * 32 * 16 + (size_t)co.max_rows * 32 * 8 + u32 * 4 + (size_t)kLine * co.max_lines * 2 + 16 +
@@ -140,7 +140,7 @@ __device__ __forceinline__ CellSmem carve_cell(double* base, const CellOp& co) {
   s.nx = a; a += PASS2 ? kLine * co.max_own * 8 : 0;
   s.T = a; a += kLine * co.max_own * 8;
   s.arv = a; a += co.Gc * 8;
-  s.wpart = a; a += kWarps * 8;
+  s.wpart = a; a += (kWarps + 2) * 8;  // + the two scalars of the top of a pass-1 step (norm, reciprocal)
   a = (a + 15u) & ~15u;
   s.walk = a; a += co.max_groups * 32 * 16;
   s.ent4 = a; a += co.max_rows * 32 * 8;
@@ -215,6 +215,8 @@ __device__ __forceinline__ double atom_poll(const uint4* p, uint32_t tag) {
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
 __device__ __forceinline__ void bar_arrive_top() { asm volatile("bar.arrive 2, %0;" ::"n"(kBlock) : "memory"); }
 __device__ __forceinline__ void bar_wait_top() { asm volatile("bar.sync 2, %0;" ::"n"(kBlock) : "memory"); }
+// barrier 3: the warps that polled the all-reduce lines of the top of a step, among themselves
+__device__ __forceinline__ void bar_ar_warps(uint32_t threads) { asm volatile("bar.sync 3, %0;" ::"r"(threads) : "memory"); }
 
 // ----------------------------------------------------------------------------- exchange steps
 __device__ __forceinline__ double flip_sign(double v, uint32_t mask) {
@@ -506,8 +508,22 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
     // ---------------- top of the step: ||b||^2 or beta_{j-1}^2 and the node values of the current vector (workers);
     // the owner warp meanwhile waits for the node sums of its lines
     if (!owner) {
-      if (warp < ar_warps) cell_ar_poll(co, s, epoch);
-      else cell_poll_gather(co, s, c, (uint32_t)j, ar_warps, kWorkerWarps - ar_warps, 1.0);
+      if (warp < ar_warps) {
+        // the all-reduce usually completes before the node values do: the norm and its reciprocal (a sum of Gc numbers, a
+        // square root and a division -- ~500 cycles of dependent FP64) are formed by warp 0 in the shadow of the other
+        // warps' gather polls and handed over in shared memory
+        cell_ar_poll(co, s, epoch);
+        bar_ar_warps(ar_warps * 32);
+        if (warp == 0) {
+          const double root = sqrt(cell_ar_total(co, s));
+          if (lane == 0) {
+            sts_f64(s.wpart + kWarps * 8, root);
+            sts_f64(s.wpart + (kWarps + 1) * 8, 1.0 / root);
+          }
+        }
+      } else {
+        cell_poll_gather(co, s, c, (uint32_t)j, ar_warps, kWorkerWarps - ar_warps, 1.0);
+      }
       trace_mark(tr, j, 1);
       trace_mark_warp(tr, j, 32);
       bar_workers();
@@ -521,22 +537,22 @@ __global__ void __launch_bounds__(kBlock, 1) pass1_cell_kernel(const IncidenceOp
       trace_mark_warp(tr, j, 32);
       bar_wait_top();
     }
-    const double tot = cell_ar_total(co, s);
+    const double root = lds_f64(s.wpart + kWarps * 8), rinv = lds_f64(s.wpart + (kWarps + 1) * 8);
     if (j == 0) {
-      bnorm = sqrt(tot);
+      bnorm = root;
       if (bnorm <= a.tol) {
         status = ST_ZERO_B;
         break;
       }
-      sc = 1.0 / bnorm;
+      sc = rinv;
     } else {
-      const double beta = sqrt(tot);
+      const double beta = root;
       if (blockIdx.x == 0 && tid == 0) a.betas[j - 1] = beta;
       if (beta <= a.tol) {  // breakdown: stop (mod.rs:331-338)
         status = ST_BREAKDOWN;
         break;
       }
-      sc = 1.0 / beta;  // recip, then multiply (mod.rs:312)
+      sc = rinv;  // recip, then multiply (mod.rs:312)
       bp = beta;
     }
 
