@@ -481,7 +481,7 @@ int finish_setup(tpl_op* op) {
       op->smem_res2 = tpl::resident_smem_bytes(op->inc.p, A, op->G, op->res.R, op->res.max_long, true);
       int max_optin = 0;
       CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, op->device));
-      op->resident_ok = op->smem_res2 + 1024 <= (size_t)max_optin;
+      op->resident_ok = op->smem_res2 + 2048 <= (size_t)max_optin;  // + the kernels' static shared memory (CtaShared: 1.5 KB)
     }
     if (op->resident_ok) {
       if (int rc = set_smem(tpl::pass1_resident_kernel<false>, op->smem_res1)) return rc;
