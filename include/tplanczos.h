@@ -160,8 +160,8 @@ uint64_t tpl_op_device_bytes(const tpl_op* op);
  * 1 = one cooperative launch per Lanczos step (streaming kernels; what a step callback uses); 2 = persistent streaming
  * kernels with tiled node sums even when a resident shape would fit; 3 = streaming kernels with gathered node rows;
  * 4 = chunk-resident kernels even when the cell partition would fit; 5 = blocked streaming kernels (node-block partition,
- * cell-order vectors, bulk-copy input ring) even when a resident shape would fit.  In mode 0 the streaming regime prefers
- * the blocked kernels over the tiled ones.  All modes run the same per-element arithmetic;
+ * cell-order vectors, bulk-copy input ring) even when a resident shape would fit.  In mode 0 the streaming regime runs
+ * the blocked kernels from ~1 M arcs (cells of >= 6.5 k arcs) and the tiled ones below.  All modes run the same per-element arithmetic;
  * they differ in the (fixed) order in which a node row is summed, i.e. by rounding only. */
 int tpl_op_set_mode(tpl_op* op, int mode);
 /* Name of the kernel family a whole-pass solve through this handle runs: "cells", "chunks", "blocked", "tiled", "gather",
