@@ -106,3 +106,14 @@ def test_layout_of_a_shard_ignores_nodes_without_local_arcs():
     assert active_tails < 0.4 * inst.p
     assert st["PT"] <= active_tails / 12 + 8          # not p / 12 + (nodes without out-arcs)
     assert st["PH"] <= inst.p / 12 + 8
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4, 5])
+def test_the_checker_catches_deliberate_defects(kind, monkeypatch):
+    """The checker is what vouches for the device-built tables (tpl_op_layout_check): it must reject a layout with ONE
+    defect in one tile -- a flipped sign, a sum flushed to the wrong slot, a wrong chain depth, two exchanged entries,
+    a wrong slot for a slice's last node (TPL_PLAN_CORRUPT in tpl_blocks_plan)."""
+    inst = datagen.gen_kkt(40_000, 3, 3, "wc")
+    assert plan(inst.m, inst.p, inst.tail, inst.head, inst.d)["code"] == 0
+    monkeypatch.setenv("TPL_PLAN_CORRUPT", str(kind))
+    assert plan(inst.m, inst.p, inst.tail, inst.head, inst.d)["code"] != 0

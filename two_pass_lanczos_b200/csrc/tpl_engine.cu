@@ -1237,6 +1237,36 @@ int tpl_blocks_plan(size_t m, size_t p, const uint32_t* tail, const uint32_t* he
   for (uint32_t e : hb.th) hsh = (hsh ^ e) * 1099511628211ull;
   for (uint32_t e : hb.gidx) hsh = (hsh ^ e) * 1099511628211ull;
   stats[13] = hsh;
+  // TPL_PLAN_CORRUPT=<kind> (tests of the checker itself): one deliberate defect in the lists of the first non-empty tile before
+  // they are checked -- 1: the minus bit of an entry flipped, 2: the slot a node's sum is flushed to replaced by the dummy,
+  // 3: a chain depth changed, 4: two entries of one slice exchanged, 5: the slot of a slice's last node changed.
+  if (const char* e = std::getenv("TPL_PLAN_CORRUPT")) {
+    const int kind = std::atoi(e);
+    const uint32_t B = tpl::kFoldThreads, PL = hb.PT + hb.PH;
+    for (const uint4& h4 : hb.thdr) {
+      const uint32_t L = h4.y & 0xffffffu;
+      if (L < 3) continue;
+      uint32_t* blk = hb.lent.data() + h4.x;
+      if (kind == 1) {
+        blk[B * 2] ^= tpl::kBEntMinus;
+      } else if (kind == 2) {
+        bool hit = false;
+        for (size_t w = 2 * (size_t)B; w < (size_t)(L + 1) * B && !hit; ++w)  // rows 2 .. L: not the first entry of a slice
+          if (blk[w] & tpl::kBEntNew) {
+            blk[w] = (blk[w] & ~(tpl::kBEntNodeMask << tpl::kBEntNodeShift)) | (PL << tpl::kBEntNodeShift);
+            hit = true;
+          }
+        if (!hit) continue;
+      } else if (kind == 3) {
+        blk[1] = (blk[1] & ~0xffu) | (((blk[1] & 0xffu) + 1u) & 0xffu);
+      } else if (kind == 4) {
+        std::swap(blk[(size_t)1 * B], blk[(size_t)L * B]);
+      } else if (kind == 5) {
+        blk[0] = (blk[0] & 0xffu) | (((((blk[0] >> 8) & tpl::kBEntNodeMask) + 1u) % (PL + 1u)) << 8);
+      }
+      break;
+    }
+  }
   stats[14] = (uint64_t)tpl::check_blocks(m, p, tail, head, d, d_len, hb);
   stats[15] = tpl::block_smem_bytes(hb.PT + hb.PH, hb.T, (int)hb.ring2, hb.lblk, hb.nl, hb.ntb, true, false, hb.ntile);
   stats[8] |= (uint64_t)hb.nl << 24;
